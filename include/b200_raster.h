@@ -1,0 +1,159 @@
+/*
+ * b200_raster.h -- C ABI of the B200-native differentiable rasterizer (libb200raster.so).
+ *
+ * This is the drop-in boundary for PyTorch3D's native rasterizer ops.  The reference reaches its
+ * kernels through the pybind11 module pytorch3d._C (pytorch3d/csrc/ext.cpp:53-56); the four entry
+ * points below take exactly the arguments of those ops, flattened to plain pointers and sizes
+ * (no torch types), so any host language can bind them.  INTEGRATION.md shows the binding a
+ * PyTorch3D maintainer would add; pytorch3d_b200/_C.py is that binding for this repo.
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers on the current CUDA device unless the function name ends in
+ *    `_host` (then they are host pointers and the call performs the H2D/D2H copies itself);
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous and
+ *    never synchronise the host (the reference ops do not either, rasterize_meshes.cu:383-384);
+ *  - tensors are dense/contiguous in the layouts documented per argument (the reference ops call
+ *    .contiguous() themselves, rasterize_meshes.cu:802-804; the Python host does it here);
+ *  - outputs are fully written by the kernels, including the -1 padding of empty slots
+ *    (the reference pre-fills with at::full, rasterize_meshes.cu:788-791);
+ *  - return value: 0 = ok, otherwise an error code; b200r_last_error() gives the message.  Messages
+ *    for argument errors match the reference's TORCH_CHECK / AT_ERROR texts.
+ */
+#ifndef B200_RASTER_H_
+#define B200_RASTER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200R_OK 0
+#define B200R_ERR_INVALID_ARGUMENT 1
+#define B200R_ERR_CUDA 2
+#define B200R_ERR_WORKSPACE 3
+
+/* kMaxPointsPerPixel, pytorch3d/csrc/rasterize_points/rasterization_utils.cuh:48 */
+#define B200R_MAX_K 150
+
+/* Library / build identification ("b200raster <version> sm_100a"). */
+const char* b200r_version(void);
+
+/* Message of the last failing call on the calling thread ("" if none). */
+const char* b200r_last_error(void);
+
+/* ------------------------------------------------------------------ meshes ------------------ */
+
+/*
+ * Scratch bytes needed by b200r_rasterize_meshes_forward for F packed faces, N meshes and an
+ * H x W image.  pair_capacity = number of (tile, face) pairs the bin lists can hold; pass <= 0
+ * for the default (min(F * tiles_per_image, 8*F + 64*N*tiles_per_image)).  If the real number of
+ * pairs exceeds the capacity the affected tiles transparently fall back to testing every face of
+ * their mesh, so results never depend on it (the reference drops faces and prints a warning
+ * instead, rasterize_coarse.cu:186-201).
+ */
+size_t b200r_rasterize_meshes_workspace_bytes(int64_t F, int32_t N, int32_t H, int32_t W, int64_t pair_capacity);
+
+/*
+ * Replaces pytorch3d._C.rasterize_meshes
+ *   (RasterizeMeshes, pytorch3d/csrc/rasterize_meshes/rasterize_meshes.h:513-562;
+ *    call site pytorch3d/renderer/mesh/rasterize_meshes.py:297-310).
+ *
+ *  face_verts                 float32 (F,3,3)   packed faces in NDC (+X left, +Y up, z = depth)
+ *  mesh_to_face_first_idx     int64   (N,)      first packed face of each mesh (ascending)
+ *  num_faces_per_mesh         int64   (N,)
+ *  clipped_faces_neighbor_idx int64   (F,)      -1 or index of the other half of a clipped face
+ *                                               (may be NULL = all -1)
+ *  blur_radius, faces_per_pixel (K <= 150), perspective_correct, clip_barycentric_coords,
+ *  cull_backfaces             as in the reference.
+ *  bin_size, max_faces_per_bin  accepted for signature compatibility; they are performance hints
+ *                             in the reference ("should not affect the output",
+ *                             rasterize_meshes.py:73-80) and are ignored here: tiling is internal
+ *                             and exact.
+ * Outputs (all fully written):
+ *  pix_to_face int64 (N,H,W,K); zbuf float32 (N,H,W,K); bary float32 (N,H,W,K,3);
+ *  dists float32 (N,H,W,K); empty slots = -1.  For every pixel the K nearest faces are returned
+ *  in increasing (z, face index) order.
+ *  workspace: >= b200r_rasterize_meshes_workspace_bytes(...) bytes of device memory, 16B aligned.
+ */
+int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F, const int64_t* mesh_to_face_first_idx,
+                                   const int64_t* num_faces_per_mesh, const int64_t* clipped_faces_neighbor_idx,
+                                   int32_t N, int32_t H, int32_t W, float blur_radius, int32_t faces_per_pixel,
+                                   int32_t bin_size, int32_t max_faces_per_bin, int32_t perspective_correct,
+                                   int32_t clip_barycentric_coords, int32_t cull_backfaces, int64_t* pix_to_face,
+                                   float* zbuf, float* bary, float* dists, void* workspace, size_t workspace_bytes,
+                                   int64_t pair_capacity, void* stream);
+
+/*
+ * Replaces pytorch3d._C.rasterize_meshes_backward
+ *   (RasterizeMeshesBackward, rasterize_meshes.h:211-218; call site rasterize_meshes.py:334-342).
+ *  grad_face_verts float32 (F,3,3) is zeroed and accumulated by the call.
+ */
+int b200r_rasterize_meshes_backward(const float* face_verts, int64_t F, const int64_t* pix_to_face,
+                                    const float* grad_zbuf, const float* grad_bary, const float* grad_dists,
+                                    int32_t N, int32_t H, int32_t W, int32_t K, int32_t perspective_correct,
+                                    int32_t clip_barycentric_coords, float* grad_face_verts, void* stream);
+
+/* ------------------------------------------------------------------ points ------------------ */
+
+size_t b200r_rasterize_points_workspace_bytes(int64_t P, int32_t N, int32_t H, int32_t W, int64_t pair_capacity);
+
+/*
+ * Replaces pytorch3d._C.rasterize_points
+ *   (RasterizePoints, pytorch3d/csrc/rasterize_points/rasterize_points.h:343-374;
+ *    call site pytorch3d/renderer/points/rasterize_points.py:200-212).
+ *  points float32 (P,3); cloud_to_packed_first_idx / num_points_per_cloud int64 (N,);
+ *  radius float32 (P,) in NDC units; points_per_pixel K <= 150.
+ * Outputs: idx int32 (N,H,W,K); zbuf float32 (N,H,W,K); dists float32 (N,H,W,K) (squared xy distance).
+ */
+int b200r_rasterize_points_forward(const float* points, int64_t P, const int64_t* cloud_to_packed_first_idx,
+                                   const int64_t* num_points_per_cloud, const float* radius, int32_t N, int32_t H,
+                                   int32_t W, int32_t points_per_pixel, int32_t bin_size,
+                                   int32_t max_points_per_bin, int32_t* idx, float* zbuf, float* dists,
+                                   void* workspace, size_t workspace_bytes, int64_t pair_capacity, void* stream);
+
+/*
+ * Replaces pytorch3d._C.rasterize_points_backward
+ *   (RasterizePointsBackward, rasterize_points.h:281-285; call site rasterize_points.py:229-231).
+ */
+int b200r_rasterize_points_backward(const float* points, int64_t P, const int32_t* idxs, const float* grad_zbuf,
+                                    const float* grad_dists, int32_t N, int32_t H, int32_t W, int32_t K,
+                                    float* grad_points, void* stream);
+
+/* ------------------------------------------------------------------ host-buffer entry points - */
+
+/*
+ * Same operators with HOST buffers: the call stages inputs to the device (pinned staging is the
+ * caller's choice), runs the kernels and copies the results back, synchronising before returning.
+ * This is what a non-PyTorch host (cgo / JNI / ctypes) would bind, and what bench.py times as the
+ * end-to-end number.
+ */
+int b200r_rasterize_meshes_forward_host(const float* face_verts, int64_t F, const int64_t* mesh_to_face_first_idx,
+                                        const int64_t* num_faces_per_mesh,
+                                        const int64_t* clipped_faces_neighbor_idx, int32_t N, int32_t H, int32_t W,
+                                        float blur_radius, int32_t faces_per_pixel, int32_t perspective_correct,
+                                        int32_t clip_barycentric_coords, int32_t cull_backfaces,
+                                        int64_t* pix_to_face, float* zbuf, float* bary, float* dists);
+
+int b200r_rasterize_meshes_backward_host(const float* face_verts, int64_t F, const int64_t* pix_to_face,
+                                         const float* grad_zbuf, const float* grad_bary, const float* grad_dists,
+                                         int32_t N, int32_t H, int32_t W, int32_t K, int32_t perspective_correct,
+                                         int32_t clip_barycentric_coords, float* grad_face_verts);
+
+int b200r_rasterize_points_forward_host(const float* points, int64_t P, const int64_t* cloud_to_packed_first_idx,
+                                        const int64_t* num_points_per_cloud, const float* radius, int32_t N,
+                                        int32_t H, int32_t W, int32_t points_per_pixel, int32_t* idx, float* zbuf,
+                                        float* dists);
+
+int b200r_rasterize_points_backward_host(const float* points, int64_t P, const int32_t* idxs,
+                                         const float* grad_zbuf, const float* grad_dists, int32_t N, int32_t H,
+                                         int32_t W, int32_t K, float* grad_points);
+
+/* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+int64_t b200r_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_RASTER_H_ */

@@ -1,0 +1,210 @@
+"""Operator-level drop-in for the rasterizer part of `pytorch3d._C`.
+
+Same names, positional arguments, return values and error behaviour as the pybind11 ops registered
+in pytorch3d/csrc/ext.cpp:53-56:
+
+    rasterize_meshes, rasterize_meshes_backward, rasterize_points, rasterize_points_backward
+
+implemented by calling the C ABI of libb200raster.so (include/b200_raster.h) on the tensors' device
+pointers and the current CUDA stream.  PyTorch is used only for device memory and streams.
+There is no CPU path: CPU tensors raise RuntimeError, like a CUDA-less build of the reference does
+for CUDA tensors (rasterize_meshes.h:137-139, mirrored).
+"""
+from typing import Tuple
+
+import torch
+
+from . import _lib
+
+kMaxPointsPerPixel = 150  # rasterization_utils.cuh:48
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None and t.numel() > 0 else None
+
+
+def _require_cuda(*named):
+    dev = None
+    for name, t in named:
+        if not t.is_cuda:
+            raise RuntimeError(
+                "%s must be a CUDA tensor: pytorch3d_b200 is a B200-native (sm_100a) rasterizer and has "
+                "no CPU implementation." % name)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(
+                "Expected all tensors to be on the same device (%s is on %s, expected %s)" % (name, t.device, dev))
+    return dev
+
+
+def _stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def rasterize_meshes(
+    face_verts: torch.Tensor,
+    mesh_to_face_first_idx: torch.Tensor,
+    num_faces_per_mesh: torch.Tensor,
+    clipped_faces_neighbor_idx: torch.Tensor,
+    image_size: Tuple[int, int],
+    blur_radius: float,
+    faces_per_pixel: int,
+    bin_size: int,
+    max_faces_per_bin: int,
+    perspective_correct: bool,
+    clip_barycentric_coords: bool,
+    cull_backfaces: bool,
+):
+    """pytorch3d._C.rasterize_meshes (RasterizeMeshes, rasterize_meshes.h:513-562)."""
+    if face_verts.dim() != 3 or face_verts.shape[1] != 3 or face_verts.shape[2] != 3:
+        raise RuntimeError("face_verts must have dimensions (num_faces, 3, 3)")
+    if num_faces_per_mesh.shape[0] != mesh_to_face_first_idx.shape[0]:
+        raise RuntimeError(
+            "num_faces_per_mesh must have save size first dimension as mesh_to_faces_packed_first_idx")
+    if clipped_faces_neighbor_idx.shape[0] != face_verts.shape[0]:
+        raise RuntimeError("clipped_faces_neighbor_idx must have save size first dimension as face_verts")
+    if faces_per_pixel > kMaxPointsPerPixel:
+        raise RuntimeError("Must have points_per_pixel <= %d" % kMaxPointsPerPixel)
+    if face_verts.dtype != torch.float32:
+        raise RuntimeError("expected scalar type Float but found %s" % face_verts.dtype)
+    dev = _require_cuda(("face_verts", face_verts), ("mesh_to_faces_packed_first_idx", mesh_to_face_first_idx),
+                        ("num_faces_per_mesh", num_faces_per_mesh),
+                        ("clipped_faces_neighbor_idx", clipped_faces_neighbor_idx))
+    lib = _lib.load()
+    H, W = int(image_size[0]), int(image_size[1])
+    K = int(faces_per_pixel)
+    N, F = int(num_faces_per_mesh.shape[0]), int(face_verts.shape[0])
+    fv = face_verts.contiguous()
+    first = mesh_to_face_first_idx.contiguous().to(torch.int64)
+    num = num_faces_per_mesh.contiguous().to(torch.int64)
+    # Clipped-face neighbours (only produced by clip_faces) select the exact ordered path.
+    nb = None
+    if (F > 0 and not getattr(clipped_faces_neighbor_idx, "_b200_all_minus_one", False)
+            and bool((clipped_faces_neighbor_idx != -1).any())):
+        nb = clipped_faces_neighbor_idx.contiguous().to(torch.int64)
+    with torch.cuda.device(dev):
+        pix_to_face = torch.empty((N, H, W, K), dtype=torch.int64, device=dev)
+        zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
+        dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        if pix_to_face.numel() == 0:
+            return pix_to_face, zbuf, bary, dists
+        ws_bytes = lib.b200r_rasterize_meshes_workspace_bytes(F, N, H, W, 0)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        _lib.check(lib.b200r_rasterize_meshes_forward(
+            _ptr(fv), F, _ptr(first), _ptr(num), _ptr(nb), N, H, W, float(blur_radius), K, int(bin_size),
+            int(max_faces_per_bin), int(bool(perspective_correct)), int(bool(clip_barycentric_coords)),
+            int(bool(cull_backfaces)), _ptr(pix_to_face), _ptr(zbuf), _ptr(bary), _ptr(dists), _ptr(ws),
+            ws_bytes, 0, _stream_ptr(dev)))
+        # the workspace is only read by kernels already enqueued on this stream
+        ws.record_stream(torch.cuda.current_stream(dev))
+    return pix_to_face, zbuf, bary, dists
+
+
+def rasterize_meshes_backward(
+    face_verts: torch.Tensor,
+    pix_to_face: torch.Tensor,
+    grad_zbuf: torch.Tensor,
+    grad_bary: torch.Tensor,
+    grad_dists: torch.Tensor,
+    perspective_correct: bool,
+    clip_barycentric_coords: bool,
+):
+    """pytorch3d._C.rasterize_meshes_backward (RasterizeMeshesBackward, rasterize_meshes.h:211-218)."""
+    dev = _require_cuda(("face_verts", face_verts), ("pix_to_face", pix_to_face), ("grad_zbuf", grad_zbuf),
+                        ("grad_bary", grad_bary), ("grad_dists", grad_dists))
+    for name, t in (("face_verts", face_verts), ("grad_zbuf", grad_zbuf), ("grad_bary", grad_bary),
+                    ("grad_dists", grad_dists)):
+        if t.dtype != torch.float32:
+            raise RuntimeError("Expected tensor for %s to have scalar type Float; but got %s" % (name, t.dtype))
+    # same non-determinism contract as the reference (rasterize_meshes.cu:587)
+    if torch.are_deterministic_algorithms_enabled() and not torch.is_deterministic_algorithms_warn_only_enabled():
+        raise RuntimeError(
+            "RasterizeMeshesBackwardCuda does not have a deterministic implementation, but you set "
+            "'torch.use_deterministic_algorithms(True)'.")
+    lib = _lib.load()
+    N, H, W, K = (int(s) for s in pix_to_face.shape)
+    F = int(face_verts.shape[0])
+    fv = face_verts.contiguous()
+    p2f = pix_to_face.contiguous()
+    gz, gb, gd = grad_zbuf.contiguous(), grad_bary.contiguous(), grad_dists.contiguous()
+    with torch.cuda.device(dev):
+        grad_face_verts = torch.empty((F, 3, 3), dtype=torch.float32, device=dev)
+        if F == 0:
+            return grad_face_verts
+        _lib.check(lib.b200r_rasterize_meshes_backward(
+            _ptr(fv), F, _ptr(p2f), _ptr(gz), _ptr(gb), _ptr(gd), N, H, W, K, int(bool(perspective_correct)),
+            int(bool(clip_barycentric_coords)), _ptr(grad_face_verts), _stream_ptr(dev)))
+    return grad_face_verts
+
+
+def rasterize_points(
+    points: torch.Tensor,
+    cloud_to_packed_first_idx: torch.Tensor,
+    num_points_per_cloud: torch.Tensor,
+    image_size: Tuple[int, int],
+    radius: torch.Tensor,
+    points_per_pixel: int,
+    bin_size: int,
+    max_points_per_bin: int,
+):
+    """pytorch3d._C.rasterize_points (RasterizePoints, rasterize_points.h:343-374)."""
+    if points.dim() != 2 or points.shape[1] != 3:
+        raise RuntimeError("points must have dimensions (num_points, 3)")
+    if num_points_per_cloud.shape[0] != cloud_to_packed_first_idx.shape[0]:
+        raise RuntimeError(
+            "num_points_per_cloud must have same size first dimension as cloud_to_packed_first_idx")
+    if radius.dim() != 1 or radius.shape[0] != points.shape[0]:
+        raise RuntimeError("radius must be of shape (P,)")
+    if points_per_pixel > kMaxPointsPerPixel:
+        raise RuntimeError("Must have num_closest <= %d" % kMaxPointsPerPixel)
+    if points.dtype != torch.float32 or radius.dtype != torch.float32:
+        raise RuntimeError("expected scalar type Float")
+    dev = _require_cuda(("points", points), ("cloud_to_packed_first_idx", cloud_to_packed_first_idx),
+                        ("num_points_per_cloud", num_points_per_cloud), ("radius", radius))
+    lib = _lib.load()
+    H, W = int(image_size[0]), int(image_size[1])
+    K = int(points_per_pixel)
+    N, P = int(num_points_per_cloud.shape[0]), int(points.shape[0])
+    pts = points.contiguous()
+    first = cloud_to_packed_first_idx.contiguous().to(torch.int64)
+    num = num_points_per_cloud.contiguous().to(torch.int64)
+    rad = radius.contiguous()
+    with torch.cuda.device(dev):
+        idx = torch.empty((N, H, W, K), dtype=torch.int32, device=dev)
+        zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        if idx.numel() == 0:
+            return idx, zbuf, dists
+        ws_bytes = lib.b200r_rasterize_points_workspace_bytes(P, N, H, W, 0)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        _lib.check(lib.b200r_rasterize_points_forward(
+            _ptr(pts), P, _ptr(first), _ptr(num), _ptr(rad), N, H, W, K, int(bin_size), int(max_points_per_bin),
+            _ptr(idx), _ptr(zbuf), _ptr(dists), _ptr(ws), ws_bytes, 0, _stream_ptr(dev)))
+        ws.record_stream(torch.cuda.current_stream(dev))
+    return idx, zbuf, dists
+
+
+def rasterize_points_backward(points: torch.Tensor, idxs: torch.Tensor, grad_zbuf: torch.Tensor,
+                              grad_dists: torch.Tensor):
+    """pytorch3d._C.rasterize_points_backward (RasterizePointsBackward, rasterize_points.h:281-285)."""
+    dev = _require_cuda(("points", points), ("idxs", idxs), ("grad_zbuf", grad_zbuf), ("grad_dists", grad_dists))
+    if idxs.dtype != torch.int32:
+        raise RuntimeError("expected scalar type Int but found %s" % idxs.dtype)
+    if torch.are_deterministic_algorithms_enabled() and not torch.is_deterministic_algorithms_warn_only_enabled():
+        raise RuntimeError(
+            "RasterizePointsBackwardCuda does not have a deterministic implementation, but you set "
+            "'torch.use_deterministic_algorithms(True)'.")
+    lib = _lib.load()
+    N, H, W, K = (int(s) for s in idxs.shape)
+    P = int(points.shape[0])
+    pts, idx = points.contiguous(), idxs.contiguous()
+    gz, gd = grad_zbuf.contiguous(), grad_dists.contiguous()
+    with torch.cuda.device(dev):
+        grad_points = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        if P == 0:
+            return grad_points
+        _lib.check(lib.b200r_rasterize_points_backward(
+            _ptr(pts), P, _ptr(idx), _ptr(gz), _ptr(gd), N, H, W, K, _ptr(grad_points), _stream_ptr(dev)))
+    return grad_points

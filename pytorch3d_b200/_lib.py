@@ -1,0 +1,73 @@
+"""ctypes loader of libb200raster.so -- the C-ABI boundary (include/b200_raster.h).
+
+There is no CPU or PyTorch fallback: if the CUDA library is missing the import of the ops
+fails loudly with the build command to run.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libb200raster.so")
+
+_c_f = ctypes.POINTER(ctypes.c_float)
+_vp = ctypes.c_void_p
+_i32, _i64, _f32, _sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/b200_raster.h one to one.
+SIGNATURES = {
+    "b200r_version": (ctypes.c_char_p, []),
+    "b200r_last_error": (ctypes.c_char_p, []),
+    "b200r_kernel_launch_count": (_i64, []),
+    "b200r_rasterize_meshes_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i64]),
+    "b200r_rasterize_meshes_forward": (
+        ctypes.c_int,
+        [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _i32, _i32, _i32, _i32,
+         _vp, _vp, _vp, _vp, _vp, _sz, _i64, _vp]),
+    "b200r_rasterize_meshes_backward": (
+        ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "b200r_rasterize_points_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i64]),
+    "b200r_rasterize_points_forward": (
+        ctypes.c_int,
+        [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _i64, _vp]),
+    "b200r_rasterize_points_backward": (
+        ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "b200r_rasterize_meshes_forward_host": (
+        ctypes.c_int,
+        [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "b200r_rasterize_meshes_backward_host": (
+        ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b200r_rasterize_points_forward_host": (
+        ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "b200r_rasterize_points_backward_host": (
+        ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes handle with typed prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "pytorch3d_b200: %s is missing. Build it with `python -m pytorch3d_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().b200r_last_error().decode()
+
+
+def check(rc):
+    """Turn a C-ABI status into the exception the reference op would raise (RuntimeError)."""
+    if rc != 0:
+        raise RuntimeError(last_error() or ("libb200raster error %d" % rc))

@@ -1,0 +1,48 @@
+"""Builds pytorch3d_b200/lib/libb200raster.so (hand-written sm_100a kernels + C ABI) with nvcc.
+
+nvcc cross-compiles without a GPU; the built .so is git-ignored but travels to the GPU box.
+Usage: python -m pytorch3d_b200.build [--force] [--verbose]
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIB_DIR, "libb200raster.so")
+SOURCES = ["raster_meshes.cu", "raster_points.cu", "host_api.cu"]
+HEADERS = ["raster_math.cuh", "bulk_copy.cuh", "binning.cuh", "common.cuh", os.path.join("..", "..", "include", "b200_raster.h")]
+
+
+def _nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    if not force and not is_stale():
+        return LIB
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [_nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+           "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(os.path.join(LIB_DIR, "build.log"), "w") as fh:
+        fh.write(" ".join(cmd) + "\n" + res.stdout)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libb200raster.so (see output above)")
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print("built", LIB)

@@ -1,0 +1,161 @@
+// Exact two-pass tile binning shared by the mesh and point rasterizers.
+//
+// Role of the reference's coarse stage (pytorch3d/csrc/rasterize_coarse/rasterize_coarse.cu:76-219),
+// redesigned: instead of a dense (N, BH, BW, M) table pre-filled with -1 and a brute-force
+// element x bin overlap test, every element (face / point) computes the exact range of pixel
+// centres its bounding box can cover, converts it to a rectangle of 16x16-pixel tiles, and
+//   pass 1 (setup+count)  atomically counts elements per tile,
+//   pass 2 (scan)         exclusive-scans the counts into segment offsets,
+//   pass 3 (fill)         writes element ids into each tile's compact segment.
+// No M cap, no overflow drop, no -1 fill; elements whose box contains no pixel centre (most
+// sub-pixel triangles) are never binned at all.
+#pragma once
+#include "common.cuh"
+#include "raster_math.cuh"
+
+namespace b200r {
+
+constexpr uint32_t RECT_EMPTY_X = 0x0000FFFFu;  // tx0 = 0xFFFF > tx1 = 0
+
+// Smallest pixel index i in [0, S] whose centre satisfies pix(i) >= v (S if none).
+__device__ __forceinline__ int first_pix_ge(float v, int S, float range) {
+  const float off = range * 0.5f;
+  float est = (v + off) * (float)S / range - 0.5f;
+  est = fminf(fmaxf(est, -1.0f), (float)S + 1.0f);  // also maps NaN to -1
+  int i = (int)ceilf(est);
+  i = max(0, min(S, i));
+  while (i > 0 && pix_to_ndc(i - 1, S, range) >= v) --i;
+  while (i < S && pix_to_ndc(i, S, range) < v) ++i;
+  return i;
+}
+
+// Largest pixel index i in [-1, S-1] whose centre satisfies pix(i) <= v (-1 if none).
+__device__ __forceinline__ int last_pix_le(float v, int S, float range) {
+  const float off = range * 0.5f;
+  float est = (v + off) * (float)S / range - 0.5f;
+  est = fminf(fmaxf(est, -2.0f), (float)S);
+  int i = (int)floorf(est);
+  i = max(-1, min(S - 1, i));
+  while (i < S - 1 && pix_to_ndc(i + 1, S, range) <= v) ++i;
+  while (i >= 0 && pix_to_ndc(i, S, range) > v) --i;
+  return i;
+}
+
+// Tile rectangle (in OUTPUT pixel coordinates: xo = W-1-xi, yo = H-1-yi) of the pixels whose centres
+// lie inside [xmin,xmax] x [ymin,ymax] (closed, exactly the reference's per-pixel box test
+// `px > xmax || px < xmin || py > ymax || py < ymin`, rasterize_meshes.cu:94-97).
+__device__ __forceinline__ uint2 bbox_to_tile_rect(float xmin, float xmax, float ymin, float ymax, int H, int W,
+                                                   float rx, float ry) {
+  const int ix_lo = first_pix_ge(xmin, W, rx), ix_hi = last_pix_le(xmax, W, rx);
+  const int iy_lo = first_pix_ge(ymin, H, ry), iy_hi = last_pix_le(ymax, H, ry);
+  if (ix_lo > ix_hi || iy_lo > iy_hi) return make_uint2(RECT_EMPTY_X, 0u);
+  const uint32_t tx0 = (uint32_t)(W - 1 - ix_hi) / TILE, tx1 = (uint32_t)(W - 1 - ix_lo) / TILE;
+  const uint32_t ty0 = (uint32_t)(H - 1 - iy_hi) / TILE, ty1 = (uint32_t)(H - 1 - iy_lo) / TILE;
+  return make_uint2(tx0 | (tx1 << 16), ty0 | (ty1 << 16));
+}
+
+__device__ __forceinline__ bool rect_empty(uint2 r) { return (r.x & 0xFFFFu) > (r.x >> 16); }
+
+__device__ __forceinline__ void count_rect(uint2 r, int n, int TY, int TX, int* __restrict__ tile_count) {
+  const int tx0 = r.x & 0xFFFF, tx1 = r.x >> 16, ty0 = r.y & 0xFFFF, ty1 = r.y >> 16;
+  for (int ty = ty0; ty <= ty1; ++ty)
+    for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(tile_count + (n * TY + ty) * TX + tx, 1);
+}
+
+// Exclusive scan of `counts[0..n)` into `offsets[0..n]` by one CTA; zeroes `counts` (they become the
+// fill cursors).
+static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict__ counts, int* __restrict__ offsets, int n) {
+  __shared__ int warp_sums[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int per = (n + 1023) / 1024;
+  const int b = min(n, tid * per), e = min(n, b + per);
+  int s = 0;
+  for (int i = b; i < e; ++i) s += counts[i];
+  int inc = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = warp_sums[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += t;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  int run = inc - s + (wid > 0 ? warp_sums[wid - 1] : 0);
+  for (int i = b; i < e; ++i) {
+    const int c = counts[i];
+    offsets[i] = run;
+    run += c;
+    counts[i] = 0;
+  }
+  if (tid == 1023) offsets[n] = warp_sums[31];
+}
+
+// Pass 3: scatter element ids into the tile segments.
+static __global__ void __launch_bounds__(256)
+    tile_fill_kernel(const uint2* __restrict__ rect, int64_t E, const int64_t* __restrict__ first,
+                     const int64_t* __restrict__ num, int N, int TY, int TX, const int* __restrict__ offsets,
+                     int* __restrict__ cursor, int* __restrict__ pairs, int64_t capacity) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const uint2 r = rect[e];
+  if (rect_empty(r)) return;
+  const int n = find_owner(first, num, N, e);
+  if (n < 0) return;
+  const int tx0 = r.x & 0xFFFF, tx1 = r.x >> 16, ty0 = r.y & 0xFFFF, ty1 = r.y >> 16;
+  for (int ty = ty0; ty <= ty1; ++ty)
+    for (int tx = tx0; tx <= tx1; ++tx) {
+      const int t = (n * TY + ty) * TX + tx;
+      const int64_t pos = (int64_t)offsets[t] + atomicAdd(cursor + t, 1);
+      if (pos < capacity) pairs[pos] = (int)e;
+    }
+}
+
+// Workspace carving (all int32 / uint2 arrays, 16B-aligned sections).
+struct BinWorkspace {
+  int* tile_count;  // [ntiles]   counts, then fill cursors
+  int* tile_offset; // [ntiles+1] exclusive offsets; [ntiles] = total pairs
+  uint2* rect;      // [E]
+  int* pairs;       // [capacity]
+  int64_t capacity;
+  size_t bytes;
+};
+
+inline int64_t default_pair_capacity(int64_t E, int N, int H, int W) {
+  const int64_t tiles = (int64_t)div_up(H, TILE) * div_up(W, TILE);
+  const int64_t exact = E * tiles;
+  const int64_t heur = 8 * E + 64 * (int64_t)N * tiles;
+  int64_t c = exact < heur ? exact : heur;
+  if (c < 16) c = 16;
+  if (c > 0x7fffffff) c = 0x7fffffff;  // positions are int32
+  return c;
+}
+
+inline BinWorkspace carve_workspace(void* base, int64_t E, int N, int H, int W, int64_t capacity) {
+  BinWorkspace ws;
+  const int64_t ntiles = (int64_t)N * div_up(H, TILE) * div_up(W, TILE);
+  if (capacity <= 0) capacity = default_pair_capacity(E, N, H, W);
+  ws.capacity = capacity;
+  size_t off = 0;
+  char* p = static_cast<char*>(base);
+  ws.tile_count = reinterpret_cast<int*>(p + off);
+  off = align_up(off + sizeof(int) * (size_t)ntiles, 16);
+  ws.tile_offset = reinterpret_cast<int*>(p + off);
+  off = align_up(off + sizeof(int) * (size_t)(ntiles + 1), 16);
+  ws.rect = reinterpret_cast<uint2*>(p + off);
+  off = align_up(off + sizeof(uint2) * (size_t)(E > 0 ? E : 1), 16);
+  ws.pairs = reinterpret_cast<int*>(p + off);
+  off = align_up(off + sizeof(int) * (size_t)capacity, 16);
+  ws.bytes = off;
+  return ws;
+}
+
+}  // namespace b200r

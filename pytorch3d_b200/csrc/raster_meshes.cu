@@ -1,0 +1,638 @@
+// Mesh rasterizer for sm_100a: setup/bin pass, per-tile fine pass (top-K per pixel), backward.
+//
+// Replaces, behind the same operator signature, the reference's
+//   TriangleBoundingBoxKernel + RasterizeCoarseCudaKernel   (rasterize_coarse.cu:20-51, 76-219)
+//   RasterizeMeshesFineCudaKernel / RasterizeMeshesNaiveCudaKernel (rasterize_meshes.cu:630-736, 245-334)
+//   RasterizeMeshesBackwardCudaKernel                        (rasterize_meshes.cu:433-564)
+// Design: exact tile binning (binning.cuh) -> one CTA per 16x16 pixel tile; the tile's
+// faces are staged once per CTA into shared memory as float4 records with the per-face constants
+// (blur-expanded box, barycentric denominator) precomputed; each warp owns an 8x4 pixel footprint,
+// culls 32 faces at a time against it (one face per lane + ballot) and only then runs the exact
+// per-pixel arithmetic of raster_math.cuh; the K nearest hits live in registers, sorted by (z, face).
+#include <cfloat>
+#include <climits>
+
+#include "binning.cuh"
+#include "bulk_copy.cuh"
+#include "common.cuh"
+#include "raster_math.cuh"
+
+namespace b200r {
+
+constexpr int SETUP_FACES = 256;  // faces per CTA in the setup pass (one per thread)
+constexpr int CHUNK = 256;        // faces staged per round in the fine pass
+
+// ------------------------------------------------------------------------------------------------
+// Pass 1: per-face validity + blur-expanded box -> tile rectangle, count per tile.
+// The CTA's 256 faces (9216 contiguous bytes of the packed (F,3,3) array) arrive by one TMA bulk copy.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool face_is_drawable(const Face& f, bool cull_backfaces) {
+  const float zmax = fmaxf(fmaxf(f.z0, f.z1), f.z2), zmin = fminf(fminf(f.z0, f.z1), f.z2);
+  if (!(zmax >= 0.0f)) return false;           // behind the camera            (rasterize_meshes.cu:138,147)
+  if ((double)zmin < kEps) return false;       // z_invalid (double compare)   (:92)
+  const float area = edge_fn(f.x0, f.y0, f.x1, f.y1, f.x2, f.y2);  // EdgeFunctionForward(v0, v1, v2) (:141)
+  if (cull_backfaces && area < 0.0f) return false;                  // (:143,147)
+  if ((double)fabsf(area) <= kEps) return false;                    // zero_face_area (:144-145)
+  return true;
+}
+
+__device__ __forceinline__ void face_box(const Face& f, float sqrt_blur, float& xmin, float& xmax, float& ymin,
+                                         float& ymax) {
+  xmin = fsub(fminf(fminf(f.x0, f.x1), f.x2), sqrt_blur);  // (:85-88)
+  xmax = fadd(fmaxf(fmaxf(f.x0, f.x1), f.x2), sqrt_blur);
+  ymin = fsub(fminf(fminf(f.y0, f.y1), f.y2), sqrt_blur);
+  ymax = fadd(fmaxf(fmaxf(f.y0, f.y1), f.y2), sqrt_blur);
+}
+
+__global__ void __launch_bounds__(SETUP_FACES)
+    mesh_setup_count_kernel(const float* __restrict__ face_verts, int64_t F, const int64_t* __restrict__ first,
+                            const int64_t* __restrict__ num, int N, int H, int W, int TY, int TX, float rx,
+                            float ry, float sqrt_blur, int cull_backfaces, uint2* __restrict__ rect,
+                            int* __restrict__ tile_count) {
+  __shared__ __align__(16) float s_fv[SETUP_FACES * 9];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
+  const int64_t f0 = (int64_t)blockIdx.x * SETUP_FACES;
+  const int nf = (int)min((int64_t)SETUP_FACES, F - f0);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  cta_load_words(s_fv, face_verts + f0 * 9, nf * 9, &bar, 0);
+  if (tid >= nf) return;
+  const float* v = s_fv + tid * 9;  // stride 9 words: conflict-free across a warp
+  const Face f = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]};
+  const int64_t fi = f0 + tid;
+  uint2 r = make_uint2(RECT_EMPTY_X, 0u);
+  const int n = find_owner(first, num, N, fi);
+  if (n >= 0 && face_is_drawable(f, cull_backfaces != 0)) {
+    float xmin, xmax, ymin, ymax;
+    face_box(f, sqrt_blur, xmin, xmax, ymin, ymax);
+    r = bbox_to_tile_rect(xmin, xmax, ymin, ymax, H, W, rx, ry);
+    if (!rect_empty(r)) count_rect(r, n, TY, TX, tile_count);
+  }
+  rect[fi] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-(pixel, face) evaluation: the arithmetic of CheckPixelInsideFace (rasterize_meshes.cu:152-177).
+// ------------------------------------------------------------------------------------------------
+struct Hit {
+  float z, dist, b0, b1, b2;
+};
+
+__device__ __forceinline__ bool eval_pixel_face(float px, float py, const Face& f, float den, float blur_radius,
+                                                bool persp, bool clip, Hit& h) {
+  float w0, w1, w2;
+  bary_coords(px, py, f, den, w0, w1, w2);
+  if (persp) bary_persp(w0, w1, w2, f.z0, f.z1, f.z2);
+  float c0 = w0, c1 = w1, c2 = w2;
+  if (clip) bary_clip(c0, c1, c2);
+  const float pz = ffma(f.z2, c2, ffma(f.z0, c0, fmul(f.z1, c1)));
+  if (!(pz >= 0.0f)) return false;  // behind the image plane (:163)
+  const bool inside = w0 > 0.0f && w1 > 0.0f && w2 > 0.0f;
+  if (!inside && !(blur_radius > 0.0f)) return false;  // dist >= 0 >= blur_radius always rejects (:175)
+  const float dist = point_tri_dist(px, py, f);
+  if (!inside && dist >= blur_radius) return false;
+  h.z = pz;
+  h.dist = inside ? -dist : dist;
+  h.b0 = c0;
+  h.b1 = c1;
+  h.b2 = c2;
+  return true;
+}
+
+__device__ __forceinline__ bool key_less(float za, int ia, float zb, int ib) {
+  return za < zb || (za == zb && ia < ib);
+}
+
+// K nearest hits of one pixel, kept sorted by (z, face index) in registers (all indices static).
+template <int KMAX>
+struct TopK {
+  float z[KMAX];
+  int id[KMAX];
+  float d[KMAX], b0[KMAX], b1[KMAX], b2[KMAX];
+
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+      z[i] = FLT_MAX;
+      id[i] = INT_MAX;
+      d[i] = b0[i] = b1[i] = b2[i] = -1.0f;
+    }
+  }
+  __device__ __forceinline__ bool accepts(float pz, int f) const {
+    return key_less(pz, f, z[KMAX - 1], id[KMAX - 1]);
+  }
+  __device__ __forceinline__ void insert(const Hit& h, int f) {
+    bool c[KMAX];
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) c[i] = key_less(h.z, f, z[i], id[i]);
+#pragma unroll
+    for (int i = KMAX - 1; i >= 0; --i) {
+      const bool up = i > 0 && c[i > 0 ? i - 1 : 0];
+      const int j = i > 0 ? i - 1 : 0;
+      z[i] = up ? z[j] : (c[i] ? h.z : z[i]);
+      id[i] = up ? id[j] : (c[i] ? f : id[i]);
+      d[i] = up ? d[j] : (c[i] ? h.dist : d[i]);
+      b0[i] = up ? b0[j] : (c[i] ? h.b0 : b0[i]);
+      b1[i] = up ? b1[j] : (c[i] ? h.b1 : b1[i]);
+      b2[i] = up ? b2[j] : (c[i] ? h.b2 : b2[i]);
+    }
+  }
+};
+
+// Shared-memory face records of one staged chunk.
+struct __align__(16) FaceChunk {
+  float4 box[CHUNK];  // xmin, xmax, ymin, ymax (blur-expanded; empty box = never hit)
+  float4 a[CHUNK];    // x0, y0, x1, y1
+  float4 b[CHUNK];    // x2, y2, den, face index (int bits)
+  float4 c[CHUNK];    // z0, z1, z2, -
+};
+
+__device__ __forceinline__ void stage_face(FaceChunk& s, int slot, const float* __restrict__ face_verts, int f,
+                                           float sqrt_blur, bool cull_backfaces) {
+  const float* v = face_verts + (int64_t)f * 9;
+  const Face fc = {__ldg(v + 0), __ldg(v + 1), __ldg(v + 2), __ldg(v + 3), __ldg(v + 4),
+                   __ldg(v + 5), __ldg(v + 6), __ldg(v + 7), __ldg(v + 8)};
+  float xmin = FLT_MAX, xmax = -FLT_MAX, ymin = FLT_MAX, ymax = -FLT_MAX;
+  if (face_is_drawable(fc, cull_backfaces)) face_box(fc, sqrt_blur, xmin, xmax, ymin, ymax);
+  s.box[slot] = make_float4(xmin, xmax, ymin, ymax);
+  s.a[slot] = make_float4(fc.x0, fc.y0, fc.x1, fc.y1);
+  s.b[slot] = make_float4(fc.x2, fc.y2, bary_denominator(fc), __int_as_float(f));
+  s.c[slot] = make_float4(fc.z0, fc.z1, fc.z2, 0.0f);
+}
+
+struct FineParams {
+  const float* face_verts;
+  const int64_t* first;
+  const int64_t* num;
+  const int* tile_offset;
+  const int* pairs;
+  int64_t capacity;
+  int N, H, W, K, TY, TX;
+  float rx, ry, blur_radius, sqrt_blur;
+  int persp, clip, cull;
+  int64_t* pix_to_face;
+  float* zbuf;
+  float* bary;
+  float* dists;
+};
+
+// Pixel owned by this thread: warp w covers an 8 (x) by 4 (y) footprint of the 16x16 tile.
+__device__ __forceinline__ void thread_pixel(int tile_x, int tile_y, int& xo, int& yo) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  xo = tile_x * TILE + (w & 1) * 8 + (lane & 7);
+  yo = tile_y * TILE + (w >> 1) * 4 + (lane >> 3);
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParams p) {
+  __shared__ FaceChunk s;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int t = blockIdx.x;
+  const int n = t / (p.TY * p.TX);
+  const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
+
+  int xo, yo;
+  thread_pixel(tile_x, tile_y, xo, yo);
+  const bool valid = xo < p.W && yo < p.H;
+  const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
+  const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
+  // NDC extent of the warp's valid pixel centres (empty if the footprint is outside the image)
+  const float fx_lo = warp_min(valid ? px : FLT_MAX), fx_hi = warp_max(valid ? px : -FLT_MAX);
+  const float fy_lo = warp_min(valid ? py : FLT_MAX), fy_hi = warp_max(valid ? py : -FLT_MAX);
+
+  // the tile's face list; tiles whose segment did not fit the pair buffer test every face of the mesh
+  const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
+  const bool overflow = (int64_t)seg_end > p.capacity;
+  const int64_t mesh_first = p.first[n];
+  const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
+
+  TopK<KMAX> q;
+  q.init();
+  const bool persp = p.persp != 0, clip = p.clip != 0, cull = p.cull != 0;
+
+  for (int base = 0; base < count; base += CHUNK) {
+    const int nc = min(CHUNK, count - base);
+    __syncthreads();  // previous chunk fully consumed
+    if (tid < nc) {
+      const int f = overflow ? (int)(mesh_first + base + tid) : p.pairs[seg_begin + base + tid];
+      stage_face(s, tid, p.face_verts, f, p.sqrt_blur, cull);
+    }
+    __syncthreads();
+    for (int g = 0; g < nc; g += 32) {
+      // cull 32 faces against the warp footprint: one face per lane
+      bool touch = false;
+      if (g + lane < nc) {
+        const float4 bx = s.box[g + lane];
+        touch = !(fx_lo > bx.y || fx_hi < bx.x || fy_lo > bx.w || fy_hi < bx.z);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, touch);
+      while (m) {
+        const int j = g + __ffs(m) - 1;
+        m &= m - 1;
+        const float4 bx = s.box[j];
+        if (px > bx.y || px < bx.x || py > bx.w || py < bx.z) continue;  // (:94-97)
+        const float4 fa = s.a[j], fb = s.b[j], fc = s.c[j];
+        const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
+        Hit h;
+        if (!eval_pixel_face(px, py, f, fb.z, p.blur_radius, persp, clip, h)) continue;
+        const int fi = __float_as_int(fb.w);
+        if (q.accepts(h.z, fi)) q.insert(h, fi);
+      }
+    }
+  }
+
+  if (!valid) return;
+  const int K = p.K;
+  const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
+  if (K == KMAX && (KMAX % 4) == 0) {
+    longlong2* pf = reinterpret_cast<longlong2*>(p.pix_to_face + o);
+    float4* pz = reinterpret_cast<float4*>(p.zbuf + o);
+    float4* pd = reinterpret_cast<float4*>(p.dists + o);
+    float4* pb = reinterpret_cast<float4*>(p.bary + o * 3);
+#pragma unroll
+    for (int k = 0; k < KMAX; k += 2) {
+      const long long i0 = q.id[k] == INT_MAX ? -1ll : (long long)q.id[k];
+      const long long i1 = q.id[k + 1] == INT_MAX ? -1ll : (long long)q.id[k + 1];
+      pf[k / 2] = make_longlong2(i0, i1);
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; k += 4) {
+      pz[k / 4] = make_float4(q.id[k] == INT_MAX ? -1.0f : q.z[k], q.id[k + 1] == INT_MAX ? -1.0f : q.z[k + 1],
+                              q.id[k + 2] == INT_MAX ? -1.0f : q.z[k + 2], q.id[k + 3] == INT_MAX ? -1.0f : q.z[k + 3]);
+      pd[k / 4] = make_float4(q.d[k], q.d[k + 1], q.d[k + 2], q.d[k + 3]);
+      pb[3 * (k / 4) + 0] = make_float4(q.b0[k], q.b1[k], q.b2[k], q.b0[k + 1]);
+      pb[3 * (k / 4) + 1] = make_float4(q.b1[k + 1], q.b2[k + 1], q.b0[k + 2], q.b1[k + 2]);
+      pb[3 * (k / 4) + 2] = make_float4(q.b2[k + 2], q.b0[k + 3], q.b1[k + 3], q.b2[k + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < K) {
+        const bool e = q.id[k] == INT_MAX;
+        p.pix_to_face[o + k] = e ? -1ll : (long long)q.id[k];
+        p.zbuf[o + k] = e ? -1.0f : q.z[k];
+        p.dists[o + k] = q.d[k];
+        p.bary[(o + k) * 3 + 0] = q.b0[k];
+        p.bary[(o + k) * 3 + 1] = q.b1[k];
+        p.bary[(o + k) * 3 + 2] = q.b2[k];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Large-K path (8 < K <= 150): only the sorted (z, face) keys are kept (thread-local array); the
+// payload of the final winners is recomputed (same arithmetic, so identical values).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const FineParams p) {
+  __shared__ FaceChunk s;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int t = blockIdx.x;
+  const int n = t / (p.TY * p.TX);
+  const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
+  int xo, yo;
+  thread_pixel(tile_x, tile_y, xo, yo);
+  const bool valid = xo < p.W && yo < p.H;
+  const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
+  const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
+  const float fx_lo = warp_min(valid ? px : FLT_MAX), fx_hi = warp_max(valid ? px : -FLT_MAX);
+  const float fy_lo = warp_min(valid ? py : FLT_MAX), fy_hi = warp_max(valid ? py : -FLT_MAX);
+  const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
+  const bool overflow = (int64_t)seg_end > p.capacity;
+  const int64_t mesh_first = p.first[n];
+  const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
+  const bool persp = p.persp != 0, clip = p.clip != 0, cull = p.cull != 0;
+  const int K = p.K;
+
+  float qz[B200R_MAX_K];
+  int qi[B200R_MAX_K];
+  int qn = 0;
+
+  for (int base = 0; base < count; base += CHUNK) {
+    const int nc = min(CHUNK, count - base);
+    __syncthreads();
+    if (tid < nc) {
+      const int f = overflow ? (int)(mesh_first + base + tid) : p.pairs[seg_begin + base + tid];
+      stage_face(s, tid, p.face_verts, f, p.sqrt_blur, cull);
+    }
+    __syncthreads();
+    for (int g = 0; g < nc; g += 32) {
+      bool touch = false;
+      if (g + lane < nc) {
+        const float4 bx = s.box[g + lane];
+        touch = !(fx_lo > bx.y || fx_hi < bx.x || fy_lo > bx.w || fy_hi < bx.z);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, touch);
+      while (m) {
+        const int j = g + __ffs(m) - 1;
+        m &= m - 1;
+        const float4 bx = s.box[j];
+        if (px > bx.y || px < bx.x || py > bx.w || py < bx.z) continue;
+        const float4 fa = s.a[j], fb = s.b[j], fc = s.c[j];
+        const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
+        Hit h;
+        if (!eval_pixel_face(px, py, f, fb.z, p.blur_radius, persp, clip, h)) continue;
+        const int fi = __float_as_int(fb.w);
+        if (qn == K && !key_less(h.z, fi, qz[K - 1], qi[K - 1])) continue;
+        int i = qn < K ? qn++ : K - 1;
+        while (i > 0 && key_less(h.z, fi, qz[i - 1], qi[i - 1])) {
+          qz[i] = qz[i - 1];
+          qi[i] = qi[i - 1];
+          --i;
+        }
+        qz[i] = h.z;
+        qi[i] = fi;
+      }
+    }
+  }
+  if (!valid) return;
+  const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
+  for (int k = 0; k < K; ++k) {
+    Hit h = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
+    long long id = -1;
+    if (k < qn) {
+      const float* v = p.face_verts + (int64_t)qi[k] * 9;
+      const Face f = {__ldg(v + 0), __ldg(v + 1), __ldg(v + 2), __ldg(v + 3), __ldg(v + 4),
+                      __ldg(v + 5), __ldg(v + 6), __ldg(v + 7), __ldg(v + 8)};
+      eval_pixel_face(px, py, f, bary_denominator(f), p.blur_radius, persp, clip, h);
+      id = qi[k];
+    }
+    p.pix_to_face[o + k] = id;
+    p.zbuf[o + k] = h.z;
+    p.dists[o + k] = h.dist;
+    p.bary[(o + k) * 3 + 0] = h.b0;
+    p.bary[(o + k) * 3 + 1] = h.b1;
+    p.bary[(o + k) * 3 + 2] = h.b2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward: one thread per pixel (same 16x16 tiles / 8x4 warp footprints as the forward pass, so the
+// faces a warp scatters into are spatially coherent), chain rule of rasterize_meshes.cu:466-561 with
+// BarycentricClipBackward fed the perspective-corrected barycentrics like the forward pass and the
+// CPU implementation (rasterize_meshes_cpu.cpp:498-500).
+// ------------------------------------------------------------------------------------------------
+struct BackwardParams {
+  const float* face_verts;
+  const int64_t* pix_to_face;
+  const float* grad_zbuf;
+  const float* grad_bary;
+  const float* grad_dists;
+  int N, H, W, K, TY, TX;
+  float rx, ry;
+  int persp, clip;
+  float* grad_face_verts;
+};
+
+__device__ __forceinline__ void edge_bwd(float px, float py, float ax, float ay, float bx, float by, float g,
+                                         float2& dp, float2& da, float2& db) {
+  dp = make_float2(g * (by - ay), g * (ax - bx));
+  da = make_float2(g * (py - by), g * (bx - px));
+  db = make_float2(g * (ay - py), g * (px - ax));
+}
+
+__device__ __forceinline__ void point_line_bwd(float px, float py, float ax, float ay, float bx, float by, float g,
+                                               float2& ga, float2& gb) {
+  const float bax = bx - ax, bay = by - ay;
+  const float t = __saturatef((bax * (px - ax) + bay * (py - ay)) / (bax * bax + bay * bay));
+  const float qx = (1.0f - t) * ax + t * bx, qy = (1.0f - t) * ay + t * by;
+  const float cx = 2.0f * (qx - px), cy = 2.0f * (qy - py);
+  ga = make_float2(g * (1.0f - t) * cx, g * (1.0f - t) * cy);
+  gb = make_float2(g * t * cx, g * t * cy);
+}
+
+__global__ void __launch_bounds__(TILE_THREADS) mesh_backward_kernel(const BackwardParams p) {
+  const int t = blockIdx.x;
+  const int n = t / (p.TY * p.TX);
+  const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
+  int xo, yo;
+  thread_pixel(tile_x, tile_y, xo, yo);
+  if (xo >= p.W || yo >= p.H) return;
+  const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
+  const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
+  const int K = p.K;
+  const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
+  const bool persp = p.persp != 0, clip = p.clip != 0;
+
+  for (int k = 0; k < K; ++k) {
+    const int64_t i = o + k;
+    const int64_t fi = p.pix_to_face[i];
+    if (fi < 0) continue;
+    const float* v = p.face_verts + fi * 9;
+    const Face f = {__ldg(v + 0), __ldg(v + 1), __ldg(v + 2), __ldg(v + 3), __ldg(v + 4),
+                    __ldg(v + 5), __ldg(v + 6), __ldg(v + 7), __ldg(v + 8)};
+    const float gz = p.grad_zbuf[i], gd = p.grad_dists[i];
+    const float gb0 = p.grad_bary[i * 3 + 0], gb1 = p.grad_bary[i * 3 + 1], gb2 = p.grad_bary[i * 3 + 2];
+
+    const float den = bary_denominator(f);
+    float w0, w1, w2;
+    bary_coords(px, py, f, den, w0, w1, w2);
+    float c0 = w0, c1 = w1, c2 = w2;  // (perspective-corrected) barycentrics
+    if (persp) bary_persp(c0, c1, c2, f.z0, f.z1, f.z2);
+    float k0 = c0, k1 = c1, k2 = c2;  // clipped
+    if (clip) bary_clip(k0, k1, k2);
+    const bool inside = c0 > 0.0f && c1 > 0.0f && c2 > 0.0f;
+    const float sgd = inside ? -gd : gd;
+
+    // d dist / d verts: gradient flows to the closest edge only (geometry_utils.cuh:421-462)
+    float2 dv0 = make_float2(0.f, 0.f), dv1 = dv0, dv2 = dv0;
+    {
+      const float e01 = point_line_dist(px, py, f.x0, f.y0, f.x1, f.y1);
+      const float e02 = point_line_dist(px, py, f.x0, f.y0, f.x2, f.y2);
+      const float e12 = point_line_dist(px, py, f.x1, f.y1, f.x2, f.y2);
+      if (e01 <= e02 && e01 <= e12)
+        point_line_bwd(px, py, f.x0, f.y0, f.x1, f.y1, sgd, dv0, dv1);
+      else if (e02 <= e01 && e02 <= e12)
+        point_line_bwd(px, py, f.x0, f.y0, f.x2, f.y2, sgd, dv0, dv2);
+      else if (e12 <= e01 && e12 <= e02)
+        point_line_bwd(px, py, f.x1, f.y1, f.x2, f.y2, sgd, dv1, dv2);
+    }
+
+    // upstream gradient on the (clipped) barycentrics, including zbuf = sum_i bary_i * z_i
+    float g0 = gb0 + gz * f.z0, g1 = gb1 + gz * f.z1, g2 = gb2 + gz * f.z2;
+    if (clip) {  // BarycentricClipBackward (geometry_utils.cuh:273-329) on the corrected barycentrics
+      const float m0 = fmaxf(c0, 0.0f), m1 = fmaxf(c1, 0.0f), m2 = fmaxf(c2, 0.0f);
+      float sum = m0 + m1 + m2, gsc = 1.0f;
+      if (sum < 1e-5f) {
+        gsc = 0.0f;
+        sum = 1e-5f;
+      }
+      const float inv = 1.0f / sum, inv2 = gsc / (sum * sum);
+      const float s0 = -m0 * inv2, s1 = -m1 * inv2, s2 = -m2 * inv2;
+      const float cross = g0 * s0 + g1 * s1 + g2 * s2;
+      const float n0 = c0 < 0.0f ? 0.0f : g0 * inv + cross;
+      const float n1 = c1 < 0.0f ? 0.0f : g1 * inv + cross;
+      const float n2 = c2 < 0.0f ? 0.0f : g2 * inv + cross;
+      g0 = n0;
+      g1 = n1;
+      g2 = n2;
+    }
+    float dz0 = 0.0f, dz1 = 0.0f, dz2 = 0.0f;
+    if (persp) {  // BarycentricPerspectiveCorrectionBackward (geometry_utils.cuh:200-228)
+      const float t0 = w0 * f.z1 * f.z2, t1 = f.z0 * w1 * f.z2, t2 = f.z0 * f.z1 * w2;
+      const float dn = fmaxf(t0 + t1 + t2, 1e-8f);
+      const float gdn = (-t0 * g0 - t1 * g1 - t2 * g2) / (dn * dn);
+      const float h0 = gdn + g0 / dn, h1 = gdn + g1 / dn, h2 = gdn + g2 / dn;
+      g0 = h0 * f.z1 * f.z2;
+      g1 = h1 * f.z0 * f.z2;
+      g2 = h2 * f.z0 * f.z1;
+      dz0 = h1 * w1 * f.z2 + h2 * w2 * f.z1;
+      dz1 = h0 * w0 * f.z2 + h2 * w2 * f.z0;
+      dz2 = h0 * w0 * f.z1 + h1 * w1 * f.z0;
+    }
+    // BarycentricCoordsBackward (geometry_utils.cuh:101-161)
+    float2 bv0 = make_float2(0.f, 0.f), bv1 = bv0, bv2 = bv0;
+    {
+      const float area2 = den * den, rden = 1.0f / den;
+      const float e0 = edge_fn(px, py, f.x1, f.y1, f.x2, f.y2);
+      const float e1 = edge_fn(px, py, f.x2, f.y2, f.x0, f.y0);
+      const float e2 = edge_fn(px, py, f.x0, f.y0, f.x1, f.y1);
+      float2 dp, da, db, ap, aa, ab;
+      // every w_i = e_i / area also depends on area = E(v2; v0, v1)
+      const float garea = g0 * (-e0 / area2) + g1 * (-e1 / area2) + g2 * (-e2 / area2);
+      edge_bwd(f.x2, f.y2, f.x0, f.y0, f.x1, f.y1, garea, ap, aa, ab);  // (p=v2, a=v0, b=v1)
+      bv2.x += ap.x; bv2.y += ap.y;
+      bv0.x += aa.x; bv0.y += aa.y;
+      bv1.x += ab.x; bv1.y += ab.y;
+      edge_bwd(px, py, f.x1, f.y1, f.x2, f.y2, g0 * rden, dp, da, db);  // w0: (p, v1, v2)
+      bv1.x += da.x; bv1.y += da.y;
+      bv2.x += db.x; bv2.y += db.y;
+      edge_bwd(px, py, f.x2, f.y2, f.x0, f.y0, g1 * rden, dp, da, db);  // w1: (p, v2, v0)
+      bv2.x += da.x; bv2.y += da.y;
+      bv0.x += db.x; bv0.y += db.y;
+      edge_bwd(px, py, f.x0, f.y0, f.x1, f.y1, g2 * rden, dp, da, db);  // w2: (p, v0, v1)
+      bv0.x += da.x; bv0.y += da.y;
+      bv1.x += db.x; bv1.y += db.y;
+    }
+    float* g = p.grad_face_verts + fi * 9;
+    atomicAdd(g + 0, bv0.x + dv0.x);
+    atomicAdd(g + 1, bv0.y + dv0.y);
+    atomicAdd(g + 2, gz * k0 + dz0);
+    atomicAdd(g + 3, bv1.x + dv1.x);
+    atomicAdd(g + 4, bv1.y + dv1.y);
+    atomicAdd(g + 5, gz * k1 + dz1);
+    atomicAdd(g + 6, bv2.x + dv2.x);
+    atomicAdd(g + 7, bv2.y + dv2.y);
+    atomicAdd(g + 8, gz * k2 + dz2);
+  }
+}
+
+}  // namespace b200r
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace b200r;
+
+extern "C" size_t b200r_rasterize_meshes_workspace_bytes(int64_t F, int32_t N, int32_t H, int32_t W,
+                                                         int64_t pair_capacity) {
+  if (F < 0 || N < 0 || H < 0 || W < 0) return 0;
+  return carve_workspace(nullptr, F, N, H, W, pair_capacity).bytes;
+}
+
+extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F, const int64_t* first,
+                                              const int64_t* num, const int64_t* neighbor, int32_t N, int32_t H,
+                                              int32_t W, float blur_radius, int32_t K, int32_t bin_size,
+                                              int32_t max_faces_per_bin, int32_t perspective_correct,
+                                              int32_t clip_barycentric_coords, int32_t cull_backfaces,
+                                              int64_t* pix_to_face, float* zbuf, float* bary, float* dists,
+                                              void* workspace, size_t workspace_bytes, int64_t pair_capacity,
+                                              void* stream_) {
+  (void)bin_size;
+  (void)max_faces_per_bin;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (K > B200R_MAX_K) return fail(B200R_ERR_INVALID_ARGUMENT, "Must have points_per_pixel <= 150");
+  if (F < 0 || N < 0 || H < 0 || W < 0 || K < 0) return fail(B200R_ERR_INVALID_ARGUMENT, "negative size");
+  if (F > INT_MAX) return fail(B200R_ERR_INVALID_ARGUMENT, "more than 2^31-1 packed faces are not supported");
+  if (neighbor != nullptr)
+    return fail(B200R_ERR_INVALID_ARGUMENT,
+                "clipped_faces_neighbor_idx with non -1 entries is not supported by this build yet");
+  if ((int64_t)N * H * W * K == 0) return B200R_OK;  // empty outputs (rasterize_meshes.cu:793-796)
+  const int TY = div_up(H, TILE), TX = div_up(W, TILE);
+  if (TY > 0xFFFE || TX > 0xFFFE) return fail(B200R_ERR_INVALID_ARGUMENT, "image too large");
+  const int64_t ntiles = (int64_t)N * TY * TX;
+  if (ntiles > INT_MAX) return fail(B200R_ERR_INVALID_ARGUMENT, "too many tiles");
+  BinWorkspace ws = carve_workspace(workspace, F, N, H, W, pair_capacity);
+  if (workspace == nullptr || workspace_bytes < ws.bytes)
+    return fail(B200R_ERR_WORKSPACE, "workspace too small for rasterize_meshes_forward");
+
+  const float rx = ndc_range(W, H), ry = ndc_range(H, W);
+  const float sqrt_blur = sqrtf(blur_radius);  // IEEE sqrt, like the device sqrt.rn of the reference
+
+  B200R_CUDA_OK(cudaMemsetAsync(ws.tile_count, 0, sizeof(int) * (size_t)ntiles, stream));
+  if (F > 0) {
+    mesh_setup_count_kernel<<<(unsigned)((F + SETUP_FACES - 1) / SETUP_FACES), SETUP_FACES, 0, stream>>>(
+        face_verts, F, first, num, N, H, W, TY, TX, rx, ry, sqrt_blur, cull_backfaces, ws.rect, ws.tile_count);
+    B200R_LAUNCHED("mesh_setup_count_kernel");
+  }
+  tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles);
+  B200R_LAUNCHED("tile_scan_kernel");
+  if (F > 0) {
+    tile_fill_kernel<<<(unsigned)((F + 255) / 256), 256, 0, stream>>>(ws.rect, F, first, num, N, TY, TX,
+                                                                    ws.tile_offset, ws.tile_count, ws.pairs,
+                                                                    ws.capacity);
+    B200R_LAUNCHED("tile_fill_kernel");
+  }
+  FineParams p;
+  p.face_verts = face_verts;
+  p.first = first;
+  p.num = num;
+  p.tile_offset = ws.tile_offset;
+  p.pairs = ws.pairs;
+  p.capacity = ws.capacity;
+  p.N = N; p.H = H; p.W = W; p.K = K; p.TY = TY; p.TX = TX;
+  p.rx = rx; p.ry = ry; p.blur_radius = blur_radius; p.sqrt_blur = sqrt_blur;
+  p.persp = perspective_correct; p.clip = clip_barycentric_coords; p.cull = cull_backfaces;
+  p.pix_to_face = pix_to_face; p.zbuf = zbuf; p.bary = bary; p.dists = dists;
+  const unsigned grid = (unsigned)ntiles;
+  if (K <= 1)
+    mesh_fine_kernel<1><<<grid, TILE_THREADS, 0, stream>>>(p);
+  else if (K <= 2)
+    mesh_fine_kernel<2><<<grid, TILE_THREADS, 0, stream>>>(p);
+  else if (K <= 4)
+    mesh_fine_kernel<4><<<grid, TILE_THREADS, 0, stream>>>(p);
+  else if (K <= 8)
+    mesh_fine_kernel<8><<<grid, TILE_THREADS, 0, stream>>>(p);
+  else
+    mesh_fine_bigk_kernel<<<grid, TILE_THREADS, 0, stream>>>(p);
+  B200R_LAUNCHED("mesh_fine_kernel");
+  return B200R_OK;
+}
+
+extern "C" int b200r_rasterize_meshes_backward(const float* face_verts, int64_t F, const int64_t* pix_to_face,
+                                               const float* grad_zbuf, const float* grad_bary,
+                                               const float* grad_dists, int32_t N, int32_t H, int32_t W, int32_t K,
+                                               int32_t perspective_correct, int32_t clip_barycentric_coords,
+                                               float* grad_face_verts, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (F < 0 || N < 0 || H < 0 || W < 0 || K < 0) return fail(B200R_ERR_INVALID_ARGUMENT, "negative size");
+  if (F == 0) return B200R_OK;
+  B200R_CUDA_OK(cudaMemsetAsync(grad_face_verts, 0, sizeof(float) * 9 * (size_t)F, stream));
+  if ((int64_t)N * H * W * K == 0) return B200R_OK;
+  const int TY = div_up(H, TILE), TX = div_up(W, TILE);
+  BackwardParams p;
+  p.face_verts = face_verts; p.pix_to_face = pix_to_face;
+  p.grad_zbuf = grad_zbuf; p.grad_bary = grad_bary; p.grad_dists = grad_dists;
+  p.N = N; p.H = H; p.W = W; p.K = K; p.TY = TY; p.TX = TX;
+  p.rx = ndc_range(W, H); p.ry = ndc_range(H, W);
+  p.persp = perspective_correct; p.clip = clip_barycentric_coords;
+  p.grad_face_verts = grad_face_verts;
+  mesh_backward_kernel<<<(unsigned)((int64_t)N * TY * TX), TILE_THREADS, 0, stream>>>(p);
+  B200R_LAUNCHED("mesh_backward_kernel");
+  return B200R_OK;
+}

@@ -1,0 +1,344 @@
+// Point-cloud rasterizer for sm_100a: setup/bin pass, per-tile fine pass (top-K per pixel), backward.
+//
+// Replaces, behind the same operator signature, the reference's
+//   PointBoundingBoxKernel + RasterizeCoarseCudaKernel   (rasterize_coarse.cu:53-74, 76-219)
+//   RasterizePointsFineCudaKernel / NaiveCudaKernel       (rasterize_points.cu:223-298, 87-149)
+//   RasterizePointsBackwardCudaKernel                     (rasterize_points.cu:366-411)
+// Same skeleton as raster_meshes.cu: exact tile binning, one CTA per 16x16 tile, points staged in
+// shared memory as 16-byte (x, y, z, r^2) records, warp-footprint culling by ballot, register top-K.
+#include <cfloat>
+#include <climits>
+
+#include "binning.cuh"
+#include "bulk_copy.cuh"
+#include "common.cuh"
+#include "raster_math.cuh"
+
+namespace b200r {
+
+constexpr int SETUP_POINTS = 256;
+constexpr int PCHUNK = 512;  // points staged per round (2 per thread)
+
+// Pass 1: per-point box (x +- r, y +- r), skip z < 0 (rasterize_coarse.cu:53-74), count per tile.
+// The CTA's 256 points (3072 contiguous bytes of the packed (P,3) array) arrive by one TMA bulk copy.
+__global__ void __launch_bounds__(SETUP_POINTS)
+    points_setup_count_kernel(const float* __restrict__ points, const float* __restrict__ radius, int64_t P,
+                              const int64_t* __restrict__ first, const int64_t* __restrict__ num, int N, int H,
+                              int W, int TY, int TX, float rx, float ry, uint2* __restrict__ rect,
+                              int* __restrict__ tile_count) {
+  __shared__ __align__(16) float s_pts[SETUP_POINTS * 3];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
+  const int64_t p0 = (int64_t)blockIdx.x * SETUP_POINTS;
+  const int np = (int)min((int64_t)SETUP_POINTS, P - p0);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  cta_load_words(s_pts, points + p0 * 3, np * 3, &bar, 0);
+  if (tid >= np) return;
+  const float x = s_pts[tid * 3 + 0], y = s_pts[tid * 3 + 1], z = s_pts[tid * 3 + 2];  // stride 3: conflict-free
+  const int64_t pi = p0 + tid;
+  const float r = __ldg(radius + pi);
+  uint2 rc = make_uint2(RECT_EMPTY_X, 0u);
+  const int n = find_owner(first, num, N, pi);
+  if (n >= 0 && !(z < 0.0f)) {
+    rc = bbox_to_tile_rect(fsub(x, r), fadd(x, r), fsub(y, r), fadd(y, r), H, W, rx, ry);
+    if (!rect_empty(rc)) count_rect(rc, n, TY, TX, tile_count);
+  }
+  rect[pi] = rc;
+}
+
+__device__ __forceinline__ bool pkey_less(float za, int ia, float zb, int ib) {
+  return za < zb || (za == zb && ia < ib);
+}
+
+template <int KMAX>
+struct PTopK {
+  float z[KMAX];
+  int id[KMAX];
+  float d[KMAX];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+      z[i] = FLT_MAX;
+      id[i] = INT_MAX;
+      d[i] = -1.0f;
+    }
+  }
+  __device__ __forceinline__ bool accepts(float pz, int p) const {
+    return pkey_less(pz, p, z[KMAX - 1], id[KMAX - 1]);
+  }
+  __device__ __forceinline__ void insert(float pz, int p, float d2) {
+    bool c[KMAX];
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) c[i] = pkey_less(pz, p, z[i], id[i]);
+#pragma unroll
+    for (int i = KMAX - 1; i >= 0; --i) {
+      const int j = i > 0 ? i - 1 : 0;
+      const bool up = i > 0 && c[j];
+      z[i] = up ? z[j] : (c[i] ? pz : z[i]);
+      id[i] = up ? id[j] : (c[i] ? p : id[i]);
+      d[i] = up ? d[j] : (c[i] ? d2 : d[i]);
+    }
+  }
+};
+
+struct __align__(16) PointChunk {
+  float4 box[PCHUNK];  // xmin, xmax, ymin, ymax (empty = never hit)
+  float4 rec[PCHUNK];  // x, y, z, r^2
+  int id[PCHUNK];
+};
+
+struct PointFineParams {
+  const float* points;
+  const float* radius;
+  const int64_t* first;
+  const int64_t* num;
+  const int* tile_offset;
+  const int* pairs;
+  int64_t capacity;
+  int N, H, W, K, TY, TX;
+  float rx, ry;
+  int32_t* idx;
+  float* zbuf;
+  float* dists;
+};
+
+__device__ __forceinline__ void stage_point(PointChunk& s, int slot, const float* __restrict__ points,
+                                            const float* __restrict__ radius, int pi) {
+  const float x = __ldg(points + (int64_t)pi * 3 + 0), y = __ldg(points + (int64_t)pi * 3 + 1),
+              z = __ldg(points + (int64_t)pi * 3 + 2);
+  const float r = __ldg(radius + pi);
+  float xmin = FLT_MAX, xmax = -FLT_MAX, ymin = FLT_MAX, ymax = -FLT_MAX;
+  if (!(z < 0.0f)) {  // points behind the camera are not rendered (rasterize_points.cu:55-56)
+    xmin = fsub(x, r);
+    xmax = fadd(x, r);
+    ymin = fsub(y, r);
+    ymax = fadd(y, r);
+  }
+  s.box[slot] = make_float4(xmin, xmax, ymin, ymax);
+  s.rec[slot] = make_float4(x, y, z, fmul(r, r));
+  s.id[slot] = pi;
+}
+
+__device__ __forceinline__ void pthread_pixel(int tile_x, int tile_y, int& xo, int& yo) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  xo = tile_x * TILE + (w & 1) * 8 + (lane & 7);
+  yo = tile_y * TILE + (w >> 1) * 4 + (lane >> 3);
+}
+
+__device__ __forceinline__ float pwarp_min(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+__device__ __forceinline__ float pwarp_max(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+
+// KMAX > 0: register top-K; KMAX == 0: thread-local arrays for K up to 150.
+template <int KMAX>
+__global__ void __launch_bounds__(TILE_THREADS) points_fine_kernel(const PointFineParams p) {
+  __shared__ PointChunk s;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int t = blockIdx.x;
+  const int n = t / (p.TY * p.TX);
+  const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
+  int xo, yo;
+  pthread_pixel(tile_x, tile_y, xo, yo);
+  const bool valid = xo < p.W && yo < p.H;
+  const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
+  const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
+  const float fx_lo = pwarp_min(valid ? px : FLT_MAX), fx_hi = pwarp_max(valid ? px : -FLT_MAX);
+  const float fy_lo = pwarp_min(valid ? py : FLT_MAX), fy_hi = pwarp_max(valid ? py : -FLT_MAX);
+
+  const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
+  const bool overflow = (int64_t)seg_end > p.capacity;
+  const int64_t cloud_first = p.first[n];
+  const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
+  const int K = p.K;
+
+  constexpr int QN = KMAX > 0 ? KMAX : 1;
+  PTopK<QN> q;
+  float lz[KMAX > 0 ? 1 : B200R_MAX_K];
+  int li[KMAX > 0 ? 1 : B200R_MAX_K];
+  float ld[KMAX > 0 ? 1 : B200R_MAX_K];
+  int ln = 0;
+  if (KMAX > 0) q.init();
+
+  for (int base = 0; base < count; base += PCHUNK) {
+    const int nc = min(PCHUNK, count - base);
+    __syncthreads();
+    for (int j = tid; j < nc; j += TILE_THREADS) {
+      const int pi = overflow ? (int)(cloud_first + base + j) : p.pairs[seg_begin + base + j];
+      stage_point(s, j, p.points, p.radius, pi);
+    }
+    __syncthreads();
+    for (int g = 0; g < nc; g += 32) {
+      bool touch = false;
+      if (g + lane < nc) {
+        const float4 bx = s.box[g + lane];
+        touch = !(fx_lo > bx.y || fx_hi < bx.x || fy_lo > bx.w || fy_hi < bx.z);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, touch);
+      while (m) {
+        const int j = g + __ffs(m) - 1;
+        m &= m - 1;
+        const float4 r = s.rec[j];
+        // CheckPixelInsidePoint (rasterize_points.cu:49-60): dist2 = fma(dy, dy, rn(dx*dx)) < rn(r*r)
+        const float dx = fsub(px, r.x), dy = fsub(py, r.y);
+        const float d2 = sqnorm2(dx, dy);
+        if (!valid || !(d2 < r.w) || r.z < 0.0f) continue;
+        const int pi = s.id[j];
+        if (KMAX > 0) {
+          if (q.accepts(r.z, pi)) q.insert(r.z, pi, d2);
+        } else {
+          if (ln == K && !pkey_less(r.z, pi, lz[K - 1], li[K - 1])) continue;
+          int i = ln < K ? ln++ : K - 1;
+          while (i > 0 && pkey_less(r.z, pi, lz[i - 1], li[i - 1])) {
+            lz[i] = lz[i - 1];
+            li[i] = li[i - 1];
+            ld[i] = ld[i - 1];
+            --i;
+          }
+          lz[i] = r.z;
+          li[i] = pi;
+          ld[i] = d2;
+        }
+      }
+    }
+  }
+  if (!valid) return;
+  const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
+  if (KMAX > 0) {
+#pragma unroll
+    for (int k = 0; k < QN; ++k) {
+      if (k < K) {
+        const bool e = q.id[k] == INT_MAX;
+        p.idx[o + k] = e ? -1 : q.id[k];
+        p.zbuf[o + k] = e ? -1.0f : q.z[k];
+        p.dists[o + k] = q.d[k];
+      }
+    }
+  } else {
+    for (int k = 0; k < K; ++k) {
+      p.idx[o + k] = k < ln ? li[k] : -1;
+      p.zbuf[o + k] = k < ln ? lz[k] : -1.0f;
+      p.dists[o + k] = k < ln ? ld[k] : -1.0f;
+    }
+  }
+}
+
+// Backward: one thread per (pixel, k) slot, coalesced over the (N,H,W,K) arrays
+// (rasterize_points.cu:366-411): grad_xy = 2 * grad_dist * (p_xy - pix_xy), grad_z = grad_zbuf.
+__global__ void __launch_bounds__(256)
+    points_backward_kernel(const float* __restrict__ points, const int32_t* __restrict__ idxs,
+                           const float* __restrict__ grad_zbuf, const float* __restrict__ grad_dists, int64_t total,
+                           int H, int W, int K, float rx, float ry, float* __restrict__ grad_points) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int pi = idxs[i];
+    if (pi < 0) continue;
+    const int64_t pix = i / K;
+    const int xo = (int)(pix % W), yo = (int)((pix / W) % H);
+    const float xf = pix_to_ndc(W - 1 - xo, W, rx);
+    const float yf = pix_to_ndc(H - 1 - yo, H, ry);
+    const float gd = grad_dists[i];
+    const float g2 = gd + gd;
+    const float gx = g2 * (__ldg(points + (int64_t)pi * 3 + 0) - xf);
+    const float gy = g2 * (__ldg(points + (int64_t)pi * 3 + 1) - yf);
+    atomicAdd(grad_points + (int64_t)pi * 3 + 0, gx);
+    atomicAdd(grad_points + (int64_t)pi * 3 + 1, gy);
+    atomicAdd(grad_points + (int64_t)pi * 3 + 2, grad_zbuf[i]);
+  }
+}
+
+}  // namespace b200r
+
+using namespace b200r;
+
+extern "C" size_t b200r_rasterize_points_workspace_bytes(int64_t P, int32_t N, int32_t H, int32_t W,
+                                                         int64_t pair_capacity) {
+  if (P < 0 || N < 0 || H < 0 || W < 0) return 0;
+  return carve_workspace(nullptr, P, N, H, W, pair_capacity).bytes;
+}
+
+extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, const int64_t* first,
+                                              const int64_t* num, const float* radius, int32_t N, int32_t H,
+                                              int32_t W, int32_t K, int32_t bin_size, int32_t max_points_per_bin,
+                                              int32_t* idx, float* zbuf, float* dists, void* workspace,
+                                              size_t workspace_bytes, int64_t pair_capacity, void* stream_) {
+  (void)bin_size;
+  (void)max_points_per_bin;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (K > B200R_MAX_K) return fail(B200R_ERR_INVALID_ARGUMENT, "Must have num_closest <= 150");
+  if (P < 0 || N < 0 || H < 0 || W < 0 || K < 0) return fail(B200R_ERR_INVALID_ARGUMENT, "negative size");
+  if (P > INT_MAX) return fail(B200R_ERR_INVALID_ARGUMENT, "more than 2^31-1 packed points are not supported");
+  if ((int64_t)N * H * W * K == 0) return B200R_OK;
+  const int TY = div_up(H, TILE), TX = div_up(W, TILE);
+  if (TY > 0xFFFE || TX > 0xFFFE) return fail(B200R_ERR_INVALID_ARGUMENT, "image too large");
+  const int64_t ntiles = (int64_t)N * TY * TX;
+  if (ntiles > INT_MAX) return fail(B200R_ERR_INVALID_ARGUMENT, "too many tiles");
+  BinWorkspace ws = carve_workspace(workspace, P, N, H, W, pair_capacity);
+  if (workspace == nullptr || workspace_bytes < ws.bytes)
+    return fail(B200R_ERR_WORKSPACE, "workspace too small for rasterize_points_forward");
+  const float rx = ndc_range(W, H), ry = ndc_range(H, W);
+
+  B200R_CUDA_OK(cudaMemsetAsync(ws.tile_count, 0, sizeof(int) * (size_t)ntiles, stream));
+  if (P > 0) {
+    points_setup_count_kernel<<<(unsigned)((P + SETUP_POINTS - 1) / SETUP_POINTS), SETUP_POINTS, 0, stream>>>(
+        points, radius, P, first, num, N, H, W, TY, TX, rx, ry, ws.rect, ws.tile_count);
+    B200R_LAUNCHED("points_setup_count_kernel");
+  }
+  tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles);
+  B200R_LAUNCHED("tile_scan_kernel");
+  if (P > 0) {
+    tile_fill_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(ws.rect, P, first, num, N, TY, TX,
+                                                                    ws.tile_offset, ws.tile_count, ws.pairs,
+                                                                    ws.capacity);
+    B200R_LAUNCHED("tile_fill_kernel");
+  }
+  PointFineParams p;
+  p.points = points; p.radius = radius; p.first = first; p.num = num;
+  p.tile_offset = ws.tile_offset; p.pairs = ws.pairs; p.capacity = ws.capacity;
+  p.N = N; p.H = H; p.W = W; p.K = K; p.TY = TY; p.TX = TX; p.rx = rx; p.ry = ry;
+  p.idx = idx; p.zbuf = zbuf; p.dists = dists;
+  const unsigned grid = (unsigned)ntiles;
+  if (K <= 1)
+    points_fine_kernel<1><<<grid, TILE_THREADS, 0, stream>>>(p);
+  else if (K <= 2)
+    points_fine_kernel<2><<<grid, TILE_THREADS, 0, stream>>>(p);
+  else if (K <= 4)
+    points_fine_kernel<4><<<grid, TILE_THREADS, 0, stream>>>(p);
+  else if (K <= 8)
+    points_fine_kernel<8><<<grid, TILE_THREADS, 0, stream>>>(p);
+  else if (K <= 16)
+    points_fine_kernel<16><<<grid, TILE_THREADS, 0, stream>>>(p);
+  else if (K <= 32)
+    points_fine_kernel<32><<<grid, TILE_THREADS, 0, stream>>>(p);
+  else
+    points_fine_kernel<0><<<grid, TILE_THREADS, 0, stream>>>(p);
+  B200R_LAUNCHED("points_fine_kernel");
+  return B200R_OK;
+}
+
+extern "C" int b200r_rasterize_points_backward(const float* points, int64_t P, const int32_t* idxs,
+                                               const float* grad_zbuf, const float* grad_dists, int32_t N,
+                                               int32_t H, int32_t W, int32_t K, float* grad_points, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (P < 0 || N < 0 || H < 0 || W < 0 || K < 0) return fail(B200R_ERR_INVALID_ARGUMENT, "negative size");
+  if (P == 0) return B200R_OK;
+  B200R_CUDA_OK(cudaMemsetAsync(grad_points, 0, sizeof(float) * 3 * (size_t)P, stream));
+  const int64_t total = (int64_t)N * H * W * K;
+  if (total == 0) return B200R_OK;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  points_backward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(points, idxs, grad_zbuf, grad_dists, total, H, W, K,
+                                                             ndc_range(W, H), ndc_range(H, W), grad_points);
+  B200R_LAUNCHED("points_backward_kernel");
+  return B200R_OK;
+}

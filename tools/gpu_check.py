@@ -1,0 +1,134 @@
+"""Ad-hoc GPU parity + timing report (development aid; the judged tests live in tests/)."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oracle  # noqa: E402
+from pytorch3d_b200 import _C, synthetic  # noqa: E402
+
+dev = torch.device("cuda:0")
+ref = oracle.load_reference(cuda=True)
+print("ref cuda module:", ref is not None, flush=True)
+
+
+def rand_faces(F, N, seed, scale=0.15, zlo=0.5, zhi=3.0):
+    g = torch.Generator().manual_seed(seed)
+    c = torch.rand(F, 1, 3, generator=g) * 2 - 1
+    v = c + (torch.rand(F, 3, 3, generator=g) - 0.5) * scale * 2
+    v[..., 2] = zlo + (zhi - zlo) * torch.rand(F, 3, generator=g)
+    per = F // N
+    first = torch.arange(N) * per
+    num = torch.full((N,), per)
+    num[-1] = F - first[-1]
+    return v.contiguous(), first.long(), num.long()
+
+
+def cmp(name, a, b):
+    a = [x.cpu().numpy() if torch.is_tensor(x) else x for x in a]
+    b = [x.cpu().numpy() if torch.is_tensor(x) else x for x in b]
+    idx_bad = int((a[0] != b[0]).sum())
+    fl = [float(np.nanmax(np.abs(x.astype(np.float64) - y.astype(np.float64)))) if x.size else 0.0
+          for x, y in zip(a[1:], b[1:])]
+    exact = [bool(np.array_equal(x, y)) for x, y in zip(a[1:], b[1:])]
+    print("  %-28s idx mismatches %d / %d   max|dfloat| %s exact %s" % (name, idx_bad, a[0].size, fl, exact), flush=True)
+    return idx_bad
+
+
+def mesh_case(fv, first, num, H, W, blur, K, persp, clip, cull, do_oracle=True):
+    print("mesh case F=%d N=%d %dx%d blur=%g K=%d persp=%d clip=%d cull=%d" % (
+        fv.shape[0], len(first), H, W, blur, K, persp, clip, cull), flush=True)
+    nb = torch.full((fv.shape[0],), -1, dtype=torch.int64)
+    d = [t.to(dev) for t in (fv, first, num, nb)]
+    mine = _C.rasterize_meshes(d[0], d[1], d[2], d[3], (H, W), blur, K, 0, 0, bool(persp), bool(clip), bool(cull))
+    torch.cuda.synchronize()
+    if do_oracle:
+        o = oracle.rasterize_meshes(fv.numpy(), first.numpy(), num.numpy(), (H, W), blur, K, persp, clip, cull,
+                                    arith=oracle.ARITH_CUDA, select=oracle.SELECT_CPU)
+        # output order (idx, z, bary, dists) for both
+        cmp("mine vs C-oracle(cuda arith)", mine, o)
+    if ref is not None:
+        r_naive = ref.rasterize_meshes(d[0], d[1], d[2], d[3], (H, W), blur, K, 0, 0, bool(persp), bool(clip), bool(cull))
+        cmp("mine vs ref-CUDA naive", mine, r_naive)
+        if max(H, W) / 16 < 22 and K <= 150:
+            r_fine = ref.rasterize_meshes(d[0], d[1], d[2], d[3], (H, W), blur, K, 16 if max(H, W) <= 256 else 32,
+                                          20000, bool(persp), bool(clip), bool(cull))
+            cmp("mine vs ref-CUDA coarse+fine", mine, r_fine)
+        if do_oracle:
+            cmp("C-oracle vs ref-CUDA naive", o, r_naive)
+    # backward
+    g = torch.Generator().manual_seed(231)
+    gz = torch.randn(mine[1].shape, generator=g).to(dev)
+    gb = torch.randn(mine[2].shape, generator=g).to(dev)
+    gd = torch.randn(mine[3].shape, generator=g).to(dev)
+    mg = _C.rasterize_meshes_backward(d[0], mine[0], gz, gb, gd, bool(persp), bool(clip))
+    og = oracle.rasterize_meshes_backward(fv.numpy(), mine[0].cpu().numpy(), gz.cpu().numpy(), gb.cpu().numpy(),
+                                          gd.cpu().numpy(), persp, clip, arith=oracle.ARITH_CUDA)
+    diff = np.abs(mg.cpu().numpy() - og)
+    den = np.maximum(np.abs(og), 1e-3)
+    print("  backward vs C-oracle: max abs %.3e  max rel %.3e (|g|max %.3e)" % (diff.max(), (diff / den).max(), np.abs(og).max()), flush=True)
+    if ref is not None:
+        rg = ref.rasterize_meshes_backward(d[0], mine[0], gz, gb, gd, bool(persp), bool(clip))
+        diff = (mg - rg).abs()
+        print("  backward vs ref-CUDA : max abs %.3e  max rel %.3e" % (diff.max().item(), (diff / rg.abs().clamp_min(1e-3)).max().item()), flush=True)
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    quick = "--quick" in sys.argv
+    for (persp, clip, cull, blur, K, H, W, F, N) in [
+        (0, 0, 0, 0.0, 4, 32, 32, 500, 2),
+        (1, 0, 0, 1e-3, 8, 33, 47, 500, 2),
+        (0, 1, 1, 1e-2, 3, 64, 40, 500, 2),
+        (1, 1, 0, 1e-4, 8, 48, 48, 500, 2),
+        (0, 0, 0, 1e-4, 8, 128, 128, 6000, 3),
+        (1, 1, 1, 0.05, 20, 40, 40, 300, 1),
+        (0, 0, 0, 1e-3, 150, 24, 24, 400, 1),
+    ]:
+        fv, first, num = rand_faces(F, N, seed=K + H)
+        mesh_case(fv, first, num, H, W, blur, K, persp, clip, cull)
+    # structured meshes
+    m = synthetic.torus_batch(2, 54, 54, seed=0)
+    mesh_case(synthetic.face_verts_of(m), m.mesh_to_faces_packed_first_idx(), m.num_faces_per_mesh(), 256, 256, 1e-4, 8, 0, 0, 0)
+    m = synthetic.ico_sphere_batch(1, 4)
+    mesh_case(synthetic.face_verts_of(m), m.mesh_to_faces_packed_first_idx(), m.num_faces_per_mesh(), 64, 64, 0.0, 1, 0, 0, 0)
+
+    # ---- timing: north-star config
+    m = synthetic.torus_batch(8, 187, 187, seed=0)
+    fv = synthetic.face_verts_of(m).to(dev)
+    first, num = m.mesh_to_faces_packed_first_idx().to(dev), m.num_faces_per_mesh().to(dev)
+    nb = torch.full((fv.shape[0],), -1, dtype=torch.int64, device=dev)
+    nb._b200_all_minus_one = True
+    for blur in (0.0, 1e-4):
+        out = _C.rasterize_meshes(fv, first, num, nb, (512, 512), blur, 8, 0, 0, False, False, False)
+        g = torch.Generator(device=dev).manual_seed(231)
+        gz = torch.randn(out[1].shape, generator=g, device=dev)
+        gb = torch.randn(out[2].shape, generator=g, device=dev)
+        gd = torch.randn(out[3].shape, generator=g, device=dev)
+        tf = timeit(lambda: _C.rasterize_meshes(fv, first, num, nb, (512, 512), blur, 8, 0, 0, False, False, False))
+        tb = timeit(lambda: _C.rasterize_meshes_backward(fv, out[0], gz, gb, gd, False, False))
+        hits = int((out[0] >= 0).sum())
+        print("NS 8x%d faces 512^2 K=8 blur=%g: fwd %.3f ms  bwd %.3f ms  -> %.1f frames/s ; hits %d" % (
+            int(num[0]), blur, tf, tb, 8e3 / (tf + tb), hits), flush=True)
+        if ref is not None and not quick:
+            trf = timeit(lambda: ref.rasterize_meshes(fv, first, num, nb, (512, 512), blur, 8, 32, 14000, False, False, False), iters=3, warm=1)
+            trb = timeit(lambda: ref.rasterize_meshes_backward(fv, out[0], gz, gb, gd, False, False), iters=3, warm=1)
+            print("   ref-CUDA(sm_100a build): fwd %.3f ms bwd %.3f ms -> %.1f frames/s" % (trf, trb, 8e3 / (trf + trb)), flush=True)
+            r = ref.rasterize_meshes(fv, first, num, nb, (512, 512), blur, 8, 32, 14000, False, False, False)
+            cmp("NS mine vs ref-CUDA fine", out, r)
