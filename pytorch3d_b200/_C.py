@@ -78,10 +78,10 @@ def rasterize_meshes(
     fv = face_verts.contiguous()
     first = mesh_to_face_first_idx.contiguous().to(torch.int64)
     num = num_faces_per_mesh.contiguous().to(torch.int64)
-    # Clipped-face neighbours (only produced by clip_faces) select the exact ordered path.
+    # Clipped-face neighbours (only produced by clip_faces): the kernel variant with the neighbour logic is
+    # used unless the caller tagged the tensor as all -1 (our own wrapper does); no host sync either way.
     nb = None
-    if (F > 0 and not getattr(clipped_faces_neighbor_idx, "_b200_all_minus_one", False)
-            and bool((clipped_faces_neighbor_idx != -1).any())):
+    if F > 0 and not getattr(clipped_faces_neighbor_idx, "_b200_all_minus_one", False):
         nb = clipped_faces_neighbor_idx.contiguous().to(torch.int64)
     with torch.cuda.device(dev):
         pix_to_face = torch.empty((N, H, W, K), dtype=torch.int64, device=dev)

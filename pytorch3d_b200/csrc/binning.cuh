@@ -119,6 +119,60 @@ static __global__ void __launch_bounds__(256)
     }
 }
 
+// Pass 4: sort every tile segment into ascending element order (one CTA per tile).  The fill pass
+// scatters with atomics, so segment order is arbitrary; ascending order makes the fine pass visit a
+// pixel's candidates exactly in the order of the reference's naive kernels (rasterize_meshes.cu:301,
+// rasterize_points.cu:128), which is what pins tie-breaking and makes the output deterministic.
+// "Normalised" bitonic network (every compare-exchange ascending), valid for any segment length:
+// partners beyond the end are treated as +inf and skipped.
+constexpr int SORT_THREADS = 128;
+constexpr int SORT_SMEM_ELEMS = 4096;
+
+static __global__ void __launch_bounds__(SORT_THREADS)
+    tile_sort_kernel(const int* __restrict__ offsets, int* __restrict__ pairs, int64_t capacity) {
+  __shared__ int s_keys[SORT_SMEM_ELEMS];
+  const int t = blockIdx.x;
+  const int begin = offsets[t], end = offsets[t + 1];
+  const int n = end - begin;
+  if (n < 2 || (int64_t)end > capacity) return;  // overflowed tiles are rasterised from the mesh range
+  const bool in_smem = n <= SORT_SMEM_ELEMS;
+  int* keys = in_smem ? s_keys : pairs + begin;
+  if (in_smem) {
+    for (int i = threadIdx.x; i < n; i += SORT_THREADS) s_keys[i] = pairs[begin + i];
+  }
+  __syncthreads();
+  for (int k = 2; (k >> 1) < n; k <<= 1) {
+    // first step of the merge: partner = mirror image inside the block of size k
+    for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+      const int j = i ^ (k - 1);
+      if (j > i && j < n) {
+        const int a = keys[i], b = keys[j];
+        if (b < a) {
+          keys[i] = b;
+          keys[j] = a;
+        }
+      }
+    }
+    __syncthreads();
+    for (int d = k >> 2; d > 0; d >>= 1) {
+      for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+        const int j = i ^ d;
+        if (j > i && j < n) {
+          const int a = keys[i], b = keys[j];
+          if (b < a) {
+            keys[i] = b;
+            keys[j] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (in_smem) {
+    for (int i = threadIdx.x; i < n; i += SORT_THREADS) pairs[begin + i] = s_keys[i];
+  }
+}
+
 // Workspace carving (all int32 / uint2 arrays, 16B-aligned sections).
 struct BinWorkspace {
   int* tile_count;  // [ntiles]   counts, then fill cursors

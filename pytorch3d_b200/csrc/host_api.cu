@@ -106,12 +106,10 @@ extern "C" int b200r_rasterize_meshes_forward_host(const float* face_verts, int6
                                                    int32_t cull_backfaces, int64_t* pix_to_face, float* zbuf,
                                                    float* bary, float* dists) {
   if (F < 0 || N < 0 || H < 0 || W < 0 || K < 0) return fail(B200R_ERR_INVALID_ARGUMENT, "negative size");
-  if (neighbor != nullptr) {
+  if (neighbor != nullptr) {  // only stage the neighbour table when it carries information
     bool any = false;
     for (int64_t i = 0; i < F && !any; ++i) any = neighbor[i] != -1;
-    if (any)
-      return fail(B200R_ERR_INVALID_ARGUMENT,
-                  "clipped_faces_neighbor_idx with non -1 entries is not supported by this build yet");
+    if (!any) neighbor = nullptr;
   }
   B200R_TRY(ensure_ctx());
   cudaStream_t s = ctx().stream;
@@ -129,8 +127,13 @@ extern "C" int b200r_rasterize_meshes_forward_host(const float* face_verts, int6
   B200R_TRY(h2d(d_fv, face_verts, sizeof(float) * 9 * (size_t)F, s));
   B200R_TRY(h2d(d_first, first, sizeof(int64_t) * (size_t)N, s));
   B200R_TRY(h2d(d_num, num, sizeof(int64_t) * (size_t)N, s));
+  void* d_nb = nullptr;
+  if (neighbor != nullptr) {
+    B200R_TRY(dev_buf(10, sizeof(int64_t) * (size_t)F, &d_nb));
+    B200R_TRY(h2d(d_nb, neighbor, sizeof(int64_t) * (size_t)F, s));
+  }
   B200R_TRY(b200r_rasterize_meshes_forward(
-      (const float*)d_fv, F, (const int64_t*)d_first, (const int64_t*)d_num, nullptr, N, H,
+      (const float*)d_fv, F, (const int64_t*)d_first, (const int64_t*)d_num, (const int64_t*)d_nb, N, H,
       W, blur_radius, K, 0, 0, perspective_correct, clip_barycentric_coords, cull_backfaces, (int64_t*)d_p2f,
       (float*)d_z, (float*)d_b, (float*)d_d, d_ws, ws_bytes, 0, s));
   B200R_TRY(d2h(pix_to_face, d_p2f, sizeof(int64_t) * slots, s));

@@ -8,7 +8,8 @@
 // faces are staged once per CTA into shared memory as float4 records with the per-face constants
 // (blur-expanded box, barycentric denominator) precomputed; each warp owns an 8x4 pixel footprint,
 // culls 32 faces at a time against it (one face per lane + ballot) and only then runs the exact
-// per-pixel arithmetic of raster_math.cuh; the K nearest hits live in registers, sorted by (z, face).
+// per-pixel arithmetic of raster_math.cuh; the K nearest hits live in registers (the reference's queue
+// semantics, fed in ascending face order from sorted tile lists).
 #include <cfloat>
 #include <climits>
 
@@ -104,41 +105,114 @@ __device__ __forceinline__ bool eval_pixel_face(float px, float py, const Face& 
 }
 
 __device__ __forceinline__ bool key_less(float za, int ia, float zb, int ib) {
-  return za < zb || (za == zb && ia < ib);
+  return za < zb || (za == zb && ia < ib);  // operator< of the reference's Pixel (rasterize_meshes.cu:30-32)
 }
 
-// K nearest hits of one pixel, kept sorted by (z, face index) in registers (all indices static).
+// The K nearest hits of one pixel.  This is the reference's per-pixel queue (rasterize_meshes.cu:179-237)
+// restated for registers: an UNSORTED array of K slots plus the tracked maximum (q_max_z, q_max_idx); a new
+// hit fills the next free slot, or -- when the queue is full and pz < q_max_z -- overwrites the tracked
+// maximum, after which the maximum is searched again (first slot with a strictly larger z wins).  Faces
+// reach the queue in ascending index order (sorted tile lists), so ties are resolved exactly as by the
+// reference's naive kernel.  All array indices are compile-time constants (predicated updates), so the
+// queue never leaves the register file.
 template <int KMAX>
 struct TopK {
   float z[KMAX];
   int id[KMAX];
   float d[KMAX], b0[KMAX], b1[KMAX], b2[KMAX];
+  int size;
+  float max_z;
+  int max_idx;
 
   __device__ __forceinline__ void init() {
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
-      z[i] = FLT_MAX;
-      id[i] = INT_MAX;
+      z[i] = -1.0f;
+      id[i] = -1;
       d[i] = b0[i] = b1[i] = b2[i] = -1.0f;
     }
+    size = 0;
+    max_z = -1000.0f;  // (:292)
+    max_idx = -1;
   }
-  __device__ __forceinline__ bool accepts(float pz, int f) const {
-    return key_less(pz, f, z[KMAX - 1], id[KMAX - 1]);
+  __device__ __forceinline__ void put(int slot, const Hit& h, int f) {
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+      const bool w = i == slot;
+      z[i] = w ? h.z : z[i];
+      id[i] = w ? f : id[i];
+      d[i] = w ? h.dist : d[i];
+      b0[i] = w ? h.b0 : b0[i];
+      b1[i] = w ? h.b1 : b1[i];
+      b2[i] = w ? h.b2 : b2[i];
+    }
   }
-  __device__ __forceinline__ void insert(const Hit& h, int f) {
-    bool c[KMAX];
+  // Handle a face that covers the pixel (the `else` branch at :216-236).
+  __device__ __forceinline__ void offer(const Hit& h, int f, int K) {
+    if (size < K) {
+      put(size, h, f);
+      if (h.z > max_z) {
+        max_z = h.z;
+        max_idx = size;
+      }
+      ++size;
+    } else if (h.z < max_z) {
+      put(max_idx, h, f);
+      max_z = h.z;
 #pragma unroll
-    for (int i = 0; i < KMAX; ++i) c[i] = key_less(h.z, f, z[i], id[i]);
+      for (int i = 0; i < KMAX; ++i) {
+        if (i < K && z[i] > max_z) {
+          max_z = z[i];
+          max_idx = i;
+        }
+      }
+    }
+  }
+  // Clipped-face neighbour handling (:186-215): if the other half of a clipped quad is already queued,
+  // keep whichever half is closer to the pixel.  Returns true if the hit was consumed here.
+  __device__ __forceinline__ bool offer_neighbor(const Hit& h, int f, int neighbor) {
+    int at = -1;
 #pragma unroll
-    for (int i = KMAX - 1; i >= 0; --i) {
-      const bool up = i > 0 && c[i > 0 ? i - 1 : 0];
-      const int j = i > 0 ? i - 1 : 0;
-      z[i] = up ? z[j] : (c[i] ? h.z : z[i]);
-      id[i] = up ? id[j] : (c[i] ? f : id[i]);
-      d[i] = up ? d[j] : (c[i] ? h.dist : d[i]);
-      b0[i] = up ? b0[j] : (c[i] ? h.b0 : b0[i]);
-      b1[i] = up ? b1[j] : (c[i] ? h.b1 : b1[i]);
-      b2[i] = up ? b2[j] : (c[i] ? h.b2 : b2[i]);
+    for (int i = KMAX - 1; i >= 0; --i)
+      if (i < size && id[i] == neighbor) at = i;  // first match
+    if (at < 0) return false;
+    float nd = 0.0f;
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) nd = i == at ? fabsf(d[i]) : nd;
+    if (fabsf(h.dist) < nd) {
+      put(at, h, f);
+      if (h.z > max_z) {
+        max_z = h.z;
+        max_idx = at;
+      }
+    }
+    return true;
+  }
+  // BubbleSort(q, q_size) on (z, idx) (:322 / rasterization_utils.cuh:52-66).  Keys are unique, so any
+  // sorting network gives the same result; unfilled slots are pushed to the end.
+  __device__ __forceinline__ void sort() {
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+      if (i >= size) {
+        z[i] = FLT_MAX;
+        id[i] = INT_MAX;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < KMAX; ++r) {
+#pragma unroll
+      for (int i = r & 1; i + 1 < KMAX; i += 2) {
+        if (key_less(z[i + 1], id[i + 1], z[i], id[i])) {
+          float t;
+          int ti;
+          t = z[i]; z[i] = z[i + 1]; z[i + 1] = t;
+          ti = id[i]; id[i] = id[i + 1]; id[i + 1] = ti;
+          t = d[i]; d[i] = d[i + 1]; d[i + 1] = t;
+          t = b0[i]; b0[i] = b0[i + 1]; b0[i + 1] = t;
+          t = b1[i]; b1[i] = b1[i + 1]; b1[i + 1] = t;
+          t = b2[i]; b2[i] = b2[i + 1]; b2[i + 1] = t;
+        }
+      }
     }
   }
 };
@@ -148,11 +222,12 @@ struct __align__(16) FaceChunk {
   float4 box[CHUNK];  // xmin, xmax, ymin, ymax (blur-expanded; empty box = never hit)
   float4 a[CHUNK];    // x0, y0, x1, y1
   float4 b[CHUNK];    // x2, y2, den, face index (int bits)
-  float4 c[CHUNK];    // z0, z1, z2, -
+  float4 c[CHUNK];    // z0, z1, z2, clipped-face neighbour index (int bits, -1 = none)
 };
 
-__device__ __forceinline__ void stage_face(FaceChunk& s, int slot, const float* __restrict__ face_verts, int f,
-                                           float sqrt_blur, bool cull_backfaces) {
+__device__ __forceinline__ void stage_face(FaceChunk& s, int slot, const float* __restrict__ face_verts,
+                                           const int64_t* __restrict__ neighbor, int f, float sqrt_blur,
+                                           bool cull_backfaces) {
   const float* v = face_verts + (int64_t)f * 9;
   const Face fc = {__ldg(v + 0), __ldg(v + 1), __ldg(v + 2), __ldg(v + 3), __ldg(v + 4),
                    __ldg(v + 5), __ldg(v + 6), __ldg(v + 7), __ldg(v + 8)};
@@ -161,11 +236,14 @@ __device__ __forceinline__ void stage_face(FaceChunk& s, int slot, const float* 
   s.box[slot] = make_float4(xmin, xmax, ymin, ymax);
   s.a[slot] = make_float4(fc.x0, fc.y0, fc.x1, fc.y1);
   s.b[slot] = make_float4(fc.x2, fc.y2, bary_denominator(fc), __int_as_float(f));
-  s.c[slot] = make_float4(fc.z0, fc.z1, fc.z2, 0.0f);
+  // the reference reads the int64 neighbour index into an int (:186)
+  const int nb = neighbor ? (int)__ldg(neighbor + f) : -1;
+  s.c[slot] = make_float4(fc.z0, fc.z1, fc.z2, __int_as_float(nb));
 }
 
 struct FineParams {
   const float* face_verts;
+  const int64_t* neighbor;  // clipped_faces_neighbor_idx or nullptr
   const int64_t* first;
   const int64_t* num;
   const int* tile_offset;
@@ -198,7 +276,7 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-template <int KMAX>
+template <int KMAX, bool NB>
 __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParams p) {
   __shared__ FaceChunk s;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -224,13 +302,14 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParam
   TopK<KMAX> q;
   q.init();
   const bool persp = p.persp != 0, clip = p.clip != 0, cull = p.cull != 0;
+  const int K = p.K;
 
   for (int base = 0; base < count; base += CHUNK) {
     const int nc = min(CHUNK, count - base);
     __syncthreads();  // previous chunk fully consumed
     if (tid < nc) {
       const int f = overflow ? (int)(mesh_first + base + tid) : p.pairs[seg_begin + base + tid];
-      stage_face(s, tid, p.face_verts, f, p.sqrt_blur, cull);
+      stage_face(s, tid, p.face_verts, p.neighbor, f, p.sqrt_blur, cull);
     }
     __syncthreads();
     for (int g = 0; g < nc; g += 32) {
@@ -245,19 +324,23 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParam
         const int j = g + __ffs(m) - 1;
         m &= m - 1;
         const float4 bx = s.box[j];
-        if (px > bx.y || px < bx.x || py > bx.w || py < bx.z) continue;  // (:94-97)
+        if (!valid || px > bx.y || px < bx.x || py > bx.w || py < bx.z) continue;  // (:94-97)
         const float4 fa = s.a[j], fb = s.b[j], fc = s.c[j];
         const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
         Hit h;
         if (!eval_pixel_face(px, py, f, fb.z, p.blur_radius, persp, clip, h)) continue;
         const int fi = __float_as_int(fb.w);
-        if (q.accepts(h.z, fi)) q.insert(h, fi);
+        if (NB) {
+          const int nb = __float_as_int(fc.w);
+          if (nb != -1 && q.offer_neighbor(h, fi, nb)) continue;
+        }
+        q.offer(h, fi, K);
       }
     }
   }
 
   if (!valid) return;
-  const int K = p.K;
+  q.sort();
   const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
   if (K == KMAX && (KMAX % 4) == 0) {
     longlong2* pf = reinterpret_cast<longlong2*>(p.pix_to_face + o);
@@ -266,14 +349,14 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParam
     float4* pb = reinterpret_cast<float4*>(p.bary + o * 3);
 #pragma unroll
     for (int k = 0; k < KMAX; k += 2) {
-      const long long i0 = q.id[k] == INT_MAX ? -1ll : (long long)q.id[k];
-      const long long i1 = q.id[k + 1] == INT_MAX ? -1ll : (long long)q.id[k + 1];
+      const long long i0 = k >= q.size ? -1ll : (long long)q.id[k];
+      const long long i1 = k + 1 >= q.size ? -1ll : (long long)q.id[k + 1];
       pf[k / 2] = make_longlong2(i0, i1);
     }
 #pragma unroll
     for (int k = 0; k < KMAX; k += 4) {
-      pz[k / 4] = make_float4(q.id[k] == INT_MAX ? -1.0f : q.z[k], q.id[k + 1] == INT_MAX ? -1.0f : q.z[k + 1],
-                              q.id[k + 2] == INT_MAX ? -1.0f : q.z[k + 2], q.id[k + 3] == INT_MAX ? -1.0f : q.z[k + 3]);
+      pz[k / 4] = make_float4(k >= q.size ? -1.0f : q.z[k], k + 1 >= q.size ? -1.0f : q.z[k + 1],
+                              k + 2 >= q.size ? -1.0f : q.z[k + 2], k + 3 >= q.size ? -1.0f : q.z[k + 3]);
       pd[k / 4] = make_float4(q.d[k], q.d[k + 1], q.d[k + 2], q.d[k + 3]);
       pb[3 * (k / 4) + 0] = make_float4(q.b0[k], q.b1[k], q.b2[k], q.b0[k + 1]);
       pb[3 * (k / 4) + 1] = make_float4(q.b1[k + 1], q.b2[k + 1], q.b0[k + 2], q.b1[k + 2]);
@@ -283,7 +366,7 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParam
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       if (k < K) {
-        const bool e = q.id[k] == INT_MAX;
+        const bool e = k >= q.size;
         p.pix_to_face[o + k] = e ? -1ll : (long long)q.id[k];
         p.zbuf[o + k] = e ? -1.0f : q.z[k];
         p.dists[o + k] = q.d[k];
@@ -296,8 +379,8 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParam
 }
 
 // ------------------------------------------------------------------------------------------------
-// Large-K path (8 < K <= 150): only the sorted (z, face) keys are kept (thread-local array); the
-// payload of the final winners is recomputed (same arithmetic, so identical values).
+// Large-K path (8 < K <= 150): the same queue in thread-local arrays holding only (z, face, dist); the
+// barycentrics of the final winners are recomputed (same arithmetic, so identical values).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const FineParams p) {
   __shared__ FaceChunk s;
@@ -319,16 +402,17 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const Fine
   const bool persp = p.persp != 0, clip = p.clip != 0, cull = p.cull != 0;
   const int K = p.K;
 
-  float qz[B200R_MAX_K];
+  float qz[B200R_MAX_K], qd[B200R_MAX_K];
   int qi[B200R_MAX_K];
-  int qn = 0;
+  int qn = 0, q_max_idx = -1;
+  float q_max_z = -1000.0f;
 
   for (int base = 0; base < count; base += CHUNK) {
     const int nc = min(CHUNK, count - base);
     __syncthreads();
     if (tid < nc) {
       const int f = overflow ? (int)(mesh_first + base + tid) : p.pairs[seg_begin + base + tid];
-      stage_face(s, tid, p.face_verts, f, p.sqrt_blur, cull);
+      stage_face(s, tid, p.face_verts, p.neighbor, f, p.sqrt_blur, cull);
     }
     __syncthreads();
     for (int g = 0; g < nc; g += 32) {
@@ -342,25 +426,67 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const Fine
         const int j = g + __ffs(m) - 1;
         m &= m - 1;
         const float4 bx = s.box[j];
-        if (px > bx.y || px < bx.x || py > bx.w || py < bx.z) continue;
+        if (!valid || px > bx.y || px < bx.x || py > bx.w || py < bx.z) continue;
         const float4 fa = s.a[j], fb = s.b[j], fc = s.c[j];
         const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
         Hit h;
         if (!eval_pixel_face(px, py, f, fb.z, p.blur_radius, persp, clip, h)) continue;
         const int fi = __float_as_int(fb.w);
-        if (qn == K && !key_less(h.z, fi, qz[K - 1], qi[K - 1])) continue;
-        int i = qn < K ? qn++ : K - 1;
-        while (i > 0 && key_less(h.z, fi, qz[i - 1], qi[i - 1])) {
-          qz[i] = qz[i - 1];
-          qi[i] = qi[i - 1];
-          --i;
+        const int nb = __float_as_int(fc.w);
+        int at = -1;
+        if (nb != -1)
+          for (int i = 0; i < qn; ++i)
+            if (qi[i] == nb) {
+              at = i;
+              break;
+            }
+        if (at >= 0) {  // (:201-215)
+          if (fabsf(h.dist) < fabsf(qd[at])) {
+            qz[at] = h.z;
+            qi[at] = fi;
+            qd[at] = h.dist;
+            if (h.z > q_max_z) {
+              q_max_z = h.z;
+              q_max_idx = at;
+            }
+          }
+        } else if (qn < K) {  // (:218-225)
+          qz[qn] = h.z;
+          qi[qn] = fi;
+          qd[qn] = h.dist;
+          if (h.z > q_max_z) {
+            q_max_z = h.z;
+            q_max_idx = qn;
+          }
+          ++qn;
+        } else if (h.z < q_max_z) {  // (:226-236)
+          qz[q_max_idx] = h.z;
+          qi[q_max_idx] = fi;
+          qd[q_max_idx] = h.dist;
+          q_max_z = h.z;
+          for (int i = 0; i < K; ++i)
+            if (qz[i] > q_max_z) {
+              q_max_z = qz[i];
+              q_max_idx = i;
+            }
         }
-        qz[i] = h.z;
-        qi[i] = fi;
       }
     }
   }
   if (!valid) return;
+  // sort by (z, face): insertion sort, keys unique
+  for (int i = 1; i < qn; ++i) {
+    const float tz = qz[i];
+    const int ti = qi[i];
+    int j = i - 1;
+    while (j >= 0 && key_less(tz, ti, qz[j], qi[j])) {
+      qz[j + 1] = qz[j];
+      qi[j + 1] = qi[j];
+      --j;
+    }
+    qz[j + 1] = tz;
+    qi[j + 1] = ti;
+  }
   const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
   for (int k = 0; k < K; ++k) {
     Hit h = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
@@ -559,9 +685,6 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
   if (K > B200R_MAX_K) return fail(B200R_ERR_INVALID_ARGUMENT, "Must have points_per_pixel <= 150");
   if (F < 0 || N < 0 || H < 0 || W < 0 || K < 0) return fail(B200R_ERR_INVALID_ARGUMENT, "negative size");
   if (F > INT_MAX) return fail(B200R_ERR_INVALID_ARGUMENT, "more than 2^31-1 packed faces are not supported");
-  if (neighbor != nullptr)
-    return fail(B200R_ERR_INVALID_ARGUMENT,
-                "clipped_faces_neighbor_idx with non -1 entries is not supported by this build yet");
   if ((int64_t)N * H * W * K == 0) return B200R_OK;  // empty outputs (rasterize_meshes.cu:793-796)
   const int TY = div_up(H, TILE), TX = div_up(W, TILE);
   if (TY > 0xFFFE || TX > 0xFFFE) return fail(B200R_ERR_INVALID_ARGUMENT, "image too large");
@@ -588,8 +711,13 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
                                                                     ws.capacity);
     B200R_LAUNCHED("tile_fill_kernel");
   }
+  if (ntiles > 0) {
+    tile_sort_kernel<<<(unsigned)ntiles, SORT_THREADS, 0, stream>>>(ws.tile_offset, ws.pairs, ws.capacity);
+    B200R_LAUNCHED("tile_sort_kernel");
+  }
   FineParams p;
   p.face_verts = face_verts;
+  p.neighbor = neighbor;
   p.first = first;
   p.num = num;
   p.tile_offset = ws.tile_offset;
@@ -600,16 +728,24 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
   p.persp = perspective_correct; p.clip = clip_barycentric_coords; p.cull = cull_backfaces;
   p.pix_to_face = pix_to_face; p.zbuf = zbuf; p.bary = bary; p.dists = dists;
   const unsigned grid = (unsigned)ntiles;
+#define B200R_FINE(KM)                                                          \
+  do {                                                                         \
+    if (neighbor)                                                              \
+      mesh_fine_kernel<KM, true><<<grid, TILE_THREADS, 0, stream>>>(p);        \
+    else                                                                       \
+      mesh_fine_kernel<KM, false><<<grid, TILE_THREADS, 0, stream>>>(p);       \
+  } while (0)
   if (K <= 1)
-    mesh_fine_kernel<1><<<grid, TILE_THREADS, 0, stream>>>(p);
+    B200R_FINE(1);
   else if (K <= 2)
-    mesh_fine_kernel<2><<<grid, TILE_THREADS, 0, stream>>>(p);
+    B200R_FINE(2);
   else if (K <= 4)
-    mesh_fine_kernel<4><<<grid, TILE_THREADS, 0, stream>>>(p);
+    B200R_FINE(4);
   else if (K <= 8)
-    mesh_fine_kernel<8><<<grid, TILE_THREADS, 0, stream>>>(p);
+    B200R_FINE(8);
   else
     mesh_fine_bigk_kernel<<<grid, TILE_THREADS, 0, stream>>>(p);
+#undef B200R_FINE
   B200R_LAUNCHED("mesh_fine_kernel");
   return B200R_OK;
 }

@@ -50,37 +50,76 @@ __global__ void __launch_bounds__(SETUP_POINTS)
   rect[pi] = rc;
 }
 
-__device__ __forceinline__ bool pkey_less(float za, int ia, float zb, int ib) {
-  return za < zb || (za == zb && ia < ib);
-}
-
+// The K nearest points of one pixel: the reference's queue (rasterize_points.cu:61-79) restated for
+// registers -- an UNSORTED array of K slots plus the tracked maximum z; a hit fills the next free slot or,
+// when full and pz < q_max_z, overwrites the tracked maximum, which is then searched again.  Points arrive
+// in ascending index order (sorted tile lists), so tie behaviour equals the reference's naive kernel.
 template <int KMAX>
 struct PTopK {
   float z[KMAX];
   int id[KMAX];
   float d[KMAX];
+  int size;
+  float max_z;
+  int max_idx;
   __device__ __forceinline__ void init() {
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
-      z[i] = FLT_MAX;
-      id[i] = INT_MAX;
+      z[i] = -1.0f;
+      id[i] = -1;
       d[i] = -1.0f;
     }
+    size = 0;
+    max_z = -1000.0f;
+    max_idx = -1;
   }
-  __device__ __forceinline__ bool accepts(float pz, int p) const {
-    return pkey_less(pz, p, z[KMAX - 1], id[KMAX - 1]);
+  __device__ __forceinline__ void put(int slot, float pz, int p, float d2) {
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+      const bool w = i == slot;
+      z[i] = w ? pz : z[i];
+      id[i] = w ? p : id[i];
+      d[i] = w ? d2 : d[i];
+    }
   }
-  __device__ __forceinline__ void insert(float pz, int p, float d2) {
-    bool c[KMAX];
+  __device__ __forceinline__ void offer(float pz, int p, float d2, int K) {
+    if (size < K) {
+      put(size, pz, p, d2);
+      if (pz > max_z) {
+        max_z = pz;
+        max_idx = size;
+      }
+      ++size;
+    } else if (pz < max_z) {
+      put(max_idx, pz, p, d2);
+      max_z = pz;
 #pragma unroll
-    for (int i = 0; i < KMAX; ++i) c[i] = pkey_less(pz, p, z[i], id[i]);
+      for (int i = 0; i < KMAX; ++i) {
+        if (i < K && z[i] > max_z) {
+          max_z = z[i];
+          max_idx = i;
+        }
+      }
+    }
+  }
+  // BubbleSort on z only (rasterize_points.cu:26-28): a STABLE sort, so z-ties keep slot order.  An
+  // odd-even transposition network with a strict compare is stable too and gives the same permutation.
+  __device__ __forceinline__ void sort() {
 #pragma unroll
-    for (int i = KMAX - 1; i >= 0; --i) {
-      const int j = i > 0 ? i - 1 : 0;
-      const bool up = i > 0 && c[j];
-      z[i] = up ? z[j] : (c[i] ? pz : z[i]);
-      id[i] = up ? id[j] : (c[i] ? p : id[i]);
-      d[i] = up ? d[j] : (c[i] ? d2 : d[i]);
+    for (int i = 0; i < KMAX; ++i)
+      if (i >= size) z[i] = FLT_MAX;
+#pragma unroll
+    for (int r = 0; r < KMAX; ++r) {
+#pragma unroll
+      for (int i = r & 1; i + 1 < KMAX; i += 2) {
+        if (z[i + 1] < z[i]) {
+          float t;
+          int ti;
+          t = z[i]; z[i] = z[i + 1]; z[i + 1] = t;
+          ti = id[i]; id[i] = id[i + 1]; id[i + 1] = ti;
+          t = d[i]; d[i] = d[i + 1]; d[i + 1] = t;
+        }
+      }
     }
   }
 };
@@ -167,7 +206,8 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_kernel(const PointFi
   float lz[KMAX > 0 ? 1 : B200R_MAX_K];
   int li[KMAX > 0 ? 1 : B200R_MAX_K];
   float ld[KMAX > 0 ? 1 : B200R_MAX_K];
-  int ln = 0;
+  int ln = 0, l_max_idx = -1;
+  float l_max_z = -1000.0f;
   if (KMAX > 0) q.init();
 
   for (int base = 0; base < count; base += PCHUNK) {
@@ -192,22 +232,29 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_kernel(const PointFi
         // CheckPixelInsidePoint (rasterize_points.cu:49-60): dist2 = fma(dy, dy, rn(dx*dx)) < rn(r*r)
         const float dx = fsub(px, r.x), dy = fsub(py, r.y);
         const float d2 = sqnorm2(dx, dy);
-        if (!valid || !(d2 < r.w) || r.z < 0.0f) continue;
+        if (!valid || r.z < 0.0f || !(d2 < r.w)) continue;
         const int pi = s.id[j];
         if (KMAX > 0) {
-          if (q.accepts(r.z, pi)) q.insert(r.z, pi, d2);
-        } else {
-          if (ln == K && !pkey_less(r.z, pi, lz[K - 1], li[K - 1])) continue;
-          int i = ln < K ? ln++ : K - 1;
-          while (i > 0 && pkey_less(r.z, pi, lz[i - 1], li[i - 1])) {
-            lz[i] = lz[i - 1];
-            li[i] = li[i - 1];
-            ld[i] = ld[i - 1];
-            --i;
+          q.offer(r.z, pi, d2, K);
+        } else if (ln < K) {
+          lz[ln] = r.z;
+          li[ln] = pi;
+          ld[ln] = d2;
+          if (r.z > l_max_z) {
+            l_max_z = r.z;
+            l_max_idx = ln;
           }
-          lz[i] = r.z;
-          li[i] = pi;
-          ld[i] = d2;
+          ++ln;
+        } else if (r.z < l_max_z) {
+          lz[l_max_idx] = r.z;
+          li[l_max_idx] = pi;
+          ld[l_max_idx] = d2;
+          l_max_z = r.z;
+          for (int i = 0; i < K; ++i)
+            if (lz[i] > l_max_z) {
+              l_max_z = lz[i];
+              l_max_idx = i;
+            }
         }
       }
     }
@@ -215,16 +262,31 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_kernel(const PointFi
   if (!valid) return;
   const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
   if (KMAX > 0) {
+    q.sort();
 #pragma unroll
     for (int k = 0; k < QN; ++k) {
       if (k < K) {
-        const bool e = q.id[k] == INT_MAX;
+        const bool e = k >= q.size;
         p.idx[o + k] = e ? -1 : q.id[k];
         p.zbuf[o + k] = e ? -1.0f : q.z[k];
         p.dists[o + k] = q.d[k];
       }
     }
   } else {
+    for (int i = 1; i < ln; ++i) {  // stable insertion sort on z only
+      const float tz = lz[i], td = ld[i];
+      const int ti = li[i];
+      int j = i - 1;
+      while (j >= 0 && tz < lz[j]) {
+        lz[j + 1] = lz[j];
+        li[j + 1] = li[j];
+        ld[j + 1] = ld[j];
+        --j;
+      }
+      lz[j + 1] = tz;
+      li[j + 1] = ti;
+      ld[j + 1] = td;
+    }
     for (int k = 0; k < K; ++k) {
       p.idx[o + k] = k < ln ? li[k] : -1;
       p.zbuf[o + k] = k < ln ? lz[k] : -1.0f;
@@ -302,6 +364,8 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
                                                                     ws.capacity);
     B200R_LAUNCHED("tile_fill_kernel");
   }
+  tile_sort_kernel<<<(unsigned)ntiles, SORT_THREADS, 0, stream>>>(ws.tile_offset, ws.pairs, ws.capacity);
+  B200R_LAUNCHED("tile_sort_kernel");
   PointFineParams p;
   p.points = points; p.radius = radius; p.first = first; p.num = num;
   p.tile_offset = ws.tile_offset; p.pairs = ws.pairs; p.capacity = ws.capacity;

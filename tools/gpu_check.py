@@ -47,7 +47,7 @@ def mesh_case(fv, first, num, H, W, blur, K, persp, clip, cull, do_oracle=True):
     torch.cuda.synchronize()
     if do_oracle:
         o = oracle.rasterize_meshes(fv.numpy(), first.numpy(), num.numpy(), (H, W), blur, K, persp, clip, cull,
-                                    arith=oracle.ARITH_CUDA, select=oracle.SELECT_CPU)
+                                    arith=oracle.ARITH_CUDA, select=oracle.SELECT_CUDA)
         # output order (idx, z, bary, dists) for both
         cmp("mine vs C-oracle(cuda arith)", mine, o)
     if ref is not None:
@@ -74,6 +74,38 @@ def mesh_case(fv, first, num, H, W, blur, K, persp, clip, cull, do_oracle=True):
         rg = ref.rasterize_meshes_backward(d[0], mine[0], gz, gb, gd, bool(persp), bool(clip))
         diff = (mg - rg).abs()
         print("  backward vs ref-CUDA : max abs %.3e  max rel %.3e" % (diff.max().item(), (diff / rg.abs().clamp_min(1e-3)).max().item()), flush=True)
+
+
+def points_case(P, N, H, W, K, seed, rlo=0.02, rhi=0.1):
+    print("points case P=%d N=%d %dx%d K=%d" % (P, N, H, W, K), flush=True)
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.rand(P, 3, generator=g) * 2 - 1
+    pts[:, 2] = torch.rand(P, generator=g) * 2 - 0.2
+    pts[::7, 2] = 0.5  # z ties
+    rad = torch.rand(P, generator=g) * (rhi - rlo) + rlo
+    per = P // N
+    first = (torch.arange(N) * per).long()
+    num = torch.full((N,), per).long(); num[-1] = P - first[-1]
+    d = [t.to(dev) for t in (pts, first, num, rad)]
+    mine = _C.rasterize_points(d[0], d[1], d[2], (H, W), d[3], K, 0, 0)
+    o = oracle.rasterize_points(pts.numpy(), first.numpy(), num.numpy(), (H, W), rad.numpy(), K,
+                                arith=oracle.ARITH_CUDA, select=oracle.SELECT_CUDA)
+    cmp("mine vs C-oracle(cuda)", mine, o)
+    if ref is not None:
+        rn = ref.rasterize_points(d[0], d[1], d[2], (H, W), d[3], K, 0, 0)
+        cmp("mine vs ref-CUDA naive", mine, rn)
+        if max(H, W) / 16 < 22:
+            rf = ref.rasterize_points(d[0], d[1], d[2], (H, W), d[3], K, 16, 20000)
+            cmp("mine vs ref-CUDA coarse+fine", mine, rf)
+    g2 = torch.Generator().manual_seed(231)
+    gz = torch.randn(mine[1].shape, generator=g2).to(dev); gd = torch.randn(mine[2].shape, generator=g2).to(dev)
+    mg = _C.rasterize_points_backward(d[0], mine[0], gz, gd)
+    og = oracle.rasterize_points_backward(pts.numpy(), mine[0].cpu().numpy(), gz.cpu().numpy(), gd.cpu().numpy(), arith=oracle.ARITH_CUDA)
+    diff = np.abs(mg.cpu().numpy() - og)
+    print("  backward vs C-oracle: max abs %.3e (|g|max %.3e)" % (diff.max(), np.abs(og).max()), flush=True)
+    if ref is not None:
+        rg = ref.rasterize_points_backward(d[0], mine[0], gz, gd)
+        print("  backward vs ref-CUDA : max abs %.3e" % (mg - rg).abs().max().item(), flush=True)
 
 
 def timeit(fn, iters=10, warm=3):
@@ -108,6 +140,25 @@ if __name__ == "__main__":
     mesh_case(synthetic.face_verts_of(m), m.mesh_to_faces_packed_first_idx(), m.num_faces_per_mesh(), 256, 256, 1e-4, 8, 0, 0, 0)
     m = synthetic.ico_sphere_batch(1, 4)
     mesh_case(synthetic.face_verts_of(m), m.mesh_to_faces_packed_first_idx(), m.num_faces_per_mesh(), 64, 64, 0.0, 1, 0, 0, 0)
+
+    for (P, N, H, W, K) in [(2000, 2, 32, 48, 5), (5000, 1, 64, 64, 10), (3000, 3, 40, 24, 1), (3000, 1, 50, 50, 40),
+                            (20000, 2, 128, 128, 8)]:
+        points_case(P, N, H, W, K, seed=P + K)
+    # C3-like timing
+    pc = synthetic.random_pointclouds(8, 100000, seed=0)
+    pts = pc.points_packed().to(dev); pf = pc.cloud_to_packed_first_idx().to(dev); pn = pc.num_points_per_cloud().to(dev)
+    rad = torch.full((pts.shape[0],), 0.01, device=dev)
+    out = _C.rasterize_points(pts, pf, pn, (512, 512), rad, 10, 0, 0)
+    g = torch.Generator(device=dev).manual_seed(231)
+    gz = torch.randn(out[1].shape, generator=g, device=dev); gd = torch.randn(out[2].shape, generator=g, device=dev)
+    tf = timeit(lambda: _C.rasterize_points(pts, pf, pn, (512, 512), rad, 10, 0, 0))
+    tb = timeit(lambda: _C.rasterize_points_backward(pts, out[0], gz, gd))
+    print("C3 8x100k pts 512^2 K=10 r=0.01: fwd %.3f ms bwd %.3f ms -> %.1f frames/s ; hits %d" % (tf, tb, 8e3 / (tf + tb), int((out[0] >= 0).sum())), flush=True)
+    if ref is not None and not quick:
+        trf = timeit(lambda: ref.rasterize_points(pts, pf, pn, (512, 512), rad, 10, 32, 20000), iters=3, warm=1)
+        trb = timeit(lambda: ref.rasterize_points_backward(pts, out[0], gz, gd), iters=3, warm=1)
+        print("   ref-CUDA: fwd %.3f ms bwd %.3f ms -> %.1f frames/s" % (trf, trb, 8e3 / (trf + trb)), flush=True)
+        cmp("C3 mine vs ref-CUDA fine", out, ref.rasterize_points(pts, pf, pn, (512, 512), rad, 10, 32, 20000))
 
     # ---- timing: north-star config
     m = synthetic.torus_batch(8, 187, 187, seed=0)
