@@ -1,0 +1,477 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the rasterizer hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path on the host cores
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+Workload ("ns", the configuration the metric is quoted on): a batch of 8 meshes of 69,938 faces each
+(seeded tori in NDC), 512 x 512, faces_per_pixel = 8, blur_radius = 0, forward + backward with dense
+upstream gradients on zbuf / bary / dists.  One "step" = one forward+backward pass over the batch.
+Multi-GPU is weak scaling: every rank renders its own batch of 8 (no data-path collective); `value` is
+frames of all ranks / max-over-ranks device time.
+
+Prints ONE JSON line (see README / the task contract for the keys).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rasterize frames/sec (fwd+bwd) 512^2 K=8"
+UNIT = "frames/s"
+WORKLOADS = {
+    # name: (meshes per rank, torus rings, torus sides, H, W, K, blur)
+    "ns": (8, 187, 187, 512, 512, 8, 0.0),
+    "c2": (8, 54, 54, 256, 256, 8, 1e-4),
+    "tiny": (2, 24, 24, 64, 64, 4, 0.0),
+}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_bytes(kernel):
+    """dram read+write bytes per launch of `kernel` from the committed ncu capture summary, or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)["kernels"][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        return {
+            "sm_mhz": float(np.median(self.samples)) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+
+def strip_transform(face_verts, y0, hs, H, W, blur):
+    """Maps rows [y0, y0+hs) of an H x W render onto a full hs x W render (same pixel-face tests):
+    uniform scale s = H / hs about the strip centre; squared distances (blur) scale by s^2."""
+    s = float(H) / float(hs)
+    fv = face_verts.clone()
+    fv[..., 0] *= s
+    fv[..., 1] = fv[..., 1] * s - float(H - 2 * y0 - hs) / float(hs)
+    return fv, blur * s * s
+
+
+def cpu_sample(face_verts, n_faces, H, W, K, blur, hs, use_ref):
+    """Forward+backward of rows [y0, y0+hs) of frame 0 on the host CPU.  Returns (seconds, frames)."""
+    import oracle
+    fv0 = face_verts[:n_faces].contiguous()
+    first = torch.zeros(1, dtype=torch.int64)
+    num = torch.tensor([n_faces], dtype=torch.int64)
+    y0 = (H - hs) // 2
+    g = torch.Generator().manual_seed(231)
+    if use_ref is not None:
+        fvs, blur_s = strip_transform(fv0, y0, hs, H, W, blur)
+        nb = torch.full((n_faces,), -1, dtype=torch.int64)
+        t0 = time.perf_counter()
+        out = use_ref.rasterize_meshes(fvs, first, num, nb, (hs, W), blur_s, K, 0, 0, False, False, False)
+        gz, gb, gd = (torch.randn(o.shape, generator=g) for o in out[1:])
+        use_ref.rasterize_meshes_backward(fvs, out[0], gz, gb, gd, False, False)
+        dt = time.perf_counter() - t0
+    else:
+        fvn = fv0.numpy()
+        t0 = time.perf_counter()
+        out = oracle.rasterize_meshes(fvn, first.numpy(), num.numpy(), (H, W), blur, K, rows=(y0, y0 + hs))
+        gz, gb, gd = (torch.randn(o.shape, generator=g).numpy() for o in out[1:])
+        oracle.rasterize_meshes_backward(fvn, out[0], gz, gb, gd, rows=(y0, y0 + hs))
+        dt = time.perf_counter() - t0
+    return dt, float(hs) / float(H)
+
+
+def load_cpu_reference():
+    import oracle
+    ref = oracle.load_reference(cuda=False)
+    if ref is not None:
+        torch.set_num_threads(os.cpu_count() or 1)
+        return ref, "reference", torch.get_num_threads()
+    oracle.build()
+    return None, "port", os.cpu_count() or 1
+
+
+def pick_strip_rows(face_verts, n_faces, H, W, K, blur, ref, budget_s, steps):
+    """Calibrate on an 8-row strip, then size the strip so that `steps` samples fit in `budget_s`."""
+    dt, _ = cpu_sample(face_verts, n_faces, H, W, K, blur, 8, ref)
+    per_row = dt / 8.0
+    rows = int(budget_s / max(steps, 1) / max(per_row, 1e-6))
+    rows = max(8, min(H, (rows // 8) * 8))
+    return rows
+
+
+# ------------------------------------------------------------------------------------------- main
+
+def build_workload(name, rank):
+    from pytorch3d_b200 import synthetic
+    nm, rings, sides, H, W, K, blur = WORKLOADS[name]
+    meshes = synthetic.torus_batch(nm, rings, sides, seed=rank)
+    return meshes, (nm, rings * sides * 2, H, W, K, blur)
+
+
+def config_dict(name, world, nm, F1, H, W, K, blur):
+    return {
+        "workload": "%s: %d meshes/GPU x %d faces (seeded tori in NDC), %dx%d, faces_per_pixel=%d, "
+                    "blur_radius=%g, fwd+bwd" % (name, nm, F1, H, W, K, blur),
+        "meshes_per_gpu": nm, "faces_per_mesh": F1, "image_size": [H, W], "faces_per_pixel": K,
+        "blur_radius": blur, "global_batch": nm * world, "parallelism": "batch-sharded x%d (no collective)" % world,
+        "l2": "no explicit flush: each step streams ~%.0f MB of fragments + upstream gradients per GPU "
+              "(>> 126 MB L2); the %.0f MB of face_verts stay L2-resident as in a real optimisation loop"
+              % (nm * H * W * K * 48 / 1e6, nm * F1 * 36 / 1e6),
+    }
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    name = args.workload
+    meshes, (nm, F1, H, W, K, blur) = build_workload(name, 0)
+    from pytorch3d_b200 import synthetic
+    fv = synthetic.face_verts_of(meshes)
+    ref, kind, cores = load_cpu_reference()
+    rows = pick_strip_rows(fv, F1, H, W, K, blur, ref, budget_s=150.0, steps=args.steps + args.warmup)
+    for _ in range(args.warmup):
+        cpu_sample(fv, F1, H, W, K, blur, rows, ref)
+    t_total, frames = 0.0, 0.0
+    for _ in range(args.steps):
+        dt, fr = cpu_sample(fv, F1, H, W, K, blur, rows, ref)
+        t_total += dt
+        frames += fr
+    value = frames / t_total
+    sample = "rows [%d,%d) of frame 0 (%d of %d rows, all %d faces) per step, fwd+bwd, %s" % (
+        (H - rows) // 2, (H - rows) // 2 + rows, rows, H, F1,
+        "reference C++ CPU ops (oracle/_ref/ref_raster_cpu.so, strip mapped onto a %dx%d render)" % (rows, W)
+        if ref is not None else "C port (oracle/raster_oracle.c)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(name, world, nm, F1, H, W, K, blur),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+class _DeviceMeshes:
+    """Packed batch whose verts/faces were just copied to the device (the e2e step's input)."""
+
+    def __init__(self, verts, faces, first, num, max_f):
+        self._v, self._f, self._first, self._num, self._F = verts, faces, first, num, max_f
+
+    def verts_packed(self):
+        return self._v
+
+    def faces_packed(self):
+        return self._f
+
+    def mesh_to_faces_packed_first_idx(self):
+        return self._first
+
+    def num_faces_per_mesh(self):
+        return self._num
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch.distributed as dist
+
+    from pytorch3d_b200 import _C, _lib, rasterize_meshes, synthetic
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    name = args.workload
+    meshes, (nm, F1, H, W, K, blur) = build_workload(name, rank)
+    fv_host = synthetic.face_verts_of(meshes)
+    fv = fv_host.to(dev)
+    first = meshes.mesh_to_faces_packed_first_idx().to(dev)
+    num = meshes.num_faces_per_mesh().to(dev)
+    nb = torch.full((fv.shape[0],), -1, dtype=torch.int64, device=dev)
+    nb._b200_all_minus_one = True
+    size = (H, W)
+
+    def fwd():
+        return _C.rasterize_meshes(fv, first, num, nb, size, blur, K, 0, 0, False, False, False)
+
+    frag = fwd()
+    g = torch.Generator(device=dev).manual_seed(231)
+    gz = torch.randn(frag[1].shape, generator=g, device=dev)
+    gb = torch.randn(frag[2].shape, generator=g, device=dev)
+    gd = torch.randn(frag[3].shape, generator=g, device=dev)
+
+    def step():
+        f = fwd()
+        return _C.rasterize_meshes_backward(fv, f[0], gz, gb, gd, False, False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident throughput (value)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = lib.b200r_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    launches = lib.b200r_kernel_launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * nm * args.steps / (ms_max * 1e-3)
+
+    # ---------------- per-kernel durations (roofline), same steps with phase events on the launch stream
+    lib.b200r_set_profiling(1)
+    import ctypes
+    buf = (ctypes.c_float * 3)()
+    ph = np.zeros(3)
+    n_prof = max(3, min(args.steps, 20))
+    for _ in range(n_prof):
+        step()
+        lib.b200r_last_phase_ms(buf)
+        ph += np.array(list(buf))
+    lib.b200r_set_profiling(0)
+    ph /= n_prof
+    peak, peak_src = measured_peak_gbs()
+    slots = nm * H * W * K
+    fine_bytes = 28.0 * slots + 36.0 * nm * F1            # fwd: write 28 B/slot, read face_verts once
+    bwd_bytes = 28.0 * slots + 72.0 * nm * F1             # bwd: read 28 B/slot + face_verts, write grads
+    fine_gbs = fine_bytes / (ph[1] * 1e-3) / 1e9 if ph[1] > 0 else 0.0
+    roofline = {
+        "kernel": "mesh_fine_kernel<8>", "bound": "hbm", "achieved": fine_gbs, "peak": peak, "unit": "GB/s",
+        "frac": fine_gbs / peak, "traffic": ncu_traffic_bytes("mesh_fine_kernel"),
+        "algorithmic_bytes_per_launch": fine_bytes, "ms_per_launch": float(ph[1]), "peak_source": peak_src,
+        "other_kernels": {
+            "binning(setup+scan+fill+sort)": {"ms": float(ph[0])},
+            "mesh_backward_kernel": {"ms": float(ph[2]), "algorithmic_bytes": bwd_bytes,
+                                     "achieved": bwd_bytes / (ph[2] * 1e-3) / 1e9 if ph[2] > 0 else 0.0,
+                                     "frac": (bwd_bytes / (ph[2] * 1e-3) / 1e9 / peak) if ph[2] > 0 else 0.0},
+        },
+        "step": {"algorithmic_bytes": fine_bytes + bwd_bytes,
+                 "achieved": (fine_bytes + bwd_bytes) * args.steps / (ms * 1e-3) / 1e9,
+                 "frac": (fine_bytes + bwd_bytes) * args.steps / (ms * 1e-3) / 1e9 / peak},
+    }
+
+    # ---------------- end to end through the public API with HOST inputs (pinned) and host results
+    verts_h = meshes.verts_packed().pin_memory()
+    faces_h = meshes.faces_packed().pin_memory()
+    grad_h = torch.empty_like(verts_h).pin_memory()
+    loss_h = torch.empty((), dtype=torch.float32).pin_memory()
+    max_f = int(meshes.num_faces_per_mesh().max())
+
+    def e2e_step():
+        v = verts_h.to(dev, non_blocking=True).requires_grad_(True)
+        f = faces_h.to(dev, non_blocking=True)
+        m = _DeviceMeshes(v, f, first, num, max_f)
+        p2f, zbuf, bary, dists = rasterize_meshes(m, size, blur_radius=blur, faces_per_pixel=K)
+        loss = (zbuf * gz).sum() + (bary * gb).sum() + (dists * gd).sum()
+        loss.backward()
+        grad_h.copy_(v.grad, non_blocking=True)
+        loss_h.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return float(loss_h)
+
+    n_e2e = max(3, min(args.steps, 50))
+    for _ in range(min(args.warmup, 5) or 1):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e = {
+        "value": world * nm * n_e2e / float(dt.item()), "unit": UNIT,
+        "h2d_bytes_per_step": int(verts_h.numel() * 4 + faces_h.numel() * 8),
+        "d2h_bytes_per_step": int(grad_h.numel() * 4 + 4),
+        "steps": n_e2e,
+        "what": "pytorch3d_b200.rasterize_meshes(meshes) + loss.backward(): verts/faces H2D from pinned host "
+                "memory, gradient w.r.t. verts and the loss D2H, every step; fragments stay on the device",
+    }
+
+    # ---------------- the same through the host-buffer C ABI (all fragments to the host)
+    e2e_abi = None
+    if rank == 0 and not args.skip_host_abi:
+        try:
+            e2e_abi = host_abi_e2e(lib, fv_host, meshes, nm, F1, H, W, K, blur)
+        except Exception as ex:  # never fatal for the headline line
+            e2e_abi = {"error": str(ex)}
+
+    # ---------------- CPU baseline (rank 0, N == 1 only): bounded sample on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        ref, kind, cores = load_cpu_reference()
+        rows = pick_strip_rows(fv_host, F1, H, W, K, blur, ref, budget_s=15.0, steps=1)
+        dtc, fr = cpu_sample(fv_host, F1, H, W, K, blur, rows, ref)
+        cpu = {"value": fr / dtc, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "rows [%d,%d) of frame 0 (%d of %d rows, all %d faces), fwd+bwd, %.1f s of CPU work" % (
+                   (H - rows) // 2, (H - rows) // 2 + rows, rows, H, F1, dtc)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(name, world, nm, F1, H, W, K, blur),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline,
+            "cpu_baseline": cpu, "e2e_host_abi": e2e_abi, "impl": "pytorch3d_b200",
+        }
+        print(json.dumps(line), flush=True)
+
+
+def host_abi_e2e(lib, fv_host, meshes, nm, F1, H, W, K, blur, steps=3):
+    """forward_host + backward_host of the C ABI: every buffer is host memory (pinned)."""
+    slots = nm * H * W * K
+    fv = fv_host.contiguous().pin_memory()
+    first = meshes.mesh_to_faces_packed_first_idx().pin_memory()
+    num = meshes.num_faces_per_mesh().pin_memory()
+    p2f = torch.empty(slots, dtype=torch.int64).pin_memory()
+    z = torch.empty(slots, dtype=torch.float32).pin_memory()
+    b = torch.empty(slots * 3, dtype=torch.float32).pin_memory()
+    d = torch.empty(slots, dtype=torch.float32).pin_memory()
+    g = torch.Generator().manual_seed(231)
+    gz = torch.randn(slots, generator=g).pin_memory()
+    gb = torch.randn(slots * 3, generator=g).pin_memory()
+    gd = torch.randn(slots, generator=g).pin_memory()
+    out = torch.empty_like(fv).pin_memory()
+    F = fv.shape[0]
+
+    def once():
+        rc = lib.b200r_rasterize_meshes_forward_host(fv.data_ptr(), F, first.data_ptr(), num.data_ptr(), None, nm, H,
+                                                     W, blur, K, 0, 0, 0, p2f.data_ptr(), z.data_ptr(), b.data_ptr(),
+                                                     d.data_ptr())
+        assert rc == 0, lib.b200r_last_error()
+        rc = lib.b200r_rasterize_meshes_backward_host(fv.data_ptr(), F, p2f.data_ptr(), gz.data_ptr(), gb.data_ptr(),
+                                                      gd.data_ptr(), nm, H, W, K, 0, 0, out.data_ptr())
+        assert rc == 0, lib.b200r_last_error()
+
+    once()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        once()
+    dt = time.perf_counter() - t0
+    return {"value": nm * steps / dt, "unit": UNIT, "steps": steps,
+            "h2d_bytes_per_step": int(F * 36 * 2 + nm * 16 + slots * (8 + 20)),
+            "d2h_bytes_per_step": int(slots * 28 + F * 36),
+            "what": "b200r_rasterize_meshes_forward_host + _backward_host: all Fragments returned to host memory and "
+                    "all upstream gradients read from host memory (PCIe-bound)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ns", choices=sorted(WORKLOADS))
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-host-abi", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -153,6 +153,16 @@ int b200r_rasterize_points_backward_host(const float* points, int64_t P, const i
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 int64_t b200r_kernel_launch_count(void);
 
+/*
+ * Phase timing for bench.py's roofline line.  When enabled, the forward / backward entry points record
+ * CUDA events on the caller's stream around their phases; b200r_last_phase_ms synchronises on those
+ * events and returns the durations of the most recent call on this thread:
+ *   out[0] = binning (setup+count, scan, fill, sort)   out[1] = fine kernel   out[2] = backward kernel
+ * (entries of phases that did not run are 0).  Disabled by default; adds no work when disabled.
+ */
+void b200r_set_profiling(int32_t enabled);
+int b200r_last_phase_ms(float out[3]);
+
 #ifdef __cplusplus
 }
 #endif

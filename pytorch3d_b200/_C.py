@@ -18,6 +18,11 @@ from . import _lib
 
 kMaxPointsPerPixel = 150  # rasterization_utils.cuh:48
 
+# Capacity (in (tile, element) pairs) of the bin lists; 0 = library default.  Results never depend on it:
+# tiles whose list does not fit fall back to testing every element of their mesh / cloud.  Tests lower it
+# to exercise that path.
+PAIR_CAPACITY = 0
+
 
 def _ptr(t):
     return t.data_ptr() if t is not None and t.numel() > 0 else None
@@ -90,13 +95,13 @@ def rasterize_meshes(
         dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
         if pix_to_face.numel() == 0:
             return pix_to_face, zbuf, bary, dists
-        ws_bytes = lib.b200r_rasterize_meshes_workspace_bytes(F, N, H, W, 0)
+        ws_bytes = lib.b200r_rasterize_meshes_workspace_bytes(F, N, H, W, PAIR_CAPACITY)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         _lib.check(lib.b200r_rasterize_meshes_forward(
             _ptr(fv), F, _ptr(first), _ptr(num), _ptr(nb), N, H, W, float(blur_radius), K, int(bin_size),
             int(max_faces_per_bin), int(bool(perspective_correct)), int(bool(clip_barycentric_coords)),
             int(bool(cull_backfaces)), _ptr(pix_to_face), _ptr(zbuf), _ptr(bary), _ptr(dists), _ptr(ws),
-            ws_bytes, 0, _stream_ptr(dev)))
+            ws_bytes, PAIR_CAPACITY, _stream_ptr(dev)))
         # the workspace is only read by kernels already enqueued on this stream
         ws.record_stream(torch.cuda.current_stream(dev))
     return pix_to_face, zbuf, bary, dists
@@ -177,11 +182,11 @@ def rasterize_points(
         dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
         if idx.numel() == 0:
             return idx, zbuf, dists
-        ws_bytes = lib.b200r_rasterize_points_workspace_bytes(P, N, H, W, 0)
+        ws_bytes = lib.b200r_rasterize_points_workspace_bytes(P, N, H, W, PAIR_CAPACITY)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         _lib.check(lib.b200r_rasterize_points_forward(
             _ptr(pts), P, _ptr(first), _ptr(num), _ptr(rad), N, H, W, K, int(bin_size), int(max_points_per_bin),
-            _ptr(idx), _ptr(zbuf), _ptr(dists), _ptr(ws), ws_bytes, 0, _stream_ptr(dev)))
+            _ptr(idx), _ptr(zbuf), _ptr(dists), _ptr(ws), ws_bytes, PAIR_CAPACITY, _stream_ptr(dev)))
         ws.record_stream(torch.cuda.current_stream(dev))
     return idx, zbuf, dists
 

@@ -41,6 +41,15 @@ inline int check_cuda(cudaError_t e, const char* what) {
     if (_rc != B200R_OK) return _rc;                         \
   } while (0)
 
+// Optional phase timing (b200r_set_profiling): events recorded on the launching stream.
+struct PhaseTimer {
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool have_fwd = false, have_bwd = false;
+  void record(int i, cudaStream_t s);
+};
+bool profiling_enabled();
+PhaseTimer& phase_timer();
+
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -22,6 +22,17 @@ std::atomic<int64_t>& launch_counter() {
   return c;
 }
 
+static std::atomic<int> g_profiling{0};
+bool profiling_enabled() { return g_profiling.load() != 0; }
+PhaseTimer& phase_timer() {
+  static thread_local PhaseTimer t;
+  return t;
+}
+void PhaseTimer::record(int i, cudaStream_t s) {
+  if (!ev[i]) cudaEventCreate(&ev[i]);
+  cudaEventRecord(ev[i], s);
+}
+
 namespace {
 
 struct DevBuf {
@@ -98,6 +109,21 @@ using namespace b200r;
 extern "C" const char* b200r_version(void) { return "b200raster 0.1.0 sm_100a"; }
 extern "C" const char* b200r_last_error(void) { return last_error_ref().c_str(); }
 extern "C" int64_t b200r_kernel_launch_count(void) { return launch_counter().load(); }
+extern "C" void b200r_set_profiling(int32_t enabled) { g_profiling.store(enabled ? 1 : 0); }
+extern "C" int b200r_last_phase_ms(float out[3]) {
+  PhaseTimer& t = phase_timer();
+  out[0] = out[1] = out[2] = 0.0f;
+  if (t.have_fwd) {
+    B200R_CUDA_OK(cudaEventSynchronize(t.ev[2]));
+    B200R_CUDA_OK(cudaEventElapsedTime(&out[0], t.ev[0], t.ev[1]));
+    B200R_CUDA_OK(cudaEventElapsedTime(&out[1], t.ev[1], t.ev[2]));
+  }
+  if (t.have_bwd) {
+    B200R_CUDA_OK(cudaEventSynchronize(t.ev[4]));
+    B200R_CUDA_OK(cudaEventElapsedTime(&out[2], t.ev[3], t.ev[4]));
+  }
+  return B200R_OK;
+}
 
 extern "C" int b200r_rasterize_meshes_forward_host(const float* face_verts, int64_t F, const int64_t* first,
                                                    const int64_t* num, const int64_t* neighbor, int32_t N,

@@ -697,6 +697,8 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
   const float rx = ndc_range(W, H), ry = ndc_range(H, W);
   const float sqrt_blur = sqrtf(blur_radius);  // IEEE sqrt, like the device sqrt.rn of the reference
 
+  const bool prof = profiling_enabled();
+  if (prof) phase_timer().record(0, stream);
   B200R_CUDA_OK(cudaMemsetAsync(ws.tile_count, 0, sizeof(int) * (size_t)ntiles, stream));
   if (F > 0) {
     mesh_setup_count_kernel<<<(unsigned)((F + SETUP_FACES - 1) / SETUP_FACES), SETUP_FACES, 0, stream>>>(
@@ -715,6 +717,7 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
     tile_sort_kernel<<<(unsigned)ntiles, SORT_THREADS, 0, stream>>>(ws.tile_offset, ws.pairs, ws.capacity);
     B200R_LAUNCHED("tile_sort_kernel");
   }
+  if (prof) phase_timer().record(1, stream);
   FineParams p;
   p.face_verts = face_verts;
   p.neighbor = neighbor;
@@ -747,6 +750,10 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
     mesh_fine_bigk_kernel<<<grid, TILE_THREADS, 0, stream>>>(p);
 #undef B200R_FINE
   B200R_LAUNCHED("mesh_fine_kernel");
+  if (prof) {
+    phase_timer().record(2, stream);
+    phase_timer().have_fwd = true;
+  }
   return B200R_OK;
 }
 
@@ -768,7 +775,13 @@ extern "C" int b200r_rasterize_meshes_backward(const float* face_verts, int64_t 
   p.rx = ndc_range(W, H); p.ry = ndc_range(H, W);
   p.persp = perspective_correct; p.clip = clip_barycentric_coords;
   p.grad_face_verts = grad_face_verts;
+  const bool prof = profiling_enabled();
+  if (prof) phase_timer().record(3, stream);
   mesh_backward_kernel<<<(unsigned)((int64_t)N * TY * TX), TILE_THREADS, 0, stream>>>(p);
   B200R_LAUNCHED("mesh_backward_kernel");
+  if (prof) {
+    phase_timer().record(4, stream);
+    phase_timer().have_bwd = true;
+  }
   return B200R_OK;
 }

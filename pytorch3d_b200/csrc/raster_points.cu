@@ -350,6 +350,8 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
     return fail(B200R_ERR_WORKSPACE, "workspace too small for rasterize_points_forward");
   const float rx = ndc_range(W, H), ry = ndc_range(H, W);
 
+  const bool prof = profiling_enabled();
+  if (prof) phase_timer().record(0, stream);
   B200R_CUDA_OK(cudaMemsetAsync(ws.tile_count, 0, sizeof(int) * (size_t)ntiles, stream));
   if (P > 0) {
     points_setup_count_kernel<<<(unsigned)((P + SETUP_POINTS - 1) / SETUP_POINTS), SETUP_POINTS, 0, stream>>>(
@@ -366,6 +368,7 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
   }
   tile_sort_kernel<<<(unsigned)ntiles, SORT_THREADS, 0, stream>>>(ws.tile_offset, ws.pairs, ws.capacity);
   B200R_LAUNCHED("tile_sort_kernel");
+  if (prof) phase_timer().record(1, stream);
   PointFineParams p;
   p.points = points; p.radius = radius; p.first = first; p.num = num;
   p.tile_offset = ws.tile_offset; p.pairs = ws.pairs; p.capacity = ws.capacity;
@@ -387,6 +390,10 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
   else
     points_fine_kernel<0><<<grid, TILE_THREADS, 0, stream>>>(p);
   B200R_LAUNCHED("points_fine_kernel");
+  if (prof) {
+    phase_timer().record(2, stream);
+    phase_timer().have_fwd = true;
+  }
   return B200R_OK;
 }
 
@@ -401,8 +408,14 @@ extern "C" int b200r_rasterize_points_backward(const float* points, int64_t P, c
   if (total == 0) return B200R_OK;
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 64) blocks = 148 * 64;
+  const bool prof = profiling_enabled();
+  if (prof) phase_timer().record(3, stream);
   points_backward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(points, idxs, grad_zbuf, grad_dists, total, H, W, K,
                                                              ndc_range(W, H), ndc_range(H, W), grad_points);
   B200R_LAUNCHED("points_backward_kernel");
+  if (prof) {
+    phase_timer().record(4, stream);
+    phase_timer().have_bwd = true;
+  }
   return B200R_OK;
 }

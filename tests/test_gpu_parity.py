@@ -1,0 +1,327 @@
+"""Parity of the CUDA path (called through the C ABI) with the oracle, the golden fixtures and -- when
+oracle/_ref/ref_raster_cuda.so travelled to the box -- the reference's own CUDA kernels.
+
+Bar: pix_to_face / idx bit-exact; zbuf / bary / dists bit-exact too against the CUDA-flavoured oracle
+(identical arithmetic), <= 1e-5 against fixtures produced by the reference's CPU build; gradients within
+the reference's own cross-implementation tolerances (tests/test_rasterize_meshes.py:543-594)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import assert_frag_equal, rand_faces, rand_points, split, upstream
+
+pytestmark = pytest.mark.gpu
+
+CUDA = dict(arith=oracle.ARITH_CUDA, select=oracle.SELECT_CUDA)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ops(built_lib):
+    from pytorch3d_b200 import _C
+    return _C
+
+
+@pytest.fixture(scope="module")
+def ref_cuda():
+    return oracle.load_reference(cuda=True)  # None on a box without the prebuilt reference
+
+
+def run_mesh(ops, dev, fv, first, num, size, blur, K, persp=0, clip=0, cull=0, nb=None):
+    if nb is None:
+        nbt = torch.full((fv.shape[0],), -1, dtype=torch.int64, device=dev)
+        nbt._b200_all_minus_one = True
+    else:
+        nbt = nb.to(dev)
+    return ops.rasterize_meshes(fv.to(dev), first.to(dev), num.to(dev), nbt, size, blur, K, 0, 0, bool(persp),
+                                bool(clip), bool(cull))
+
+
+MESH_MATRIX = [  # persp, clip, cull, blur, K, H, W, F, N
+    (0, 0, 0, 0.0, 4, 32, 32, 500, 2),
+    (1, 0, 0, 1e-3, 8, 33, 47, 500, 2),
+    (0, 1, 1, 1e-2, 3, 64, 40, 500, 2),
+    (1, 1, 0, 1e-4, 8, 48, 48, 500, 2),
+    (0, 0, 0, 1e-4, 8, 128, 128, 6000, 3),
+    (0, 0, 1, 0.0, 1, 17, 100, 800, 1),
+    (0, 0, 0, 1e-3, 2, 100, 17, 800, 4),
+    (1, 1, 1, 0.05, 20, 40, 40, 300, 1),
+    (0, 0, 0, 1e-3, 150, 24, 24, 400, 1),
+    (0, 0, 0, 1e-2, 5, 31, 31, 300, 1),
+    (0, 0, 0, 1e-2, 7, 16, 16, 300, 1),
+    (0, 0, 0, 1e-2, 9, 16, 16, 300, 1),
+]
+
+
+@pytest.mark.parametrize("persp,clip,cull,blur,K,H,W,F,N", MESH_MATRIX)
+def test_mesh_forward_equals_oracle(ops, dev, persp, clip, cull, blur, K, H, W, F, N):
+    fv, first, num = rand_faces(F, N, seed=K + H)
+    mine = run_mesh(ops, dev, fv, first, num, (H, W), blur, K, persp, clip, cull)
+    o = oracle.rasterize_meshes(fv.numpy(), first.numpy(), num.numpy(), (H, W), blur, K, persp, clip, cull, **CUDA)
+    assert_frag_equal(mine, o, "mine vs oracle")
+
+
+def test_mesh_forward_structured_with_z_ties(ops, dev, ref_cuda):
+    """Two tori at 256^2, blur 1e-4, K=8: hundreds of exact z ties straddle the K-th slot here; the
+    reference-CUDA queue semantics + ascending face order must still be reproduced bit-for-bit."""
+    from pytorch3d_b200 import synthetic
+    m = synthetic.torus_batch(2, 54, 54, seed=0)
+    fv, first, num = synthetic.face_verts_of(m), m.mesh_to_faces_packed_first_idx(), m.num_faces_per_mesh()
+    mine = run_mesh(ops, dev, fv, first, num, (256, 256), 1e-4, 8)
+    o = oracle.rasterize_meshes(fv.numpy(), first.numpy(), num.numpy(), (256, 256), 1e-4, 8, **CUDA)
+    assert_frag_equal(mine, o, "torus vs oracle")
+    lex = oracle.rasterize_meshes(fv.numpy(), first.numpy(), num.numpy(), (256, 256), 1e-4, 8,
+                                  arith=oracle.ARITH_CUDA, select=oracle.SELECT_CPU)
+    assert (lex[0] != o[0]).sum() > 0, "scene is expected to contain ties (guards the test's purpose)"
+    if ref_cuda is not None:
+        nb = torch.full((fv.shape[0],), -1, dtype=torch.int64, device=dev)
+        r = ref_cuda.rasterize_meshes(fv.to(dev), first.to(dev), num.to(dev), nb, (256, 256), 1e-4, 8, 0, 0, False,
+                                      False, False)
+        assert_frag_equal(mine, r, "torus vs reference CUDA (naive)")
+
+
+def test_config1_ico_sphere(ops, dev):
+    """BASELINE config 1: ico_sphere(level=4), batch 1, 64^2, K=1."""
+    from pytorch3d_b200 import synthetic
+    m = synthetic.ico_sphere_batch(1, 4)
+    fv, first, num = synthetic.face_verts_of(m), m.mesh_to_faces_packed_first_idx(), m.num_faces_per_mesh()
+    mine = run_mesh(ops, dev, fv, first, num, (64, 64), 0.0, 1)
+    o = oracle.rasterize_meshes(fv.numpy(), first.numpy(), num.numpy(), (64, 64), 0.0, 1, **CUDA)
+    assert_frag_equal(mine, o)
+    assert (mine[0] >= 0).sum() > 1000
+
+
+def test_mesh_golden_fixtures(ops, dev, golden):
+    names = sorted(k for k in golden if k.startswith("mesh/") and "/cpp" in k)
+    for name in names:
+        c = golden[name]
+        H, W, K, persp, clip, cull = (int(v) for v in c["args"])
+        mine = run_mesh(ops, dev, torch.from_numpy(c["face_verts"]), torch.from_numpy(c["first"]),
+                        torch.from_numpy(c["num"]), (H, W), float(c["blur"][0]), K, persp, clip, cull)
+        assert np.array_equal(mine[0].cpu().numpy(), c["pix_to_face"]), name
+        for got, want in zip(mine[1:], (c["zbuf"], c["bary"], c["dists"])):
+            assert np.abs(got.cpu().numpy() - want).max() <= 1e-5, name
+
+
+@pytest.mark.parametrize("persp,clip,cull,blur,K,H,W,F,N", MESH_MATRIX[:6])
+def test_mesh_forward_equals_reference_cuda(ops, dev, ref_cuda, persp, clip, cull, blur, K, H, W, F, N):
+    if ref_cuda is None:
+        pytest.skip("reference CUDA build not present")
+    fv, first, num = rand_faces(F, N, seed=K + H)
+    mine = run_mesh(ops, dev, fv, first, num, (H, W), blur, K, persp, clip, cull)
+    nb = torch.full((F,), -1, dtype=torch.int64, device=dev)
+    r = ref_cuda.rasterize_meshes(fv.to(dev), first.to(dev), num.to(dev), nb, (H, W), blur, K, 0, 0, bool(persp),
+                                  bool(clip), bool(cull))
+    assert_frag_equal(mine, r, "mine vs reference CUDA naive")
+
+
+def test_mesh_edge_cases(ops, dev):
+    # empty mesh in the middle of the batch, faces behind the camera, degenerate faces, huge faces
+    fv, _, _ = rand_faces(200, 1, seed=11, scale=0.3)
+    fv[10:20, :, 2] = -1.0                       # behind the camera
+    fv[20:30, 1] = fv[20:30, 0]                  # zero area
+    fv[30] = torch.tensor([[-5.0, -5.0, 1.0], [5.0, -5.0, 1.2], [0.0, 6.0, 1.4]])  # covers everything
+    fv[31] = torch.tensor([[-5.0, -5.0, 0.9], [0.0, 6.0, 1.1], [5.0, -5.0, 1.3]])  # back-facing twin
+    first = torch.tensor([0, 100, 100], dtype=torch.int64)
+    num = torch.tensor([100, 0, 100], dtype=torch.int64)
+    for cull in (0, 1):
+        mine = run_mesh(ops, dev, fv, first, num, (40, 56), 1e-3, 4, cull=cull)
+        o = oracle.rasterize_meshes(fv.numpy(), first.numpy(), num.numpy(), (40, 56), 1e-3, 4, cull_backfaces=cull,
+                                    **CUDA)
+        assert_frag_equal(mine, o, "edge cases cull=%d" % cull)
+        assert (mine[0][1] == -1).all()  # the empty mesh renders nothing
+    # no faces at all / zero-size outputs
+    e = run_mesh(ops, dev, torch.zeros(0, 3, 3), torch.zeros(1, dtype=torch.int64), torch.zeros(1, dtype=torch.int64),
+                 (8, 8), 0.0, 2)
+    assert e[0].shape == (1, 8, 8, 2) and (e[0] == -1).all() and (e[1] == -1).all() and (e[2] == -1).all()
+    z = run_mesh(ops, dev, fv, first, num, (8, 8), 0.0, 0)
+    assert z[0].shape == (3, 8, 8, 0)
+
+
+def test_mesh_pair_overflow_falls_back_exactly(ops, dev):
+    """With a deliberately tiny pair buffer most tiles overflow and rasterise from the full mesh range:
+    the result must not change (the reference drops faces in this situation, rasterize_coarse.cu:186-201)."""
+    fv, first, num = rand_faces(600, 2, seed=5, scale=0.5)
+    full = run_mesh(ops, dev, fv, first, num, (64, 64), 1e-3, 4)
+    ops.PAIR_CAPACITY = 64
+    try:
+        small = run_mesh(ops, dev, fv, first, num, (64, 64), 1e-3, 4)
+    finally:
+        ops.PAIR_CAPACITY = 0
+    assert_frag_equal(full, small, "overflow fallback")
+
+
+def test_mesh_clipped_neighbors(ops, dev):
+    fv, first, num = rand_faces(300, 1, seed=7, scale=0.35)
+    nb = torch.full((300,), -1, dtype=torch.int64)
+    nb[0:100:2] = torch.arange(1, 100, 2)
+    nb[1:100:2] = torch.arange(0, 100, 2)
+    for K in (4, 12):
+        mine = run_mesh(ops, dev, fv, first, num, (32, 32), 1e-2, K, nb=nb)
+        o = oracle.rasterize_meshes(fv.numpy(), first.numpy(), num.numpy(), (32, 32), 1e-2, K,
+                                    clipped_faces_neighbor_idx=nb.numpy(), **CUDA)
+        assert_frag_equal(mine, o, "neighbours K=%d" % K)
+
+
+@pytest.mark.parametrize("persp,clip", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_mesh_backward(ops, dev, ref_cuda, persp, clip):
+    from pytorch3d_b200 import synthetic
+    m = synthetic.torus_batch(2, 24, 24, seed=3)
+    fv, first, num = synthetic.face_verts_of(m), m.mesh_to_faces_packed_first_idx(), m.num_faces_per_mesh()
+    blur = 1e-3
+    frag = run_mesh(ops, dev, fv, first, num, (64, 64), blur, 4, persp, clip)
+    gz, gb, gd = upstream([frag[1].shape, frag[2].shape, frag[3].shape])
+    mine = ops.rasterize_meshes_backward(fv.to(dev), frag[0], gz.to(dev), gb.to(dev), gd.to(dev), bool(persp),
+                                         bool(clip)).cpu().numpy()
+    want = oracle.rasterize_meshes_backward(fv.numpy(), frag[0].cpu().numpy(), gz.numpy(), gb.numpy(), gd.numpy(),
+                                            persp, clip, arith=oracle.ARITH_CUDA)
+    scale = np.abs(want).max()
+    assert np.abs(mine - want).max() <= 2e-3 * scale
+    np.testing.assert_allclose(mine, want, rtol=2e-3, atol=2e-4 * scale)
+    if ref_cuda is not None and not (persp and clip):
+        # (with both flags the reference CUDA kernel feeds the uncorrected barycentrics to the clip
+        # backward, rasterize_meshes.cu:527-529; we follow the forward-consistent CPU form)
+        r = ref_cuda.rasterize_meshes_backward(fv.to(dev), frag[0], gz.to(dev), gb.to(dev), gd.to(dev), bool(persp),
+                                               bool(clip)).cpu().numpy()
+        np.testing.assert_allclose(mine, r, rtol=2e-3, atol=2e-4 * scale)
+
+
+def test_mesh_autograd_wrapper(ops, dev):
+    import pytorch3d_b200 as p3b
+    from pytorch3d_b200 import synthetic
+    m = synthetic.torus_batch(2, 16, 16, seed=1, device=dev)
+    m.requires_grad_(True)
+    p2f, zbuf, bary, dists = p3b.rasterize_meshes(m, 48, blur_radius=1e-3, faces_per_pixel=3)
+    gz, gb, gd = (t.to(dev) for t in upstream([zbuf.shape, bary.shape, dists.shape]))
+    ((zbuf * gz).sum() + (bary * gb).sum() + (dists * gd).sum()).backward()
+    grad_verts = m.verts_packed().grad
+    fv = synthetic.face_verts_of(m).detach().cpu()
+    want_fv = oracle.rasterize_meshes_backward(fv.numpy(), p2f.cpu().numpy(), gz.cpu().numpy(), gb.cpu().numpy(),
+                                               gd.cpu().numpy(), 0, 0, arith=oracle.ARITH_CUDA)
+    want = torch.zeros_like(m.verts_packed().detach().cpu())
+    want.index_put_((m.faces_packed().cpu().reshape(-1),), torch.from_numpy(want_fv).reshape(-1, 3), accumulate=True)
+    scale = want.abs().max()
+    assert (grad_verts.cpu() - want).abs().max() <= 2e-3 * scale
+    assert not p2f.requires_grad
+
+
+# ------------------------------------------------------------------------------------ points
+
+POINT_MATRIX = [(2000, 2, 32, 48, 5), (5000, 1, 64, 64, 10), (3000, 3, 40, 24, 1), (3000, 1, 50, 50, 40),
+                (3000, 1, 20, 20, 150), (20000, 2, 128, 128, 8), (1000, 1, 17, 33, 3)]
+
+
+@pytest.mark.parametrize("P,N,H,W,K", POINT_MATRIX)
+def test_points_forward_equals_oracle(ops, dev, ref_cuda, P, N, H, W, K):
+    pts, first, num, rad = rand_points(P, N, seed=P + K, z_ties=True)
+    mine = ops.rasterize_points(pts.to(dev), first.to(dev), num.to(dev), (H, W), rad.to(dev), K, 0, 0)
+    o = oracle.rasterize_points(pts.numpy(), first.numpy(), num.numpy(), (H, W), rad.numpy(), K, **CUDA)
+    assert_frag_equal(mine, o, "points vs oracle")
+    if ref_cuda is not None:
+        r = ref_cuda.rasterize_points(pts.to(dev), first.to(dev), num.to(dev), (H, W), rad.to(dev), K, 0, 0)
+        assert_frag_equal(mine, r, "points vs reference CUDA naive")
+
+
+def test_points_golden_fixtures(ops, dev, golden):
+    for name in sorted(k for k in golden if k.startswith("points/")):
+        c = golden[name]
+        H, W, K = (int(v) for v in c["args"])
+        mine = ops.rasterize_points(torch.from_numpy(c["points"]).to(dev), torch.from_numpy(c["first"]).to(dev),
+                                    torch.from_numpy(c["num"]).to(dev), (H, W),
+                                    torch.from_numpy(c["radius"]).to(dev), K, 0, 0)
+        assert np.array_equal(mine[0].cpu().numpy(), c["idx"]), name
+        assert np.array_equal(mine[1].cpu().numpy(), c["zbuf"]), name
+        assert np.abs(mine[2].cpu().numpy() - c["dists"]).max() <= 1e-5, name
+
+
+def test_points_backward_and_edge_cases(ops, dev):
+    pts, first, num, rad = rand_points(4000, 2, seed=9)
+    pts[:50, 2] = -0.5  # behind the camera
+    frag = ops.rasterize_points(pts.to(dev), first.to(dev), num.to(dev), (48, 48), rad.to(dev), 6, 0, 0)
+    assert not np.isin(np.arange(50), frag[0].cpu().numpy()).any()
+    gz, gd = upstream([frag[1].shape, frag[2].shape])
+    mine = ops.rasterize_points_backward(pts.to(dev), frag[0], gz.to(dev), gd.to(dev)).cpu().numpy()
+    want = oracle.rasterize_points_backward(pts.numpy(), frag[0].cpu().numpy(), gz.numpy(), gd.numpy(),
+                                            arith=oracle.ARITH_CUDA)
+    assert np.abs(mine - want).max() <= 5e-5  # reference tolerance is 2e-6 per unit gradient sum
+    # empty cloud + empty outputs
+    first2 = torch.tensor([0, 2000, 2000], dtype=torch.int64)
+    num2 = torch.tensor([2000, 0, 2000], dtype=torch.int64)
+    a = ops.rasterize_points(pts.to(dev), first2.to(dev), num2.to(dev), (24, 24), rad.to(dev), 3, 0, 0)
+    o = oracle.rasterize_points(pts.numpy(), first2.numpy(), num2.numpy(), (24, 24), rad.numpy(), 3, **CUDA)
+    assert_frag_equal(a, o)
+    assert (a[0][1] == -1).all()
+
+
+def test_points_autograd_wrapper(ops, dev):
+    import pytorch3d_b200 as p3b
+    from pytorch3d_b200 import synthetic
+    pc = synthetic.random_pointclouds(2, 3000, seed=2, device=dev)
+    pc.points_packed().requires_grad_(True)
+    idx, zbuf, dists = p3b.rasterize_points(pc, (40, 56), radius=0.05, points_per_pixel=4)
+    gz, gd = (t.to(dev) for t in upstream([zbuf.shape, dists.shape]))
+    ((zbuf * gz).sum() + (dists * gd).sum()).backward()
+    want = oracle.rasterize_points_backward(pc.points_packed().detach().cpu().numpy(), idx.cpu().numpy(),
+                                            gz.cpu().numpy(), gd.cpu().numpy(), arith=oracle.ARITH_CUDA)
+    assert np.abs(pc.points_packed().grad.cpu().numpy() - want).max() <= 5e-5
+    assert idx.dtype == torch.int32
+
+
+# ------------------------------------------------------------------------------------ full size
+
+def test_full_size_properties(ops, dev, ref_cuda):
+    """North-star size (8 x 69,938 faces, 512^2, K=8): size-independent properties, plus exact equality
+    with the reference CUDA op when it is available on the box."""
+    from pytorch3d_b200 import synthetic
+    m = synthetic.torus_batch(8, 187, 187, seed=0)
+    fv = synthetic.face_verts_of(m).to(dev)
+    first, num = m.mesh_to_faces_packed_first_idx().to(dev), m.num_faces_per_mesh().to(dev)
+    a = run_mesh(ops, dev, fv, first, num, (512, 512), 0.0, 8)
+    b = run_mesh(ops, dev, fv, first, num, (512, 512), 0.0, 8)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y), "forward must be deterministic"
+    p2f, zbuf, bary, dists = a
+    valid = p2f >= 0
+    assert valid.sum() > 1_000_000
+    assert torch.equal(valid, zbuf >= 0) and (zbuf[~valid] == -1).all() and (dists[~valid] == -1).all()
+    # valid entries first, sorted by depth
+    assert (valid[..., :-1] | ~valid[..., 1:]).all()
+    both = valid[..., :-1] & valid[..., 1:]
+    assert (zbuf[..., :-1][both] <= zbuf[..., 1:][both]).all()
+    # every index belongs to the mesh of its image; barycentrics sum to 1; inside hits have dist <= 0
+    lo = first.view(-1, 1, 1, 1)
+    hi = (first + num).view(-1, 1, 1, 1)
+    assert ((p2f >= lo) & (p2f < hi) | ~valid).all()
+    assert (bary.sum(-1)[valid] - 1).abs().max() < 1e-4
+    assert (dists[valid] <= 0).all()  # blur_radius = 0: only pixels inside a face are kept
+    # z is the barycentric interpolation of the face's vertex depths
+    zi = (bary * fv[p2f.clamp_min(0)][..., 2]).sum(-1)
+    assert (zi - zbuf)[valid].abs().max() < 1e-5
+    if ref_cuda is not None:
+        nb = torch.full((fv.shape[0],), -1, dtype=torch.int64, device=dev)
+        r = ref_cuda.rasterize_meshes(fv, first, num, nb, (512, 512), 0.0, 8, 32, 14000, False, False, False)
+        assert_frag_equal(a, r, "north-star vs reference CUDA (coarse-to-fine)")
+    # backward: linear in the upstream gradients
+    gz, gb, gd = (t.to(dev) for t in upstream([zbuf.shape, bary.shape, dists.shape]))
+    g1 = ops.rasterize_meshes_backward(fv, p2f, gz, gb, gd, False, False)
+    g2 = ops.rasterize_meshes_backward(fv, p2f, 2 * gz, 2 * gb, 2 * gd, False, False)
+    assert torch.isfinite(g1).all()
+    assert (g2 - 2 * g1).abs().max() <= 1e-3 * g1.abs().max()
+
+
+def test_side_stream_and_noncontiguous(ops, dev):
+    fv, first, num = rand_faces(400, 2, seed=21)
+    base = run_mesh(ops, dev, fv, first, num, (32, 32), 1e-3, 4)
+    s = torch.cuda.Stream(device=dev)
+    big = torch.zeros(400, 3, 6)
+    big[..., ::2] = fv
+    with torch.cuda.stream(s):
+        other = run_mesh(ops, dev, big.to(dev)[..., ::2], first, num, (32, 32), 1e-3, 4)
+    s.synchronize()
+    assert_frag_equal(base, other)
