@@ -108,18 +108,43 @@ __device__ __forceinline__ bool key_less(float za, int ia, float zb, int ib) {
   return za < zb || (za == zb && ia < ib);  // operator< of the reference's Pixel (rasterize_meshes.cu:30-32)
 }
 
+// Hit test of the fine loop: same decisions as eval_pixel_face, but only the depth (and, when it is needed
+// to decide, the distance) is produced; barycentrics and distance of the final winners are recomputed once
+// at the end by eval_pixel_face (identical arithmetic => identical values).
+template <bool ALWAYS_DIST>
+__device__ __forceinline__ bool test_pixel_face(float px, float py, const Face& f, float den, float blur_radius,
+                                                bool persp, bool clip, float& pz_out, float& dist_out) {
+  float w0, w1, w2;
+  bary_coords(px, py, f, den, w0, w1, w2);
+  if (persp) bary_persp(w0, w1, w2, f.z0, f.z1, f.z2);
+  const bool inside = w0 > 0.0f && w1 > 0.0f && w2 > 0.0f;
+  if (!inside && !(blur_radius > 0.0f)) return false;
+  float c0 = w0, c1 = w1, c2 = w2;
+  if (clip) bary_clip(c0, c1, c2);
+  const float pz = ffma(f.z2, c2, ffma(f.z0, c0, fmul(f.z1, c1)));
+  if (!(pz >= 0.0f)) return false;
+  if (ALWAYS_DIST || !inside) {
+    const float dist = point_tri_dist(px, py, f);
+    if (!inside && dist >= blur_radius) return false;
+    dist_out = dist;
+  }
+  pz_out = pz;
+  return true;
+}
+
 // The K nearest hits of one pixel.  This is the reference's per-pixel queue (rasterize_meshes.cu:179-237)
 // restated for registers: an UNSORTED array of K slots plus the tracked maximum (q_max_z, q_max_idx); a new
 // hit fills the next free slot, or -- when the queue is full and pz < q_max_z -- overwrites the tracked
 // maximum, after which the maximum is searched again (first slot with a strictly larger z wins).  Faces
 // reach the queue in ascending index order (sorted tile lists), so ties are resolved exactly as by the
-// reference's naive kernel.  All array indices are compile-time constants (predicated updates), so the
-// queue never leaves the register file.
-template <int KMAX>
+// reference's naive kernel.  Only the keys (z, face) are queued (plus |dist| when clipped-face neighbours
+// are in play); all array indices are compile-time constants (predicated updates), so the queue never
+// leaves the register file.
+template <int KMAX, bool NB>
 struct TopK {
   float z[KMAX];
   int id[KMAX];
-  float d[KMAX], b0[KMAX], b1[KMAX], b2[KMAX];
+  float d[NB ? KMAX : 1];
   int size;
   float max_z;
   int max_idx;
@@ -129,36 +154,33 @@ struct TopK {
     for (int i = 0; i < KMAX; ++i) {
       z[i] = -1.0f;
       id[i] = -1;
-      d[i] = b0[i] = b1[i] = b2[i] = -1.0f;
+      if (NB) d[i] = 0.0f;
     }
     size = 0;
     max_z = -1000.0f;  // (:292)
     max_idx = -1;
   }
-  __device__ __forceinline__ void put(int slot, const Hit& h, int f) {
+  __device__ __forceinline__ void put(int slot, float pz, int f, float dist) {
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
       const bool w = i == slot;
-      z[i] = w ? h.z : z[i];
+      z[i] = w ? pz : z[i];
       id[i] = w ? f : id[i];
-      d[i] = w ? h.dist : d[i];
-      b0[i] = w ? h.b0 : b0[i];
-      b1[i] = w ? h.b1 : b1[i];
-      b2[i] = w ? h.b2 : b2[i];
+      if (NB) d[i] = w ? dist : d[i];
     }
   }
   // Handle a face that covers the pixel (the `else` branch at :216-236).
-  __device__ __forceinline__ void offer(const Hit& h, int f, int K) {
+  __device__ __forceinline__ void offer(float pz, int f, float dist, int K) {
     if (size < K) {
-      put(size, h, f);
-      if (h.z > max_z) {
-        max_z = h.z;
+      put(size, pz, f, dist);
+      if (pz > max_z) {
+        max_z = pz;
         max_idx = size;
       }
       ++size;
-    } else if (h.z < max_z) {
-      put(max_idx, h, f);
-      max_z = h.z;
+    } else if (pz < max_z) {
+      put(max_idx, pz, f, dist);
+      max_z = pz;
 #pragma unroll
       for (int i = 0; i < KMAX; ++i) {
         if (i < K && z[i] > max_z) {
@@ -170,7 +192,7 @@ struct TopK {
   }
   // Clipped-face neighbour handling (:186-215): if the other half of a clipped quad is already queued,
   // keep whichever half is closer to the pixel.  Returns true if the hit was consumed here.
-  __device__ __forceinline__ bool offer_neighbor(const Hit& h, int f, int neighbor) {
+  __device__ __forceinline__ bool offer_neighbor(float pz, int f, float dist, int neighbor) {
     int at = -1;
 #pragma unroll
     for (int i = KMAX - 1; i >= 0; --i)
@@ -178,11 +200,11 @@ struct TopK {
     if (at < 0) return false;
     float nd = 0.0f;
 #pragma unroll
-    for (int i = 0; i < KMAX; ++i) nd = i == at ? fabsf(d[i]) : nd;
-    if (fabsf(h.dist) < nd) {
-      put(at, h, f);
-      if (h.z > max_z) {
-        max_z = h.z;
+    for (int i = 0; i < KMAX; ++i) nd = i == at ? d[NB ? i : 0] : nd;
+    if (dist < nd) {
+      put(at, pz, f, dist);
+      if (pz > max_z) {
+        max_z = pz;
         max_idx = at;
       }
     }
@@ -203,14 +225,12 @@ struct TopK {
 #pragma unroll
       for (int i = r & 1; i + 1 < KMAX; i += 2) {
         if (key_less(z[i + 1], id[i + 1], z[i], id[i])) {
-          float t;
-          int ti;
-          t = z[i]; z[i] = z[i + 1]; z[i + 1] = t;
-          ti = id[i]; id[i] = id[i + 1]; id[i + 1] = ti;
-          t = d[i]; d[i] = d[i + 1]; d[i + 1] = t;
-          t = b0[i]; b0[i] = b0[i + 1]; b0[i + 1] = t;
-          t = b1[i]; b1[i] = b1[i + 1]; b1[i + 1] = t;
-          t = b2[i]; b2[i] = b2[i + 1]; b2[i + 1] = t;
+          const float t = z[i];
+          z[i] = z[i + 1];
+          z[i + 1] = t;
+          const int ti = id[i];
+          id[i] = id[i + 1];
+          id[i + 1] = ti;
         }
       }
     }
@@ -276,10 +296,19 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Faces are consumed in rounds of LIST_ROUND: every lane first records (one byte each, in a private
+// shared-memory column) which faces of the round pass ITS pixel's box test, then walks its own list.  In the
+// first half all lanes look at the same face (broadcast LDS, ~10 instructions); in the second half every lane
+// works on a different face that is known to touch its pixel, so the expensive arithmetic runs on (nearly)
+// full warps even when triangles are pixel-sized and only a handful of the footprint's 32 pixels lie in a
+// given face's box.
+constexpr int LIST_ROUND = 64;
+
 template <int KMAX, bool NB>
 __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParams p) {
   __shared__ FaceChunk s;
-  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ unsigned char s_list[TILE_THREADS / 32][LIST_ROUND][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = blockIdx.x;
   const int n = t / (p.TY * p.TX);
   const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
@@ -299,10 +328,11 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParam
   const int64_t mesh_first = p.first[n];
   const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
 
-  TopK<KMAX> q;
+  TopK<KMAX, NB> q;
   q.init();
   const bool persp = p.persp != 0, clip = p.clip != 0, cull = p.cull != 0;
   const int K = p.K;
+  const float blur_radius = p.blur_radius;
 
   for (int base = 0; base < count; base += CHUNK) {
     const int nc = min(CHUNK, count - base);
@@ -312,39 +342,72 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParam
       stage_face(s, tid, p.face_verts, p.neighbor, f, p.sqrt_blur, cull);
     }
     __syncthreads();
-    for (int g = 0; g < nc; g += 32) {
-      // cull 32 faces against the warp footprint: one face per lane
-      bool touch = false;
-      if (g + lane < nc) {
-        const float4 bx = s.box[g + lane];
-        touch = !(fx_lo > bx.y || fx_hi < bx.x || fy_lo > bx.w || fy_hi < bx.z);
-      }
-      unsigned m = __ballot_sync(0xffffffffu, touch);
-      while (m) {
-        const int j = g + __ffs(m) - 1;
-        m &= m - 1;
-        const float4 bx = s.box[j];
-        if (!valid || px > bx.y || px < bx.x || py > bx.w || py < bx.z) continue;  // (:94-97)
-        const float4 fa = s.a[j], fb = s.b[j], fc = s.c[j];
-        const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
-        Hit h;
-        if (!eval_pixel_face(px, py, f, fb.z, p.blur_radius, persp, clip, h)) continue;
-        const int fi = __float_as_int(fb.w);
-        if (NB) {
-          const int nb = __float_as_int(fc.w);
-          if (nb != -1 && q.offer_neighbor(h, fi, nb)) continue;
+    for (int sub = 0; sub < nc; sub += LIST_ROUND) {
+      // ---- pass A: which faces of this round touch my pixel?  (ascending order is preserved)
+      int cnt = 0;
+      const int sub_end = min(nc, sub + LIST_ROUND);
+      for (int g = sub; g < sub_end; g += 32) {
+        bool touch = false;
+        if (g + lane < sub_end) {  // cull 32 faces against the warp footprint: one face per lane
+          const float4 bx = s.box[g + lane];
+          touch = !(fx_lo > bx.y || fx_hi < bx.x || fy_lo > bx.w || fy_hi < bx.z);
         }
-        q.offer(h, fi, K);
+        unsigned m = __ballot_sync(0xffffffffu, touch);
+        while (m) {
+          const int j = g + __ffs(m) - 1;
+          m &= m - 1;
+          const float4 bx = s.box[j];
+          if (valid && !(px > bx.y || px < bx.x || py > bx.w || py < bx.z)) {  // (:94-97)
+            s_list[warp][cnt][lane] = (unsigned char)j;
+            ++cnt;
+          }
+        }
+      }
+      // ---- pass B: every lane evaluates its own candidates
+      const int rounds = (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt);
+      for (int i = 0; i < rounds; ++i) {
+        if (i < cnt) {
+          const int j = s_list[warp][i][lane];
+          const float4 fa = s.a[j], fb = s.b[j], fc = s.c[j];
+          const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
+          float pz, dist = 0.0f;
+          if (test_pixel_face<NB>(px, py, f, fb.z, blur_radius, persp, clip, pz, dist)) {
+            const int fi = __float_as_int(fb.w);
+            bool consumed = false;
+            if (NB) {
+              const int nb = __float_as_int(fc.w);
+              if (nb != -1) consumed = q.offer_neighbor(pz, fi, dist, nb);
+            }
+            if (!consumed) q.offer(pz, fi, dist, K);
+          }
+        }
       }
     }
   }
 
   if (!valid) return;
   q.sort();
+  // ---- epilogue: barycentrics / distance of the winners, then one vectorised write per output
+  float od[KMAX], ob0[KMAX], ob1[KMAX], ob2[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    od[k] = ob0[k] = ob1[k] = ob2[k] = -1.0f;
+    if (k < q.size) {
+      const float* v = p.face_verts + (int64_t)q.id[k] * 9;
+      const Face f = {__ldg(v + 0), __ldg(v + 1), __ldg(v + 2), __ldg(v + 3), __ldg(v + 4),
+                      __ldg(v + 5), __ldg(v + 6), __ldg(v + 7), __ldg(v + 8)};
+      Hit h;
+      eval_pixel_face(px, py, f, bary_denominator(f), blur_radius, persp, clip, h);
+      od[k] = h.dist;
+      ob0[k] = h.b0;
+      ob1[k] = h.b1;
+      ob2[k] = h.b2;
+    }
+  }
   const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
   if (K == KMAX && (KMAX % 4) == 0) {
     longlong2* pf = reinterpret_cast<longlong2*>(p.pix_to_face + o);
-    float4* pz = reinterpret_cast<float4*>(p.zbuf + o);
+    float4* pzv = reinterpret_cast<float4*>(p.zbuf + o);
     float4* pd = reinterpret_cast<float4*>(p.dists + o);
     float4* pb = reinterpret_cast<float4*>(p.bary + o * 3);
 #pragma unroll
@@ -355,12 +418,12 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParam
     }
 #pragma unroll
     for (int k = 0; k < KMAX; k += 4) {
-      pz[k / 4] = make_float4(k >= q.size ? -1.0f : q.z[k], k + 1 >= q.size ? -1.0f : q.z[k + 1],
-                              k + 2 >= q.size ? -1.0f : q.z[k + 2], k + 3 >= q.size ? -1.0f : q.z[k + 3]);
-      pd[k / 4] = make_float4(q.d[k], q.d[k + 1], q.d[k + 2], q.d[k + 3]);
-      pb[3 * (k / 4) + 0] = make_float4(q.b0[k], q.b1[k], q.b2[k], q.b0[k + 1]);
-      pb[3 * (k / 4) + 1] = make_float4(q.b1[k + 1], q.b2[k + 1], q.b0[k + 2], q.b1[k + 2]);
-      pb[3 * (k / 4) + 2] = make_float4(q.b2[k + 2], q.b0[k + 3], q.b1[k + 3], q.b2[k + 3]);
+      pzv[k / 4] = make_float4(k >= q.size ? -1.0f : q.z[k], k + 1 >= q.size ? -1.0f : q.z[k + 1],
+                               k + 2 >= q.size ? -1.0f : q.z[k + 2], k + 3 >= q.size ? -1.0f : q.z[k + 3]);
+      pd[k / 4] = make_float4(od[k], od[k + 1], od[k + 2], od[k + 3]);
+      pb[3 * (k / 4) + 0] = make_float4(ob0[k], ob1[k], ob2[k], ob0[k + 1]);
+      pb[3 * (k / 4) + 1] = make_float4(ob1[k + 1], ob2[k + 1], ob0[k + 2], ob1[k + 2]);
+      pb[3 * (k / 4) + 2] = make_float4(ob2[k + 2], ob0[k + 3], ob1[k + 3], ob2[k + 3]);
     }
   } else {
 #pragma unroll
@@ -369,10 +432,10 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParam
         const bool e = k >= q.size;
         p.pix_to_face[o + k] = e ? -1ll : (long long)q.id[k];
         p.zbuf[o + k] = e ? -1.0f : q.z[k];
-        p.dists[o + k] = q.d[k];
-        p.bary[(o + k) * 3 + 0] = q.b0[k];
-        p.bary[(o + k) * 3 + 1] = q.b1[k];
-        p.bary[(o + k) * 3 + 2] = q.b2[k];
+        p.dists[o + k] = od[k];
+        p.bary[(o + k) * 3 + 0] = ob0[k];
+        p.bary[(o + k) * 3 + 1] = ob1[k];
+        p.bary[(o + k) * 3 + 2] = ob2[k];
       }
     }
   }
