@@ -126,50 +126,79 @@ static __global__ void __launch_bounds__(256)
 // "Normalised" bitonic network (every compare-exchange ascending), valid for any segment length:
 // partners beyond the end are treated as +inf and skipped.
 constexpr int SORT_THREADS = 128;
-constexpr int SORT_SMEM_ELEMS = 4096;
+constexpr int SORT_TILES_PER_CTA = SORT_THREADS / 32;  // one warp per tile on the fast path
+constexpr int SORT_WARP_ELEMS = 1024;                   // per-warp shared-memory capacity
+constexpr int SORT_SMEM_ELEMS = SORT_TILES_PER_CTA * SORT_WARP_ELEMS;
+
+// One compare-exchange sweep of the network over keys[0..n) by `nthreads` cooperating threads.
+template <bool MIRROR>
+__device__ __forceinline__ void sort_sweep(int* keys, int n, int d, int tid, int nthreads) {
+  for (int i = tid; i < n; i += nthreads) {
+    const int j = MIRROR ? (i ^ (d - 1)) : (i ^ d);  // MIRROR: d is the block size k
+    if (j > i && j < n) {
+      const int a = keys[i], b = keys[j];
+      if (b < a) {
+        keys[i] = b;
+        keys[j] = a;
+      }
+    }
+  }
+}
 
 static __global__ void __launch_bounds__(SORT_THREADS)
-    tile_sort_kernel(const int* __restrict__ offsets, int* __restrict__ pairs, int64_t capacity) {
+    tile_sort_kernel(const int* __restrict__ offsets, int* __restrict__ pairs, int64_t capacity, int ntiles) {
   __shared__ int s_keys[SORT_SMEM_ELEMS];
-  const int t = blockIdx.x;
-  const int begin = offsets[t], end = offsets[t + 1];
-  const int n = end - begin;
-  if (n < 2 || (int64_t)end > capacity) return;  // overflowed tiles are rasterised from the mesh range
-  const bool in_smem = n <= SORT_SMEM_ELEMS;
-  int* keys = in_smem ? s_keys : pairs + begin;
-  if (in_smem) {
-    for (int i = threadIdx.x; i < n; i += SORT_THREADS) s_keys[i] = pairs[begin + i];
+  const int t0 = blockIdx.x * SORT_TILES_PER_CTA;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTA-uniform decision: if every tile of this CTA fits a warp's buffer, sort one tile per warp with
+  // warp-level synchronisation only; otherwise the whole CTA sorts the tiles one after the other.
+  int max_n = 0;
+  for (int u = 0; u < SORT_TILES_PER_CTA; ++u) {
+    const int t = t0 + u;
+    if (t < ntiles) max_n = max(max_n, offsets[t + 1] - offsets[t]);
   }
-  __syncthreads();
-  for (int k = 2; (k >> 1) < n; k <<= 1) {
-    // first step of the merge: partner = mirror image inside the block of size k
-    for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
-      const int j = i ^ (k - 1);
-      if (j > i && j < n) {
-        const int a = keys[i], b = keys[j];
-        if (b < a) {
-          keys[i] = b;
-          keys[j] = a;
-        }
+  if (max_n <= SORT_WARP_ELEMS) {
+    const int t = t0 + warp;
+    if (t >= ntiles) return;
+    const int begin = offsets[t], end = offsets[t + 1];
+    const int n = end - begin;
+    if (n < 2 || (int64_t)end > capacity) return;  // overflowed tiles are rasterised from the mesh range
+    int* keys = s_keys + warp * SORT_WARP_ELEMS;
+    for (int i = lane; i < n; i += 32) keys[i] = pairs[begin + i];
+    __syncwarp();
+    for (int k = 2; (k >> 1) < n; k <<= 1) {
+      sort_sweep<true>(keys, n, k, lane, 32);
+      __syncwarp();
+      for (int d = k >> 2; d > 0; d >>= 1) {
+        sort_sweep<false>(keys, n, d, lane, 32);
+        __syncwarp();
       }
     }
+    for (int i = lane; i < n; i += 32) pairs[begin + i] = keys[i];
+    return;
+  }
+  for (int u = 0; u < SORT_TILES_PER_CTA; ++u) {
+    const int t = t0 + u;
+    if (t >= ntiles) break;
+    const int begin = offsets[t], end = offsets[t + 1];
+    const int n = end - begin;
+    if (n < 2 || (int64_t)end > capacity) continue;
+    const bool in_smem = n <= SORT_SMEM_ELEMS;
+    int* keys = in_smem ? s_keys : pairs + begin;
     __syncthreads();
-    for (int d = k >> 2; d > 0; d >>= 1) {
-      for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
-        const int j = i ^ d;
-        if (j > i && j < n) {
-          const int a = keys[i], b = keys[j];
-          if (b < a) {
-            keys[i] = b;
-            keys[j] = a;
-          }
-        }
-      }
+    if (in_smem)
+      for (int i = threadIdx.x; i < n; i += SORT_THREADS) s_keys[i] = pairs[begin + i];
+    __syncthreads();
+    for (int k = 2; (k >> 1) < n; k <<= 1) {
+      sort_sweep<true>(keys, n, k, threadIdx.x, SORT_THREADS);
       __syncthreads();
+      for (int d = k >> 2; d > 0; d >>= 1) {
+        sort_sweep<false>(keys, n, d, threadIdx.x, SORT_THREADS);
+        __syncthreads();
+      }
     }
-  }
-  if (in_smem) {
-    for (int i = threadIdx.x; i < n; i += SORT_THREADS) pairs[begin + i] = s_keys[i];
+    if (in_smem)
+      for (int i = threadIdx.x; i < n; i += SORT_THREADS) pairs[begin + i] = s_keys[i];
   }
 }
 

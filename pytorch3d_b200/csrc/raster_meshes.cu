@@ -296,19 +296,46 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Faces are consumed in rounds of LIST_ROUND: every lane first records (one byte each, in a private
-// shared-memory column) which faces of the round pass ITS pixel's box test, then walks its own list.  In the
-// first half all lanes look at the same face (broadcast LDS, ~10 instructions); in the second half every lane
-// works on a different face that is known to touch its pixel, so the expensive arithmetic runs on (nearly)
-// full warps even when triangles are pixel-sized and only a handful of the footprint's 32 pixels lie in a
-// given face's box.
-constexpr int LIST_ROUND = 64;
+// Which pixels of a warp's 8x4 footprint lie inside a face's (blur-expanded) box?  One lane tests one face
+// against the 8 column and 4 row coordinates of the footprint and builds the 32-bit pixel mask
+// (bit = lane of the pixel); the box test is the reference's `px > xmax || px < xmin || ...` (:94-97).
+__device__ __forceinline__ unsigned box_pixel_mask(const float4 bx, const float (&col)[8], const float (&row)[4]) {
+  unsigned xm = 0, ym = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) xm |= (!(col[c] > bx.y || col[c] < bx.x) ? 1u : 0u) << c;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) ym |= (!(row[r] > bx.w || row[r] < bx.z) ? 1u : 0u) << (8 * r);
+  return xm * ym;  // ym has one bit per byte, xm < 256: the product replicates xm into the selected rows
+}
+
+// Transpose a 32x32 bit matrix held one row per lane (5 butterfly stages of shuffles): afterwards bit k of
+// lane l's word is what bit l of lane k's word was.  Turns "pixel mask per face" into "face mask per pixel".
+__device__ __forceinline__ unsigned warp_transpose_bits(unsigned a, int lane) {
+#pragma unroll
+  for (int sft = 16; sft >= 1; sft >>= 1) {
+    const unsigned lo = sft == 16 ? 0x0000FFFFu
+                      : sft == 8 ? 0x00FF00FFu
+                      : sft == 4 ? 0x0F0F0F0Fu
+                      : sft == 2 ? 0x33333333u : 0x55555555u;
+    const unsigned other = __shfl_xor_sync(0xffffffffu, a, sft);
+    a = (lane & sft) ? ((a & ~lo) | ((other & ~lo) >> sft)) : ((a & lo) | ((other & lo) << sft));
+  }
+  return a;
+}
+
+// Faces are consumed in rounds of 64.  Pass A: each lane box-tests one face against the whole footprint and
+// the warp transposes the resulting bit matrix, so that every lane ends up with a 64-bit mask of the faces
+// whose box contains ITS pixel (ascending face order = ascending bit order).  Pass B: every lane walks its
+// own mask.  In pass A the warp does ~80 instructions per 32 faces no matter how many survive; in pass B
+// each lane works on a different face that is known to touch its pixel, so the expensive arithmetic runs on
+// (nearly) full warps even when triangles are pixel-sized and only a handful of the footprint's 32 pixels
+// lie in a given face's box.
+constexpr int ROUND = 64;
 
 template <int KMAX, bool NB>
 __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParams p) {
   __shared__ FaceChunk s;
-  __shared__ unsigned char s_list[TILE_THREADS / 32][LIST_ROUND][32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int t = blockIdx.x;
   const int n = t / (p.TY * p.TX);
   const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
@@ -318,9 +345,12 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParam
   const bool valid = xo < p.W && yo < p.H;
   const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
   const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
-  // NDC extent of the warp's valid pixel centres (empty if the footprint is outside the image)
-  const float fx_lo = warp_min(valid ? px : FLT_MAX), fx_hi = warp_max(valid ? px : -FLT_MAX);
-  const float fy_lo = warp_min(valid ? py : FLT_MAX), fy_hi = warp_max(valid ? py : -FLT_MAX);
+  // the footprint's 8 column and 4 row coordinates (lane = row * 8 + column)
+  float col[8], row[4];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) col[c] = __shfl_sync(0xffffffffu, px, c);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) row[r] = __shfl_sync(0xffffffffu, py, 8 * r);
 
   // the tile's face list; tiles whose segment did not fit the pair buffer test every face of the mesh
   const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
@@ -342,32 +372,19 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParam
       stage_face(s, tid, p.face_verts, p.neighbor, f, p.sqrt_blur, cull);
     }
     __syncthreads();
-    for (int sub = 0; sub < nc; sub += LIST_ROUND) {
-      // ---- pass A: which faces of this round touch my pixel?  (ascending order is preserved)
-      int cnt = 0;
-      const int sub_end = min(nc, sub + LIST_ROUND);
-      for (int g = sub; g < sub_end; g += 32) {
-        bool touch = false;
-        if (g + lane < sub_end) {  // cull 32 faces against the warp footprint: one face per lane
-          const float4 bx = s.box[g + lane];
-          touch = !(fx_lo > bx.y || fx_hi < bx.x || fy_lo > bx.w || fy_hi < bx.z);
-        }
-        unsigned m = __ballot_sync(0xffffffffu, touch);
-        while (m) {
-          const int j = g + __ffs(m) - 1;
-          m &= m - 1;
-          const float4 bx = s.box[j];
-          if (valid && !(px > bx.y || px < bx.x || py > bx.w || py < bx.z)) {  // (:94-97)
-            s_list[warp][cnt][lane] = (unsigned char)j;
-            ++cnt;
-          }
-        }
-      }
-      // ---- pass B: every lane evaluates its own candidates
-      const int rounds = (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt);
-      for (int i = 0; i < rounds; ++i) {
-        if (i < cnt) {
-          const int j = s_list[warp][i][lane];
+    for (int sub = 0; sub < nc; sub += ROUND) {
+      // ---- pass A: 64-bit mask of the faces of this round whose box contains my pixel
+      unsigned m0 = 0, m1 = 0;
+      if (sub + lane < nc) m0 = box_pixel_mask(s.box[sub + lane], col, row);
+      if (sub + 32 + lane < nc) m1 = box_pixel_mask(s.box[sub + 32 + lane], col, row);
+      m0 = warp_transpose_bits(m0, lane);
+      if (sub + 32 < nc) m1 = warp_transpose_bits(m1, lane);
+      unsigned long long mine = valid ? (((unsigned long long)m1 << 32) | m0) : 0ull;
+      // ---- pass B: every lane evaluates its own candidates, in ascending face order
+      while (__any_sync(0xffffffffu, mine != 0ull)) {
+        if (mine != 0ull) {
+          const int j = sub + __ffsll((long long)mine) - 1;
+          mine &= mine - 1ull;
           const float4 fa = s.a[j], fb = s.b[j], fc = s.c[j];
           const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
           float pz, dist = 0.0f;
@@ -387,55 +404,61 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParam
 
   if (!valid) return;
   q.sort();
-  // ---- epilogue: barycentrics / distance of the winners, then one vectorised write per output
-  float od[KMAX], ob0[KMAX], ob1[KMAX], ob2[KMAX];
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    od[k] = ob0[k] = ob1[k] = ob2[k] = -1.0f;
-    if (k < q.size) {
-      const float* v = p.face_verts + (int64_t)q.id[k] * 9;
-      const Face f = {__ldg(v + 0), __ldg(v + 1), __ldg(v + 2), __ldg(v + 3), __ldg(v + 4),
-                      __ldg(v + 5), __ldg(v + 6), __ldg(v + 7), __ldg(v + 8)};
-      Hit h;
-      eval_pixel_face(px, py, f, bary_denominator(f), blur_radius, persp, clip, h);
-      od[k] = h.dist;
-      ob0[k] = h.b0;
-      ob1[k] = h.b1;
-      ob2[k] = h.b2;
-    }
-  }
+  // ---- epilogue: barycentrics / distance of the winners are recomputed, four slots at a time, and every
+  //      output is written with 16-byte stores (all K slots, including the -1 padding)
   const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
-  if (K == KMAX && (KMAX % 4) == 0) {
+  const bool vec = K == KMAX && (KMAX % 4) == 0;
+  if (vec) {
     longlong2* pf = reinterpret_cast<longlong2*>(p.pix_to_face + o);
-    float4* pzv = reinterpret_cast<float4*>(p.zbuf + o);
-    float4* pd = reinterpret_cast<float4*>(p.dists + o);
-    float4* pb = reinterpret_cast<float4*>(p.bary + o * 3);
 #pragma unroll
     for (int k = 0; k < KMAX; k += 2) {
       const long long i0 = k >= q.size ? -1ll : (long long)q.id[k];
       const long long i1 = k + 1 >= q.size ? -1ll : (long long)q.id[k + 1];
       pf[k / 2] = make_longlong2(i0, i1);
     }
+  }
 #pragma unroll
-    for (int k = 0; k < KMAX; k += 4) {
-      pzv[k / 4] = make_float4(k >= q.size ? -1.0f : q.z[k], k + 1 >= q.size ? -1.0f : q.z[k + 1],
-                               k + 2 >= q.size ? -1.0f : q.z[k + 2], k + 3 >= q.size ? -1.0f : q.z[k + 3]);
-      pd[k / 4] = make_float4(od[k], od[k + 1], od[k + 2], od[k + 3]);
-      pb[3 * (k / 4) + 0] = make_float4(ob0[k], ob1[k], ob2[k], ob0[k + 1]);
-      pb[3 * (k / 4) + 1] = make_float4(ob1[k + 1], ob2[k + 1], ob0[k + 2], ob1[k + 2]);
-      pb[3 * (k / 4) + 2] = make_float4(ob2[k + 2], ob0[k + 3], ob1[k + 3], ob2[k + 3]);
+  for (int k0 = 0; k0 < KMAX; k0 += 4) {
+    float od[4], ob0[4], ob1[4], ob2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u;
+      od[u] = ob0[u] = ob1[u] = ob2[u] = -1.0f;
+      if (k < KMAX && k < q.size) {
+        const float* v = p.face_verts + (int64_t)q.id[k < KMAX ? k : 0] * 9;
+        const Face f = {__ldg(v + 0), __ldg(v + 1), __ldg(v + 2), __ldg(v + 3), __ldg(v + 4),
+                        __ldg(v + 5), __ldg(v + 6), __ldg(v + 7), __ldg(v + 8)};
+        Hit h;
+        eval_pixel_face(px, py, f, bary_denominator(f), blur_radius, persp, clip, h);
+        od[u] = h.dist;
+        ob0[u] = h.b0;
+        ob1[u] = h.b1;
+        ob2[u] = h.b2;
+      }
     }
-  } else {
+    if (vec) {
+      float zz[4];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k < K) {
-        const bool e = k >= q.size;
-        p.pix_to_face[o + k] = e ? -1ll : (long long)q.id[k];
-        p.zbuf[o + k] = e ? -1.0f : q.z[k];
-        p.dists[o + k] = od[k];
-        p.bary[(o + k) * 3 + 0] = ob0[k];
-        p.bary[(o + k) * 3 + 1] = ob1[k];
-        p.bary[(o + k) * 3 + 2] = ob2[k];
+      for (int u = 0; u < 4; ++u) zz[u] = (k0 + u) >= q.size ? -1.0f : q.z[(k0 + u) < KMAX ? k0 + u : 0];
+      reinterpret_cast<float4*>(p.zbuf + o)[k0 / 4] = make_float4(zz[0], zz[1], zz[2], zz[3]);
+      reinterpret_cast<float4*>(p.dists + o)[k0 / 4] = make_float4(od[0], od[1], od[2], od[3]);
+      float4* pb = reinterpret_cast<float4*>(p.bary + o * 3) + 3 * (k0 / 4);
+      pb[0] = make_float4(ob0[0], ob1[0], ob2[0], ob0[1]);
+      pb[1] = make_float4(ob1[1], ob2[1], ob0[2], ob1[2]);
+      pb[2] = make_float4(ob2[2], ob0[3], ob1[3], ob2[3]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u;
+        if (k < KMAX && k < K) {
+          const bool e = k >= q.size;
+          p.pix_to_face[o + k] = e ? -1ll : (long long)q.id[k < KMAX ? k : 0];
+          p.zbuf[o + k] = e ? -1.0f : q.z[k < KMAX ? k : 0];
+          p.dists[o + k] = od[u];
+          p.bary[(o + k) * 3 + 0] = ob0[u];
+          p.bary[(o + k) * 3 + 1] = ob1[u];
+          p.bary[(o + k) * 3 + 2] = ob2[u];
+        }
       }
     }
   }
@@ -605,6 +628,107 @@ __device__ __forceinline__ void point_line_bwd(float px, float py, float ax, flo
   gb = make_float2(g * t * cx, g * t * cy);
 }
 
+// Gradient of one (pixel, face) hit, scattered into grad_face_verts with 9 atomics.
+__device__ __forceinline__ void backward_one(const BackwardParams& p, float px, float py, int64_t fi, float gz,
+                                             float gd, float gb0, float gb1, float gb2, bool persp, bool clip) {
+  const float* v = p.face_verts + fi * 9;
+  const Face f = {__ldg(v + 0), __ldg(v + 1), __ldg(v + 2), __ldg(v + 3), __ldg(v + 4),
+                  __ldg(v + 5), __ldg(v + 6), __ldg(v + 7), __ldg(v + 8)};
+  const float den = bary_denominator(f);
+  float w0, w1, w2;
+  bary_coords(px, py, f, den, w0, w1, w2);
+  float c0 = w0, c1 = w1, c2 = w2;  // (perspective-corrected) barycentrics
+  if (persp) bary_persp(c0, c1, c2, f.z0, f.z1, f.z2);
+  float k0 = c0, k1 = c1, k2 = c2;  // clipped
+  if (clip) bary_clip(k0, k1, k2);
+  const bool inside = c0 > 0.0f && c1 > 0.0f && c2 > 0.0f;
+  const float sgd = inside ? -gd : gd;
+
+  // d dist / d verts: gradient flows to the closest edge only (geometry_utils.cuh:421-462)
+  float2 dv0 = make_float2(0.f, 0.f), dv1 = dv0, dv2 = dv0;
+  {
+    const float e01 = point_line_dist(px, py, f.x0, f.y0, f.x1, f.y1);
+    const float e02 = point_line_dist(px, py, f.x0, f.y0, f.x2, f.y2);
+    const float e12 = point_line_dist(px, py, f.x1, f.y1, f.x2, f.y2);
+    if (e01 <= e02 && e01 <= e12)
+      point_line_bwd(px, py, f.x0, f.y0, f.x1, f.y1, sgd, dv0, dv1);
+    else if (e02 <= e01 && e02 <= e12)
+      point_line_bwd(px, py, f.x0, f.y0, f.x2, f.y2, sgd, dv0, dv2);
+    else if (e12 <= e01 && e12 <= e02)
+      point_line_bwd(px, py, f.x1, f.y1, f.x2, f.y2, sgd, dv1, dv2);
+  }
+
+  // upstream gradient on the (clipped) barycentrics, including zbuf = sum_i bary_i * z_i
+  float g0 = gb0 + gz * f.z0, g1 = gb1 + gz * f.z1, g2 = gb2 + gz * f.z2;
+  if (clip) {  // BarycentricClipBackward (geometry_utils.cuh:273-329) on the corrected barycentrics
+    const float m0 = fmaxf(c0, 0.0f), m1 = fmaxf(c1, 0.0f), m2 = fmaxf(c2, 0.0f);
+    float sum = m0 + m1 + m2, gsc = 1.0f;
+    if (sum < 1e-5f) {
+      gsc = 0.0f;
+      sum = 1e-5f;
+    }
+    const float inv = 1.0f / sum, inv2 = gsc / (sum * sum);
+    const float s0 = -m0 * inv2, s1 = -m1 * inv2, s2 = -m2 * inv2;
+    const float cross = g0 * s0 + g1 * s1 + g2 * s2;
+    const float n0 = c0 < 0.0f ? 0.0f : g0 * inv + cross;
+    const float n1 = c1 < 0.0f ? 0.0f : g1 * inv + cross;
+    const float n2 = c2 < 0.0f ? 0.0f : g2 * inv + cross;
+    g0 = n0;
+    g1 = n1;
+    g2 = n2;
+  }
+  float dz0 = 0.0f, dz1 = 0.0f, dz2 = 0.0f;
+  if (persp) {  // BarycentricPerspectiveCorrectionBackward (geometry_utils.cuh:200-228)
+    const float t0 = w0 * f.z1 * f.z2, t1 = f.z0 * w1 * f.z2, t2 = f.z0 * f.z1 * w2;
+    const float dn = fmaxf(t0 + t1 + t2, 1e-8f);
+    const float gdn = (-t0 * g0 - t1 * g1 - t2 * g2) / (dn * dn);
+    const float h0 = gdn + g0 / dn, h1 = gdn + g1 / dn, h2 = gdn + g2 / dn;
+    g0 = h0 * f.z1 * f.z2;
+    g1 = h1 * f.z0 * f.z2;
+    g2 = h2 * f.z0 * f.z1;
+    dz0 = h1 * w1 * f.z2 + h2 * w2 * f.z1;
+    dz1 = h0 * w0 * f.z2 + h2 * w2 * f.z0;
+    dz2 = h0 * w0 * f.z1 + h1 * w1 * f.z0;
+  }
+  // BarycentricCoordsBackward (geometry_utils.cuh:101-161)
+  float2 bv0 = make_float2(0.f, 0.f), bv1 = bv0, bv2 = bv0;
+  {
+    const float area2 = den * den, rden = 1.0f / den;
+    const float e0 = edge_fn(px, py, f.x1, f.y1, f.x2, f.y2);
+    const float e1 = edge_fn(px, py, f.x2, f.y2, f.x0, f.y0);
+    const float e2 = edge_fn(px, py, f.x0, f.y0, f.x1, f.y1);
+    float2 dp, da, db, ap, aa, ab;
+    // every w_i = e_i / area also depends on area = E(v2; v0, v1)
+    const float garea = g0 * (-e0 / area2) + g1 * (-e1 / area2) + g2 * (-e2 / area2);
+    edge_bwd(f.x2, f.y2, f.x0, f.y0, f.x1, f.y1, garea, ap, aa, ab);  // (p=v2, a=v0, b=v1)
+    bv2.x += ap.x; bv2.y += ap.y;
+    bv0.x += aa.x; bv0.y += aa.y;
+    bv1.x += ab.x; bv1.y += ab.y;
+    edge_bwd(px, py, f.x1, f.y1, f.x2, f.y2, g0 * rden, dp, da, db);  // w0: (p, v1, v2)
+    bv1.x += da.x; bv1.y += da.y;
+    bv2.x += db.x; bv2.y += db.y;
+    edge_bwd(px, py, f.x2, f.y2, f.x0, f.y0, g1 * rden, dp, da, db);  // w1: (p, v2, v0)
+    bv2.x += da.x; bv2.y += da.y;
+    bv0.x += db.x; bv0.y += db.y;
+    edge_bwd(px, py, f.x0, f.y0, f.x1, f.y1, g2 * rden, dp, da, db);  // w2: (p, v0, v1)
+    bv0.x += da.x; bv0.y += da.y;
+    bv1.x += db.x; bv1.y += db.y;
+  }
+  float* g = p.grad_face_verts + fi * 9;
+  atomicAdd(g + 0, bv0.x + dv0.x);
+  atomicAdd(g + 1, bv0.y + dv0.y);
+  atomicAdd(g + 2, gz * k0 + dz0);
+  atomicAdd(g + 3, bv1.x + dv1.x);
+  atomicAdd(g + 4, bv1.y + dv1.y);
+  atomicAdd(g + 5, gz * k1 + dz1);
+  atomicAdd(g + 6, bv2.x + dv2.x);
+  atomicAdd(g + 7, bv2.y + dv2.y);
+  atomicAdd(g + 8, gz * k2 + dz2);
+}
+
+// VEC: K is a multiple of 4 -> the 28 bytes/slot of (pix_to_face, grad_zbuf, grad_dists, grad_bary) are read
+// with 16-byte loads, four slots at a time; a group whose four faces are all -1 costs only the index load.
+template <bool VEC>
 __global__ void __launch_bounds__(TILE_THREADS) mesh_backward_kernel(const BackwardParams p) {
   const int t = blockIdx.x;
   const int n = t / (p.TY * p.TX);
@@ -618,106 +742,32 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_backward_kernel(const Backw
   const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
   const bool persp = p.persp != 0, clip = p.clip != 0;
 
-  for (int k = 0; k < K; ++k) {
-    const int64_t i = o + k;
-    const int64_t fi = p.pix_to_face[i];
-    if (fi < 0) continue;
-    const float* v = p.face_verts + fi * 9;
-    const Face f = {__ldg(v + 0), __ldg(v + 1), __ldg(v + 2), __ldg(v + 3), __ldg(v + 4),
-                    __ldg(v + 5), __ldg(v + 6), __ldg(v + 7), __ldg(v + 8)};
-    const float gz = p.grad_zbuf[i], gd = p.grad_dists[i];
-    const float gb0 = p.grad_bary[i * 3 + 0], gb1 = p.grad_bary[i * 3 + 1], gb2 = p.grad_bary[i * 3 + 2];
-
-    const float den = bary_denominator(f);
-    float w0, w1, w2;
-    bary_coords(px, py, f, den, w0, w1, w2);
-    float c0 = w0, c1 = w1, c2 = w2;  // (perspective-corrected) barycentrics
-    if (persp) bary_persp(c0, c1, c2, f.z0, f.z1, f.z2);
-    float k0 = c0, k1 = c1, k2 = c2;  // clipped
-    if (clip) bary_clip(k0, k1, k2);
-    const bool inside = c0 > 0.0f && c1 > 0.0f && c2 > 0.0f;
-    const float sgd = inside ? -gd : gd;
-
-    // d dist / d verts: gradient flows to the closest edge only (geometry_utils.cuh:421-462)
-    float2 dv0 = make_float2(0.f, 0.f), dv1 = dv0, dv2 = dv0;
-    {
-      const float e01 = point_line_dist(px, py, f.x0, f.y0, f.x1, f.y1);
-      const float e02 = point_line_dist(px, py, f.x0, f.y0, f.x2, f.y2);
-      const float e12 = point_line_dist(px, py, f.x1, f.y1, f.x2, f.y2);
-      if (e01 <= e02 && e01 <= e12)
-        point_line_bwd(px, py, f.x0, f.y0, f.x1, f.y1, sgd, dv0, dv1);
-      else if (e02 <= e01 && e02 <= e12)
-        point_line_bwd(px, py, f.x0, f.y0, f.x2, f.y2, sgd, dv0, dv2);
-      else if (e12 <= e01 && e12 <= e02)
-        point_line_bwd(px, py, f.x1, f.y1, f.x2, f.y2, sgd, dv1, dv2);
-    }
-
-    // upstream gradient on the (clipped) barycentrics, including zbuf = sum_i bary_i * z_i
-    float g0 = gb0 + gz * f.z0, g1 = gb1 + gz * f.z1, g2 = gb2 + gz * f.z2;
-    if (clip) {  // BarycentricClipBackward (geometry_utils.cuh:273-329) on the corrected barycentrics
-      const float m0 = fmaxf(c0, 0.0f), m1 = fmaxf(c1, 0.0f), m2 = fmaxf(c2, 0.0f);
-      float sum = m0 + m1 + m2, gsc = 1.0f;
-      if (sum < 1e-5f) {
-        gsc = 0.0f;
-        sum = 1e-5f;
+  if (VEC) {
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      const longlong2 ia = __ldg(reinterpret_cast<const longlong2*>(p.pix_to_face + o + k0));
+      const longlong2 ib = __ldg(reinterpret_cast<const longlong2*>(p.pix_to_face + o + k0) + 1);
+      const long long fi[4] = {ia.x, ia.y, ib.x, ib.y};
+      if ((fi[0] & fi[1] & fi[2] & fi[3]) < 0) continue;  // all four negative (padding)
+      const float4 gz = __ldg(reinterpret_cast<const float4*>(p.grad_zbuf + o + k0));
+      const float4 gd = __ldg(reinterpret_cast<const float4*>(p.grad_dists + o + k0));
+      const float4* gbp = reinterpret_cast<const float4*>(p.grad_bary + (o + k0) * 3);
+      const float4 b0 = __ldg(gbp), b1 = __ldg(gbp + 1), b2 = __ldg(gbp + 2);
+      const float gzs[4] = {gz.x, gz.y, gz.z, gz.w}, gds[4] = {gd.x, gd.y, gd.z, gd.w};
+      const float gbs[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (fi[u] < 0) continue;  // padded face (:472-474)
+        backward_one(p, px, py, fi[u], gzs[u], gds[u], gbs[3 * u], gbs[3 * u + 1], gbs[3 * u + 2], persp, clip);
       }
-      const float inv = 1.0f / sum, inv2 = gsc / (sum * sum);
-      const float s0 = -m0 * inv2, s1 = -m1 * inv2, s2 = -m2 * inv2;
-      const float cross = g0 * s0 + g1 * s1 + g2 * s2;
-      const float n0 = c0 < 0.0f ? 0.0f : g0 * inv + cross;
-      const float n1 = c1 < 0.0f ? 0.0f : g1 * inv + cross;
-      const float n2 = c2 < 0.0f ? 0.0f : g2 * inv + cross;
-      g0 = n0;
-      g1 = n1;
-      g2 = n2;
     }
-    float dz0 = 0.0f, dz1 = 0.0f, dz2 = 0.0f;
-    if (persp) {  // BarycentricPerspectiveCorrectionBackward (geometry_utils.cuh:200-228)
-      const float t0 = w0 * f.z1 * f.z2, t1 = f.z0 * w1 * f.z2, t2 = f.z0 * f.z1 * w2;
-      const float dn = fmaxf(t0 + t1 + t2, 1e-8f);
-      const float gdn = (-t0 * g0 - t1 * g1 - t2 * g2) / (dn * dn);
-      const float h0 = gdn + g0 / dn, h1 = gdn + g1 / dn, h2 = gdn + g2 / dn;
-      g0 = h0 * f.z1 * f.z2;
-      g1 = h1 * f.z0 * f.z2;
-      g2 = h2 * f.z0 * f.z1;
-      dz0 = h1 * w1 * f.z2 + h2 * w2 * f.z1;
-      dz1 = h0 * w0 * f.z2 + h2 * w2 * f.z0;
-      dz2 = h0 * w0 * f.z1 + h1 * w1 * f.z0;
+  } else {
+    for (int k = 0; k < K; ++k) {
+      const int64_t i = o + k;
+      const int64_t fi = p.pix_to_face[i];
+      if (fi < 0) continue;
+      backward_one(p, px, py, fi, p.grad_zbuf[i], p.grad_dists[i], p.grad_bary[i * 3 + 0], p.grad_bary[i * 3 + 1],
+                   p.grad_bary[i * 3 + 2], persp, clip);
     }
-    // BarycentricCoordsBackward (geometry_utils.cuh:101-161)
-    float2 bv0 = make_float2(0.f, 0.f), bv1 = bv0, bv2 = bv0;
-    {
-      const float area2 = den * den, rden = 1.0f / den;
-      const float e0 = edge_fn(px, py, f.x1, f.y1, f.x2, f.y2);
-      const float e1 = edge_fn(px, py, f.x2, f.y2, f.x0, f.y0);
-      const float e2 = edge_fn(px, py, f.x0, f.y0, f.x1, f.y1);
-      float2 dp, da, db, ap, aa, ab;
-      // every w_i = e_i / area also depends on area = E(v2; v0, v1)
-      const float garea = g0 * (-e0 / area2) + g1 * (-e1 / area2) + g2 * (-e2 / area2);
-      edge_bwd(f.x2, f.y2, f.x0, f.y0, f.x1, f.y1, garea, ap, aa, ab);  // (p=v2, a=v0, b=v1)
-      bv2.x += ap.x; bv2.y += ap.y;
-      bv0.x += aa.x; bv0.y += aa.y;
-      bv1.x += ab.x; bv1.y += ab.y;
-      edge_bwd(px, py, f.x1, f.y1, f.x2, f.y2, g0 * rden, dp, da, db);  // w0: (p, v1, v2)
-      bv1.x += da.x; bv1.y += da.y;
-      bv2.x += db.x; bv2.y += db.y;
-      edge_bwd(px, py, f.x2, f.y2, f.x0, f.y0, g1 * rden, dp, da, db);  // w1: (p, v2, v0)
-      bv2.x += da.x; bv2.y += da.y;
-      bv0.x += db.x; bv0.y += db.y;
-      edge_bwd(px, py, f.x0, f.y0, f.x1, f.y1, g2 * rden, dp, da, db);  // w2: (p, v0, v1)
-      bv0.x += da.x; bv0.y += da.y;
-      bv1.x += db.x; bv1.y += db.y;
-    }
-    float* g = p.grad_face_verts + fi * 9;
-    atomicAdd(g + 0, bv0.x + dv0.x);
-    atomicAdd(g + 1, bv0.y + dv0.y);
-    atomicAdd(g + 2, gz * k0 + dz0);
-    atomicAdd(g + 3, bv1.x + dv1.x);
-    atomicAdd(g + 4, bv1.y + dv1.y);
-    atomicAdd(g + 5, gz * k1 + dz1);
-    atomicAdd(g + 6, bv2.x + dv2.x);
-    atomicAdd(g + 7, bv2.y + dv2.y);
-    atomicAdd(g + 8, gz * k2 + dz2);
   }
 }
 
@@ -777,7 +827,8 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
     B200R_LAUNCHED("tile_fill_kernel");
   }
   if (ntiles > 0) {
-    tile_sort_kernel<<<(unsigned)ntiles, SORT_THREADS, 0, stream>>>(ws.tile_offset, ws.pairs, ws.capacity);
+    tile_sort_kernel<<<(unsigned)((ntiles + SORT_TILES_PER_CTA - 1) / SORT_TILES_PER_CTA), SORT_THREADS, 0, stream>>>(
+        ws.tile_offset, ws.pairs, ws.capacity, (int)ntiles);
     B200R_LAUNCHED("tile_sort_kernel");
   }
   if (prof) phase_timer().record(1, stream);
@@ -840,7 +891,10 @@ extern "C" int b200r_rasterize_meshes_backward(const float* face_verts, int64_t 
   p.grad_face_verts = grad_face_verts;
   const bool prof = profiling_enabled();
   if (prof) phase_timer().record(3, stream);
-  mesh_backward_kernel<<<(unsigned)((int64_t)N * TY * TX), TILE_THREADS, 0, stream>>>(p);
+  if (K % 4 == 0)
+    mesh_backward_kernel<true><<<(unsigned)((int64_t)N * TY * TX), TILE_THREADS, 0, stream>>>(p);
+  else
+    mesh_backward_kernel<false><<<(unsigned)((int64_t)N * TY * TX), TILE_THREADS, 0, stream>>>(p);
   B200R_LAUNCHED("mesh_backward_kernel");
   if (prof) {
     phase_timer().record(4, stream);

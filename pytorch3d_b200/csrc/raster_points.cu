@@ -366,7 +366,8 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
                                                                     ws.capacity);
     B200R_LAUNCHED("tile_fill_kernel");
   }
-  tile_sort_kernel<<<(unsigned)ntiles, SORT_THREADS, 0, stream>>>(ws.tile_offset, ws.pairs, ws.capacity);
+  tile_sort_kernel<<<(unsigned)((ntiles + SORT_TILES_PER_CTA - 1) / SORT_TILES_PER_CTA), SORT_THREADS, 0, stream>>>(
+        ws.tile_offset, ws.pairs, ws.capacity, (int)ntiles);
   B200R_LAUNCHED("tile_sort_kernel");
   if (prof) phase_timer().record(1, stream);
   PointFineParams p;

@@ -107,10 +107,14 @@ def test_mesh_golden_fixtures(ops, dev, golden):
         assert np.array_equal(mine[0].cpu().numpy(), c["pix_to_face"]), name
         for got, want in zip(mine[1:], (c["zbuf"], c["bary"], c["dists"])):
             err = np.abs(got.cpu().numpy() - want)
-            # 1e-5 absolute (the north-star bar).  The seeded random scenes with perspective correction and
-            # no clipping contain sliver faces whose extrapolated barycentrics reach 1e10; there only a
-            # relative bound is meaningful (fixtures come from the reference's non-FMA CPU arithmetic).
-            tol = np.where(np.abs(want) <= 10.0, 1e-5, 1e-2 * np.abs(want))
+            # Known-answer scenes of the reference: 1e-5 absolute (the north-star bar).  The seeded random
+            # scenes contain sliver faces and (with perspective correction, no clipping) extrapolated
+            # barycentrics up to 1e10; the fixtures come from the reference's non-FMA CPU arithmetic, so there
+            # the reference's own cross-implementation tolerance applies (test_rasterize_meshes.py:543-594).
+            if "/random/" in name:
+                tol = 1e-5 + 1e-3 * np.abs(want)
+            else:
+                tol = np.full_like(want, 1e-5)
             assert (err <= tol).all(), name
 
 
