@@ -127,13 +127,13 @@ static __global__ void __launch_bounds__(256)
 // partners beyond the end are treated as +inf and skipped.
 constexpr int SORT_THREADS = 128;
 constexpr int SORT_TILES_PER_CTA = SORT_THREADS / 32;  // one warp per tile on the fast path
-constexpr int SORT_WARP_ELEMS = 1024;                   // per-warp shared-memory capacity
-constexpr int SORT_SMEM_ELEMS = SORT_TILES_PER_CTA * SORT_WARP_ELEMS;
+constexpr int SORT_RANK_MAX = 256;                      // fast path: segments of up to 8 keys per lane
+constexpr int SORT_SMEM_ELEMS = 4096;
 
-// One compare-exchange sweep of the network over keys[0..n) by `nthreads` cooperating threads.
+// One compare-exchange sweep of the bitonic network over keys[0..n) by the whole CTA.
 template <bool MIRROR>
-__device__ __forceinline__ void sort_sweep(int* keys, int n, int d, int tid, int nthreads) {
-  for (int i = tid; i < n; i += nthreads) {
+__device__ __forceinline__ void sort_sweep(int* keys, int n, int d) {
+  for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
     const int j = MIRROR ? (i ^ (d - 1)) : (i ^ d);  // MIRROR: d is the block size k
     if (j > i && j < n) {
       const int a = keys[i], b = keys[j];
@@ -150,31 +150,41 @@ static __global__ void __launch_bounds__(SORT_THREADS)
   __shared__ int s_keys[SORT_SMEM_ELEMS];
   const int t0 = blockIdx.x * SORT_TILES_PER_CTA;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // CTA-uniform decision: if every tile of this CTA fits a warp's buffer, sort one tile per warp with
-  // warp-level synchronisation only; otherwise the whole CTA sorts the tiles one after the other.
+  // CTA-uniform decision: short segments (the common case) are rank-sorted one tile per warp -- every key's
+  // final position is the number of smaller keys (keys are unique), counted with independent compares
+  // against a broadcast shared-memory copy: no network, no barriers.  Long segments are bitonic-sorted by
+  // the whole CTA, one tile after the other.
   int max_n = 0;
   for (int u = 0; u < SORT_TILES_PER_CTA; ++u) {
     const int t = t0 + u;
     if (t < ntiles) max_n = max(max_n, offsets[t + 1] - offsets[t]);
   }
-  if (max_n <= SORT_WARP_ELEMS) {
+  if (max_n <= SORT_RANK_MAX) {
     const int t = t0 + warp;
     if (t >= ntiles) return;
     const int begin = offsets[t], end = offsets[t + 1];
     const int n = end - begin;
     if (n < 2 || (int64_t)end > capacity) return;  // overflowed tiles are rasterised from the mesh range
-    int* keys = s_keys + warp * SORT_WARP_ELEMS;
-    for (int i = lane; i < n; i += 32) keys[i] = pairs[begin + i];
-    __syncwarp();
-    for (int k = 2; (k >> 1) < n; k <<= 1) {
-      sort_sweep<true>(keys, n, k, lane, 32);
-      __syncwarp();
-      for (int d = k >> 2; d > 0; d >>= 1) {
-        sort_sweep<false>(keys, n, d, lane, 32);
-        __syncwarp();
-      }
+    int* keys = s_keys + warp * SORT_RANK_MAX;
+    int mine[SORT_RANK_MAX / 32], rank[SORT_RANK_MAX / 32];
+#pragma unroll
+    for (int u = 0; u < SORT_RANK_MAX / 32; ++u) {
+      const int i = lane + 32 * u;
+      mine[u] = i < n ? pairs[begin + i] : 0x7fffffff;
+      rank[u] = 0;
+      if (i < n) keys[i] = mine[u];
     }
-    for (int i = lane; i < n; i += 32) pairs[begin + i] = keys[i];
+    __syncwarp();
+    const int cols = (n + 31) >> 5;  // keys per lane actually in use (warp-uniform)
+    for (int i = 0; i < n; ++i) {
+      const int k = keys[i];
+#pragma unroll
+      for (int u = 0; u < SORT_RANK_MAX / 32; ++u)
+        if (u < cols) rank[u] += k < mine[u] ? 1 : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < SORT_RANK_MAX / 32; ++u)
+      if (lane + 32 * u < n) pairs[begin + rank[u]] = mine[u];
     return;
   }
   for (int u = 0; u < SORT_TILES_PER_CTA; ++u) {
@@ -190,10 +200,10 @@ static __global__ void __launch_bounds__(SORT_THREADS)
       for (int i = threadIdx.x; i < n; i += SORT_THREADS) s_keys[i] = pairs[begin + i];
     __syncthreads();
     for (int k = 2; (k >> 1) < n; k <<= 1) {
-      sort_sweep<true>(keys, n, k, threadIdx.x, SORT_THREADS);
+      sort_sweep<true>(keys, n, k);
       __syncthreads();
       for (int d = k >> 2; d > 0; d >>= 1) {
-        sort_sweep<false>(keys, n, d, threadIdx.x, SORT_THREADS);
+        sort_sweep<false>(keys, n, d);
         __syncthreads();
       }
     }

@@ -752,12 +752,20 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_backward_kernel(const Backw
       const float4 gd = __ldg(reinterpret_cast<const float4*>(p.grad_dists + o + k0));
       const float4* gbp = reinterpret_cast<const float4*>(p.grad_bary + (o + k0) * 3);
       const float4 b0 = __ldg(gbp), b1 = __ldg(gbp + 1), b2 = __ldg(gbp + 2);
-      const float gzs[4] = {gz.x, gz.y, gz.z, gz.w}, gds[4] = {gd.x, gd.y, gd.z, gd.w};
-      const float gbs[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
-#pragma unroll
+      // one copy of the gradient code: the four slots rotate through the same registers
+      long long f0 = fi[0], f1 = fi[1], f2 = fi[2], f3 = fi[3];
+      float z0 = gz.x, z1 = gz.y, z2 = gz.z, z3 = gz.w;
+      float d0 = gd.x, d1 = gd.y, d2 = gd.z, d3 = gd.w;
+      float a0 = b0.x, a1 = b0.y, a2 = b0.z, a3 = b0.w, a4 = b1.x, a5 = b1.y, a6 = b1.z, a7 = b1.w, a8 = b2.x,
+            a9 = b2.y, a10 = b2.z, a11 = b2.w;
+#pragma unroll 1
       for (int u = 0; u < 4; ++u) {
-        if (fi[u] < 0) continue;  // padded face (:472-474)
-        backward_one(p, px, py, fi[u], gzs[u], gds[u], gbs[3 * u], gbs[3 * u + 1], gbs[3 * u + 2], persp, clip);
+        if (f0 >= 0)  // else: padded face (:472-474)
+          backward_one(p, px, py, f0, z0, d0, a0, a1, a2, persp, clip);
+        f0 = f1; f1 = f2; f2 = f3;
+        z0 = z1; z1 = z2; z2 = z3;
+        d0 = d1; d1 = d2; d2 = d3;
+        a0 = a3; a1 = a4; a2 = a5; a3 = a6; a4 = a7; a5 = a8; a6 = a9; a7 = a10; a8 = a11;
       }
     }
   } else {

@@ -188,8 +188,16 @@ def test_mesh_backward(ops, dev, ref_cuda, persp, clip):
     gz, gb, gd = upstream([frag[1].shape, frag[2].shape, frag[3].shape])
     mine = ops.rasterize_meshes_backward(fv.to(dev), frag[0], gz.to(dev), gb.to(dev), gd.to(dev), bool(persp),
                                          bool(clip)).cpu().numpy()
-    want = oracle.rasterize_meshes_backward(fv.numpy(), frag[0].cpu().numpy(), gz.numpy(), gb.numpy(), gd.numpy(),
-                                            persp, clip, arith=oracle.ARITH_CUDA)
+    args = (fv.numpy(), frag[0].cpu().numpy(), gz.numpy(), gb.numpy(), gd.numpy(), persp, clip)
+    want = oracle.rasterize_meshes_backward(*args, arith=oracle.ARITH_CUDA)
+    # Pixels in the blur band of a face can be arbitrarily ill-conditioned (perspective-corrected, clipped
+    # barycentrics with near-zero denominators): there even the reference's own two arithmetics (FMA / no FMA)
+    # disagree by 100%.  Faces are compared where those two agree; they must be the overwhelming majority.
+    alt = oracle.rasterize_meshes_backward(*args, arith=oracle.ARITH_CPU)
+    fmax = np.abs(want).reshape(len(want), -1).max(1)
+    stable = np.abs(want - alt).reshape(len(want), -1).max(1) <= 1e-4 * np.maximum(fmax, 1e-6)
+    assert stable.mean() > 0.97
+    want, mine = want[stable], mine[stable]
     scale = np.abs(want).max()
     assert np.abs(mine - want).max() <= 2e-3 * scale
     np.testing.assert_allclose(mine, want, rtol=2e-3, atol=2e-4 * scale)
@@ -197,7 +205,7 @@ def test_mesh_backward(ops, dev, ref_cuda, persp, clip):
         # (with both flags the reference CUDA kernel feeds the uncorrected barycentrics to the clip
         # backward, rasterize_meshes.cu:527-529; we follow the forward-consistent CPU form)
         r = ref_cuda.rasterize_meshes_backward(fv.to(dev), frag[0], gz.to(dev), gb.to(dev), gd.to(dev), bool(persp),
-                                               bool(clip)).cpu().numpy()
+                                               bool(clip)).cpu().numpy()[stable]
         np.testing.assert_allclose(mine, r, rtol=2e-3, atol=2e-4 * scale)
 
 
