@@ -125,7 +125,7 @@ static __global__ void __launch_bounds__(256)
 // rasterize_points.cu:128), which is what pins tie-breaking and makes the output deterministic.
 // "Normalised" bitonic network (every compare-exchange ascending), valid for any segment length:
 // partners beyond the end are treated as +inf and skipped.
-constexpr int SORT_THREADS = 128;
+constexpr int SORT_THREADS = 256;
 constexpr int SORT_TILES_PER_CTA = SORT_THREADS / 32;  // one warp per tile on the fast path
 constexpr int SORT_RANK_MAX = 256;                      // fast path: segments of up to 8 keys per lane
 constexpr int SORT_SMEM_ELEMS = 4096;
@@ -150,49 +150,42 @@ static __global__ void __launch_bounds__(SORT_THREADS)
   __shared__ int s_keys[SORT_SMEM_ELEMS];
   const int t0 = blockIdx.x * SORT_TILES_PER_CTA;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // CTA-uniform decision: short segments (the common case) are rank-sorted one tile per warp -- every key's
-  // final position is the number of smaller keys (keys are unique), counted with independent compares
-  // against a broadcast shared-memory copy: no network, no barriers.  Long segments are bitonic-sorted by
-  // the whole CTA, one tile after the other.
-  int max_n = 0;
-  for (int u = 0; u < SORT_TILES_PER_CTA; ++u) {
-    const int t = t0 + u;
-    if (t < ntiles) max_n = max(max_n, offsets[t + 1] - offsets[t]);
-  }
-  if (max_n <= SORT_RANK_MAX) {
+  // Short segments (the common case) are rank-sorted one tile per warp -- every key's final position is the
+  // number of smaller keys (keys are unique), counted with independent compares against a broadcast
+  // shared-memory copy: no network, no barriers.  Longer segments are then bitonic-sorted by the whole CTA.
+  {
     const int t = t0 + warp;
-    if (t >= ntiles) return;
-    const int begin = offsets[t], end = offsets[t + 1];
+    const int begin = t < ntiles ? offsets[t] : 0, end = t < ntiles ? offsets[t + 1] : 0;
     const int n = end - begin;
-    if (n < 2 || (int64_t)end > capacity) return;  // overflowed tiles are rasterised from the mesh range
-    int* keys = s_keys + warp * SORT_RANK_MAX;
-    int mine[SORT_RANK_MAX / 32], rank[SORT_RANK_MAX / 32];
+    if (n >= 2 && n <= SORT_RANK_MAX && (int64_t)end <= capacity) {
+      int* keys = s_keys + warp * SORT_RANK_MAX;
+      int mine[SORT_RANK_MAX / 32], rank[SORT_RANK_MAX / 32];
 #pragma unroll
-    for (int u = 0; u < SORT_RANK_MAX / 32; ++u) {
-      const int i = lane + 32 * u;
-      mine[u] = i < n ? pairs[begin + i] : 0x7fffffff;
-      rank[u] = 0;
-      if (i < n) keys[i] = mine[u];
-    }
-    __syncwarp();
-    const int cols = (n + 31) >> 5;  // keys per lane actually in use (warp-uniform)
-    for (int i = 0; i < n; ++i) {
-      const int k = keys[i];
+      for (int u = 0; u < SORT_RANK_MAX / 32; ++u) {
+        const int i = lane + 32 * u;
+        mine[u] = i < n ? pairs[begin + i] : 0x7fffffff;
+        rank[u] = 0;
+        if (i < n) keys[i] = mine[u];
+      }
+      __syncwarp();
+      const int cols = (n + 31) >> 5;  // keys per lane actually in use (warp-uniform)
+      for (int i = 0; i < n; ++i) {
+        const int k = keys[i];
+#pragma unroll
+        for (int u = 0; u < SORT_RANK_MAX / 32; ++u)
+          if (u < cols) rank[u] += k < mine[u] ? 1 : 0;
+      }
 #pragma unroll
       for (int u = 0; u < SORT_RANK_MAX / 32; ++u)
-        if (u < cols) rank[u] += k < mine[u] ? 1 : 0;
+        if (lane + 32 * u < n) pairs[begin + rank[u]] = mine[u];
     }
-#pragma unroll
-    for (int u = 0; u < SORT_RANK_MAX / 32; ++u)
-      if (lane + 32 * u < n) pairs[begin + rank[u]] = mine[u];
-    return;
   }
   for (int u = 0; u < SORT_TILES_PER_CTA; ++u) {
     const int t = t0 + u;
     if (t >= ntiles) break;
     const int begin = offsets[t], end = offsets[t + 1];
     const int n = end - begin;
-    if (n < 2 || (int64_t)end > capacity) continue;
+    if (n <= SORT_RANK_MAX || (int64_t)end > capacity) continue;  // (overflowed tiles are not used)
     const bool in_smem = n <= SORT_SMEM_ELEMS;
     int* keys = in_smem ? s_keys : pairs + begin;
     __syncthreads();

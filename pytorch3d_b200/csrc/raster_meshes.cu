@@ -628,9 +628,10 @@ __device__ __forceinline__ void point_line_bwd(float px, float py, float ax, flo
   gb = make_float2(g * t * cx, g * t * cy);
 }
 
-// Gradient of one (pixel, face) hit, scattered into grad_face_verts with 9 atomics.
+// Gradient of one (pixel, face) hit with respect to the face's 9 coordinates (out[0..8]).
 __device__ __forceinline__ void backward_one(const BackwardParams& p, float px, float py, int64_t fi, float gz,
-                                             float gd, float gb0, float gb1, float gb2, bool persp, bool clip) {
+                                             float gd, float gb0, float gb1, float gb2, bool persp, bool clip,
+                                             float (&out)[9]) {
   const float* v = p.face_verts + fi * 9;
   const Face f = {__ldg(v + 0), __ldg(v + 1), __ldg(v + 2), __ldg(v + 3), __ldg(v + 4),
                   __ldg(v + 5), __ldg(v + 6), __ldg(v + 7), __ldg(v + 8)};
@@ -714,68 +715,85 @@ __device__ __forceinline__ void backward_one(const BackwardParams& p, float px, 
     bv0.x += da.x; bv0.y += da.y;
     bv1.x += db.x; bv1.y += db.y;
   }
-  float* g = p.grad_face_verts + fi * 9;
-  atomicAdd(g + 0, bv0.x + dv0.x);
-  atomicAdd(g + 1, bv0.y + dv0.y);
-  atomicAdd(g + 2, gz * k0 + dz0);
-  atomicAdd(g + 3, bv1.x + dv1.x);
-  atomicAdd(g + 4, bv1.y + dv1.y);
-  atomicAdd(g + 5, gz * k1 + dz1);
-  atomicAdd(g + 6, bv2.x + dv2.x);
-  atomicAdd(g + 7, bv2.y + dv2.y);
-  atomicAdd(g + 8, gz * k2 + dz2);
+  out[0] = bv0.x + dv0.x;
+  out[1] = bv0.y + dv0.y;
+  out[2] = gz * k0 + dz0;
+  out[3] = bv1.x + dv1.x;
+  out[4] = bv1.y + dv1.y;
+  out[5] = gz * k1 + dz1;
+  out[6] = bv2.x + dv2.x;
+  out[7] = bv2.y + dv2.y;
+  out[8] = gz * k2 + dz2;
 }
 
-// VEC: K is a multiple of 4 -> the 28 bytes/slot of (pix_to_face, grad_zbuf, grad_dists, grad_bary) are read
-// with 16-byte loads, four slots at a time; a group whose four faces are all -1 costs only the index load.
-template <bool VEC>
+// Scatter one warp's contributions.  Neighbouring pixels usually hit the same face, so before touching
+// memory the warp merges lanes that carry the same face with five butterfly stages (partner = lane ^ 1, 2, 4
+// along the footprint row, then ^ 8, 16 across rows): the lower lane of a matching pair takes over the
+// partner's sum.  What is left is one set of 9 atomics per surviving lane instead of per pixel.
+__device__ __forceinline__ void warp_scatter(float* __restrict__ grad_face_verts, int face, float (&g)[9], int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int other = __shfl_xor_sync(0xffffffffu, face, d);
+    const bool same = other == face && face >= 0;
+    const bool upper = (lane & d) != 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float v = __shfl_xor_sync(0xffffffffu, g[i], d);
+      g[i] = same ? (upper ? 0.0f : g[i] + v) : g[i];
+    }
+    if (same && upper) face = -1;  // merged into the partner
+  }
+  if (face >= 0) {
+    float* o = grad_face_verts + (int64_t)face * 9;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) atomicAdd(o + i, g[i]);
+  }
+}
+
+// KV > 0: K == KV (a multiple of 4) and the pixel's KV face indices are fetched up front with 16-byte loads
+// (a pixel with no face costs nothing else); KV == 0: any K, scalar loads.
+template <int KV>
 __global__ void __launch_bounds__(TILE_THREADS) mesh_backward_kernel(const BackwardParams p) {
   const int t = blockIdx.x;
+  const int lane = threadIdx.x & 31;
   const int n = t / (p.TY * p.TX);
   const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
   int xo, yo;
   thread_pixel(tile_x, tile_y, xo, yo);
-  if (xo >= p.W || yo >= p.H) return;
+  const bool in_image = xo < p.W && yo < p.H;
   const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
   const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
   const int K = p.K;
-  const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
+  const int64_t o = in_image ? (((int64_t)n * p.H + yo) * p.W + xo) * K : 0;
   const bool persp = p.persp != 0, clip = p.clip != 0;
 
-  if (VEC) {
-    for (int k0 = 0; k0 < K; k0 += 4) {
-      const longlong2 ia = __ldg(reinterpret_cast<const longlong2*>(p.pix_to_face + o + k0));
-      const longlong2 ib = __ldg(reinterpret_cast<const longlong2*>(p.pix_to_face + o + k0) + 1);
-      const long long fi[4] = {ia.x, ia.y, ib.x, ib.y};
-      if ((fi[0] & fi[1] & fi[2] & fi[3]) < 0) continue;  // all four negative (padding)
-      const float4 gz = __ldg(reinterpret_cast<const float4*>(p.grad_zbuf + o + k0));
-      const float4 gd = __ldg(reinterpret_cast<const float4*>(p.grad_dists + o + k0));
-      const float4* gbp = reinterpret_cast<const float4*>(p.grad_bary + (o + k0) * 3);
-      const float4 b0 = __ldg(gbp), b1 = __ldg(gbp + 1), b2 = __ldg(gbp + 2);
-      // one copy of the gradient code: the four slots rotate through the same registers
-      long long f0 = fi[0], f1 = fi[1], f2 = fi[2], f3 = fi[3];
-      float z0 = gz.x, z1 = gz.y, z2 = gz.z, z3 = gz.w;
-      float d0 = gd.x, d1 = gd.y, d2 = gd.z, d3 = gd.w;
-      float a0 = b0.x, a1 = b0.y, a2 = b0.z, a3 = b0.w, a4 = b1.x, a5 = b1.y, a6 = b1.z, a7 = b1.w, a8 = b2.x,
-            a9 = b2.y, a10 = b2.z, a11 = b2.w;
-#pragma unroll 1
-      for (int u = 0; u < 4; ++u) {
-        if (f0 >= 0)  // else: padded face (:472-474)
-          backward_one(p, px, py, f0, z0, d0, a0, a1, a2, persp, clip);
-        f0 = f1; f1 = f2; f2 = f3;
-        z0 = z1; z1 = z2; z2 = z3;
-        d0 = d1; d1 = d2; d2 = d3;
-        a0 = a3; a1 = a4; a2 = a5; a3 = a6; a4 = a7; a5 = a8; a6 = a9; a7 = a10; a8 = a11;
-      }
+  int fk[KV > 0 ? KV : 1];
+  if (KV > 0) {
+#pragma unroll
+    for (int k = 0; k < KV; k += 2) {
+      longlong2 v = make_longlong2(-1, -1);
+      if (in_image) v = __ldg(reinterpret_cast<const longlong2*>(p.pix_to_face + o + k));
+      fk[k] = (int)v.x;  // the reference reads the int64 index into an int as well (:471)
+      fk[k + 1] = (int)v.y;
     }
-  } else {
-    for (int k = 0; k < K; ++k) {
+  }
+  for (int k = 0; k < K; ++k) {
+    int face = -1;
+    if (KV > 0) {
+      face = fk[0];
+#pragma unroll
+      for (int j = 0; j + 1 < KV; ++j) fk[j] = fk[j + 1];  // rotate: one copy of the gradient code
+    } else if (in_image) {
+      face = (int)p.pix_to_face[o + k];
+    }
+    if (!__any_sync(0xffffffffu, face >= 0)) continue;  // padded slots (:472-474)
+    float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (face >= 0) {
       const int64_t i = o + k;
-      const int64_t fi = p.pix_to_face[i];
-      if (fi < 0) continue;
-      backward_one(p, px, py, fi, p.grad_zbuf[i], p.grad_dists[i], p.grad_bary[i * 3 + 0], p.grad_bary[i * 3 + 1],
-                   p.grad_bary[i * 3 + 2], persp, clip);
+      backward_one(p, px, py, face, __ldg(p.grad_zbuf + i), __ldg(p.grad_dists + i), __ldg(p.grad_bary + i * 3),
+                   __ldg(p.grad_bary + i * 3 + 1), __ldg(p.grad_bary + i * 3 + 2), persp, clip, g);
     }
+    warp_scatter(p.grad_face_verts, face, g, lane);
   }
 }
 
@@ -899,10 +917,13 @@ extern "C" int b200r_rasterize_meshes_backward(const float* face_verts, int64_t 
   p.grad_face_verts = grad_face_verts;
   const bool prof = profiling_enabled();
   if (prof) phase_timer().record(3, stream);
-  if (K % 4 == 0)
-    mesh_backward_kernel<true><<<(unsigned)((int64_t)N * TY * TX), TILE_THREADS, 0, stream>>>(p);
+  const unsigned bgrid = (unsigned)((int64_t)N * TY * TX);
+  if (K == 8)
+    mesh_backward_kernel<8><<<bgrid, TILE_THREADS, 0, stream>>>(p);
+  else if (K == 4)
+    mesh_backward_kernel<4><<<bgrid, TILE_THREADS, 0, stream>>>(p);
   else
-    mesh_backward_kernel<false><<<(unsigned)((int64_t)N * TY * TX), TILE_THREADS, 0, stream>>>(p);
+    mesh_backward_kernel<0><<<bgrid, TILE_THREADS, 0, stream>>>(p);
   B200R_LAUNCHED("mesh_backward_kernel");
   if (prof) {
     phase_timer().record(4, stream);
