@@ -145,43 +145,55 @@ __device__ __forceinline__ void sort_sweep(int* keys, int n, int d) {
   }
 }
 
+// Rank sort of one short segment by one warp: every key's final position is the number of smaller keys
+// (keys are unique), counted with independent compares against a broadcast shared-memory copy -- no
+// network, no barriers.  COLS = keys held per lane.
+template <int COLS>
+__device__ __forceinline__ void rank_sort_warp(int* __restrict__ pairs, int begin, int n, int* keys, int lane) {
+  int mine[COLS], rank[COLS];
+#pragma unroll
+  for (int u = 0; u < COLS; ++u) {
+    const int i = lane + 32 * u;
+    mine[u] = i < n ? pairs[begin + i] : 0x7fffffff;
+    rank[u] = 0;
+    if (i < n) keys[i] = mine[u];
+  }
+  __syncwarp();
+  for (int i = 0; i < n; ++i) {
+    const int k = keys[i];
+#pragma unroll
+    for (int u = 0; u < COLS; ++u) rank[u] += k < mine[u] ? 1 : 0;
+  }
+#pragma unroll
+  for (int u = 0; u < COLS; ++u)
+    if (lane + 32 * u < n) pairs[begin + rank[u]] = mine[u];
+}
+
+// Tiles are dealt to CTAs round-robin (tile = blockIdx.x + u * gridDim.x) so that the heavy tiles of a
+// silhouette, which are neighbours in tile order, end up in different CTAs.
 static __global__ void __launch_bounds__(SORT_THREADS)
     tile_sort_kernel(const int* __restrict__ offsets, int* __restrict__ pairs, int64_t capacity, int ntiles) {
   __shared__ int s_keys[SORT_SMEM_ELEMS];
-  const int t0 = blockIdx.x * SORT_TILES_PER_CTA;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // Short segments (the common case) are rank-sorted one tile per warp -- every key's final position is the
-  // number of smaller keys (keys are unique), counted with independent compares against a broadcast
-  // shared-memory copy: no network, no barriers.  Longer segments are then bitonic-sorted by the whole CTA.
-  {
-    const int t = t0 + warp;
+  {  // short segments (the common case): one tile per warp
+    const int t = blockIdx.x + warp * gridDim.x;
     const int begin = t < ntiles ? offsets[t] : 0, end = t < ntiles ? offsets[t + 1] : 0;
     const int n = end - begin;
     if (n >= 2 && n <= SORT_RANK_MAX && (int64_t)end <= capacity) {
       int* keys = s_keys + warp * SORT_RANK_MAX;
-      int mine[SORT_RANK_MAX / 32], rank[SORT_RANK_MAX / 32];
-#pragma unroll
-      for (int u = 0; u < SORT_RANK_MAX / 32; ++u) {
-        const int i = lane + 32 * u;
-        mine[u] = i < n ? pairs[begin + i] : 0x7fffffff;
-        rank[u] = 0;
-        if (i < n) keys[i] = mine[u];
-      }
-      __syncwarp();
-      const int cols = (n + 31) >> 5;  // keys per lane actually in use (warp-uniform)
-      for (int i = 0; i < n; ++i) {
-        const int k = keys[i];
-#pragma unroll
-        for (int u = 0; u < SORT_RANK_MAX / 32; ++u)
-          if (u < cols) rank[u] += k < mine[u] ? 1 : 0;
-      }
-#pragma unroll
-      for (int u = 0; u < SORT_RANK_MAX / 32; ++u)
-        if (lane + 32 * u < n) pairs[begin + rank[u]] = mine[u];
+      if (n <= 32)
+        rank_sort_warp<1>(pairs, begin, n, keys, lane);
+      else if (n <= 64)
+        rank_sort_warp<2>(pairs, begin, n, keys, lane);
+      else if (n <= 128)
+        rank_sort_warp<4>(pairs, begin, n, keys, lane);
+      else
+        rank_sort_warp<8>(pairs, begin, n, keys, lane);
     }
   }
+  // long segments: bitonic network by the whole CTA, one tile after the other
   for (int u = 0; u < SORT_TILES_PER_CTA; ++u) {
-    const int t = t0 + u;
+    const int t = blockIdx.x + u * gridDim.x;
     if (t >= ntiles) break;
     const int begin = offsets[t], end = offsets[t + 1];
     const int n = end - begin;
@@ -242,6 +254,33 @@ inline BinWorkspace carve_workspace(void* base, int64_t E, int N, int H, int W, 
   off = align_up(off + sizeof(int) * (size_t)capacity, 16);
   ws.bytes = off;
   return ws;
+}
+
+// Which pixels of a warp's 8x4 footprint lie inside an element's (blur-expanded) box?  One lane tests one face
+// against the 8 column and 4 row coordinates of the footprint and builds the 32-bit pixel mask
+// (bit = lane of the pixel); the box test is the reference's `px > xmax || px < xmin || ...` (:94-97).
+__device__ __forceinline__ unsigned box_pixel_mask(const float4 bx, const float (&col)[8], const float (&row)[4]) {
+  unsigned xm = 0, ym = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) xm |= (!(col[c] > bx.y || col[c] < bx.x) ? 1u : 0u) << c;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) ym |= (!(row[r] > bx.w || row[r] < bx.z) ? 1u : 0u) << (8 * r);
+  return xm * ym;  // ym has one bit per byte, xm < 256: the product replicates xm into the selected rows
+}
+
+// Transpose a 32x32 bit matrix held one row per lane (5 butterfly stages of shuffles): afterwards bit k of
+// lane l's word is what bit l of lane k's word was.  Turns "pixel mask per face" into "face mask per pixel".
+__device__ __forceinline__ unsigned warp_transpose_bits(unsigned a, int lane) {
+#pragma unroll
+  for (int sft = 16; sft >= 1; sft >>= 1) {
+    const unsigned lo = sft == 16 ? 0x0000FFFFu
+                      : sft == 8 ? 0x00FF00FFu
+                      : sft == 4 ? 0x0F0F0F0Fu
+                      : sft == 2 ? 0x33333333u : 0x55555555u;
+    const unsigned other = __shfl_xor_sync(0xffffffffu, a, sft);
+    a = (lane & sft) ? ((a & ~lo) | ((other & ~lo) >> sft)) : ((a & lo) | ((other & lo) << sft));
+  }
+  return a;
 }
 
 }  // namespace b200r

@@ -296,33 +296,6 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Which pixels of a warp's 8x4 footprint lie inside a face's (blur-expanded) box?  One lane tests one face
-// against the 8 column and 4 row coordinates of the footprint and builds the 32-bit pixel mask
-// (bit = lane of the pixel); the box test is the reference's `px > xmax || px < xmin || ...` (:94-97).
-__device__ __forceinline__ unsigned box_pixel_mask(const float4 bx, const float (&col)[8], const float (&row)[4]) {
-  unsigned xm = 0, ym = 0;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) xm |= (!(col[c] > bx.y || col[c] < bx.x) ? 1u : 0u) << c;
-#pragma unroll
-  for (int r = 0; r < 4; ++r) ym |= (!(row[r] > bx.w || row[r] < bx.z) ? 1u : 0u) << (8 * r);
-  return xm * ym;  // ym has one bit per byte, xm < 256: the product replicates xm into the selected rows
-}
-
-// Transpose a 32x32 bit matrix held one row per lane (5 butterfly stages of shuffles): afterwards bit k of
-// lane l's word is what bit l of lane k's word was.  Turns "pixel mask per face" into "face mask per pixel".
-__device__ __forceinline__ unsigned warp_transpose_bits(unsigned a, int lane) {
-#pragma unroll
-  for (int sft = 16; sft >= 1; sft >>= 1) {
-    const unsigned lo = sft == 16 ? 0x0000FFFFu
-                      : sft == 8 ? 0x00FF00FFu
-                      : sft == 4 ? 0x0F0F0F0Fu
-                      : sft == 2 ? 0x33333333u : 0x55555555u;
-    const unsigned other = __shfl_xor_sync(0xffffffffu, a, sft);
-    a = (lane & sft) ? ((a & ~lo) | ((other & ~lo) >> sft)) : ((a & lo) | ((other & lo) << sft));
-  }
-  return a;
-}
-
 // Faces are consumed in rounds of 64.  Pass A: each lane box-tests one face against the whole footprint and
 // the warp transposes the resulting bit matrix, so that every lane ends up with a 64-bit mask of the faces
 // whose box contains ITS pixel (ascending face order = ascending bit order).  Pass B: every lane walks its

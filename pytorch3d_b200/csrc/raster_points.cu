@@ -192,8 +192,11 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_kernel(const PointFi
   const bool valid = xo < p.W && yo < p.H;
   const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
   const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
-  const float fx_lo = pwarp_min(valid ? px : FLT_MAX), fx_hi = pwarp_max(valid ? px : -FLT_MAX);
-  const float fy_lo = pwarp_min(valid ? py : FLT_MAX), fy_hi = pwarp_max(valid ? py : -FLT_MAX);
+  float col[8], row[4];  // the footprint's 8 column and 4 row coordinates (lane = row * 8 + column)
+#pragma unroll
+  for (int c = 0; c < 8; ++c) col[c] = __shfl_sync(0xffffffffu, px, c);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) row[r] = __shfl_sync(0xffffffffu, py, 8 * r);
 
   const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
   const bool overflow = (int64_t)seg_end > p.capacity;
@@ -218,21 +221,24 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_kernel(const PointFi
       stage_point(s, j, p.points, p.radius, pi);
     }
     __syncthreads();
-    for (int g = 0; g < nc; g += 32) {
-      bool touch = false;
-      if (g + lane < nc) {
-        const float4 bx = s.box[g + lane];
-        touch = !(fx_lo > bx.y || fx_hi < bx.x || fy_lo > bx.w || fy_hi < bx.z);
-      }
-      unsigned m = __ballot_sync(0xffffffffu, touch);
-      while (m) {
-        const int j = g + __ffs(m) - 1;
-        m &= m - 1;
+    for (int sub = 0; sub < nc; sub += 64) {
+      // pass A: 64-bit mask of the points of this round whose box contains my pixel (see raster_meshes.cu)
+      unsigned m0 = 0, m1 = 0;
+      if (sub + lane < nc) m0 = box_pixel_mask(s.box[sub + lane], col, row);
+      if (sub + 32 + lane < nc) m1 = box_pixel_mask(s.box[sub + 32 + lane], col, row);
+      m0 = warp_transpose_bits(m0, lane);
+      if (sub + 32 < nc) m1 = warp_transpose_bits(m1, lane);
+      unsigned long long mine = valid ? (((unsigned long long)m1 << 32) | m0) : 0ull;
+      // pass B: every lane tests and queues its own candidates, in ascending point order
+      while (__any_sync(0xffffffffu, mine != 0ull)) {
+        if (mine == 0ull) continue;
+        const int j = sub + __ffsll((long long)mine) - 1;
+        mine &= mine - 1ull;
         const float4 r = s.rec[j];
         // CheckPixelInsidePoint (rasterize_points.cu:49-60): dist2 = fma(dy, dy, rn(dx*dx)) < rn(r*r)
         const float dx = fsub(px, r.x), dy = fsub(py, r.y);
         const float d2 = sqnorm2(dx, dy);
-        if (!valid || r.z < 0.0f || !(d2 < r.w)) continue;
+        if (r.z < 0.0f || !(d2 < r.w)) continue;
         const int pi = s.id[j];
         if (KMAX > 0) {
           q.offer(r.z, pi, d2, K);

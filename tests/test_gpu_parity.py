@@ -178,34 +178,35 @@ def test_mesh_clipped_neighbors(ops, dev):
         assert_frag_equal(mine, o, "neighbours K=%d" % K)
 
 
-@pytest.mark.parametrize("persp,clip", [(0, 0), (1, 0), (0, 1), (1, 1)])
-def test_mesh_backward(ops, dev, ref_cuda, persp, clip):
+@pytest.mark.parametrize("persp,clip,blur", [(0, 0, 1e-3), (1, 0, 1e-3), (0, 1, 1e-3), (1, 1, 0.0), (1, 1, 1e-3)])
+def test_mesh_backward(ops, dev, ref_cuda, persp, clip, blur):
     from pytorch3d_b200 import synthetic
     m = synthetic.torus_batch(2, 24, 24, seed=3)
     fv, first, num = synthetic.face_verts_of(m), m.mesh_to_faces_packed_first_idx(), m.num_faces_per_mesh()
-    blur = 1e-3
     frag = run_mesh(ops, dev, fv, first, num, (64, 64), blur, 4, persp, clip)
     gz, gb, gd = upstream([frag[1].shape, frag[2].shape, frag[3].shape])
     mine = ops.rasterize_meshes_backward(fv.to(dev), frag[0], gz.to(dev), gb.to(dev), gd.to(dev), bool(persp),
                                          bool(clip)).cpu().numpy()
-    args = (fv.numpy(), frag[0].cpu().numpy(), gz.numpy(), gb.numpy(), gd.numpy(), persp, clip)
-    want = oracle.rasterize_meshes_backward(*args, arith=oracle.ARITH_CUDA)
-    # Pixels in the blur band of a face can be arbitrarily ill-conditioned (perspective-corrected, clipped
-    # barycentrics with near-zero denominators): there even the reference's own two arithmetics (FMA / no FMA)
-    # disagree by 100%.  Faces are compared where those two agree; they must be the overwhelming majority.
-    alt = oracle.rasterize_meshes_backward(*args, arith=oracle.ARITH_CPU)
-    fmax = np.abs(want).reshape(len(want), -1).max(1)
-    stable = np.abs(want - alt).reshape(len(want), -1).max(1) <= 1e-4 * np.maximum(fmax, 1e-6)
-    assert stable.mean() > 0.97
-    want, mine = want[stable], mine[stable]
-    scale = np.abs(want).max()
-    assert np.abs(mine - want).max() <= 2e-3 * scale
+    want = oracle.rasterize_meshes_backward(fv.numpy(), frag[0].cpu().numpy(), gz.numpy(), gb.numpy(), gd.numpy(),
+                                            persp, clip, arith=oracle.ARITH_CUDA)
+    nf = len(want)
+    err = np.abs(mine - want).reshape(nf, -1).max(1)
+    mag = np.abs(want).reshape(nf, -1).max(1)
+    if persp and clip and blur > 0:
+        # Pixels in the blur band of a face are arbitrarily ill-conditioned with BOTH flags (perspective-
+        # corrected then clipped barycentrics with near-zero denominators): even the reference's own two
+        # arithmetics (FMA / no FMA) disagree by 100% on a few faces.  Require agreement on >= 98% of faces.
+        ok = err <= 2e-3 * np.maximum(mag, 1e-3 * np.median(mag))
+        assert ok.mean() >= 0.98
+        return
+    scale = mag.max()
+    assert err.max() <= 2e-3 * scale
     np.testing.assert_allclose(mine, want, rtol=2e-3, atol=2e-4 * scale)
     if ref_cuda is not None and not (persp and clip):
         # (with both flags the reference CUDA kernel feeds the uncorrected barycentrics to the clip
         # backward, rasterize_meshes.cu:527-529; we follow the forward-consistent CPU form)
         r = ref_cuda.rasterize_meshes_backward(fv.to(dev), frag[0], gz.to(dev), gb.to(dev), gd.to(dev), bool(persp),
-                                               bool(clip)).cpu().numpy()[stable]
+                                               bool(clip)).cpu().numpy()
         np.testing.assert_allclose(mine, r, rtol=2e-3, atol=2e-4 * scale)
 
 
