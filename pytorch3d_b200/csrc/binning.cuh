@@ -169,15 +169,44 @@ __device__ __forceinline__ void rank_sort_warp(int* __restrict__ pairs, int begi
     if (lane + 32 * u < n) pairs[begin + rank[u]] = mine[u];
 }
 
-// Tiles are dealt to CTAs round-robin (tile = blockIdx.x + u * gridDim.x) so that the heavy tiles of a
-// silhouette, which are neighbours in tile order, end up in different CTAs.
+// Rank sort of one medium segment (n <= 4 * SORT_THREADS) by the whole CTA, same idea, keys in shared memory.
+__device__ __forceinline__ void rank_sort_cta(int* __restrict__ pairs, int begin, int n, int* keys) {
+  constexpr int C = 4;
+  int mine[C], rank[C];
+#pragma unroll
+  for (int u = 0; u < C; ++u) {
+    const int i = threadIdx.x + SORT_THREADS * u;
+    mine[u] = i < n ? pairs[begin + i] : 0x7fffffff;
+    rank[u] = 0;
+    if (i < n) keys[i] = mine[u];
+  }
+  __syncthreads();
+  for (int i = 0; i < n; ++i) {
+    const int k = keys[i];
+#pragma unroll
+    for (int u = 0; u < C; ++u) rank[u] += k < mine[u] ? 1 : 0;
+  }
+#pragma unroll
+  for (int u = 0; u < C; ++u)
+    if (threadIdx.x + SORT_THREADS * u < n) pairs[begin + rank[u]] = mine[u];
+}
+
+// Tiles are dealt to CTAs through a multiplicative permutation of the tile index, so that the heavy tiles of
+// a silhouette (neighbours in tile order, and at the same place in every frame of a batch) end up in
+// different CTAs.
+__device__ __forceinline__ int sort_tile_of(int slot, int ntiles, int mult) {
+  return (int)(((long long)slot * mult) % ntiles);
+}
+
 static __global__ void __launch_bounds__(SORT_THREADS)
-    tile_sort_kernel(const int* __restrict__ offsets, int* __restrict__ pairs, int64_t capacity, int ntiles) {
+    tile_sort_kernel(const int* __restrict__ offsets, int* __restrict__ pairs, int64_t capacity, int ntiles,
+                     int mult) {
   __shared__ int s_keys[SORT_SMEM_ELEMS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   {  // short segments (the common case): one tile per warp
-    const int t = blockIdx.x + warp * gridDim.x;
-    const int begin = t < ntiles ? offsets[t] : 0, end = t < ntiles ? offsets[t + 1] : 0;
+    const int slot = blockIdx.x * SORT_TILES_PER_CTA + warp;
+    const int t = slot < ntiles ? sort_tile_of(slot, ntiles, mult) : -1;
+    const int begin = t >= 0 ? offsets[t] : 0, end = t >= 0 ? offsets[t + 1] : 0;
     const int n = end - begin;
     if (n >= 2 && n <= SORT_RANK_MAX && (int64_t)end <= capacity) {
       int* keys = s_keys + warp * SORT_RANK_MAX;
@@ -191,16 +220,21 @@ static __global__ void __launch_bounds__(SORT_THREADS)
         rank_sort_warp<8>(pairs, begin, n, keys, lane);
     }
   }
-  // long segments: bitonic network by the whole CTA, one tile after the other
+  // longer segments: the whole CTA, one tile after the other (rank sort up to 1024 keys, bitonic beyond)
   for (int u = 0; u < SORT_TILES_PER_CTA; ++u) {
-    const int t = blockIdx.x + u * gridDim.x;
-    if (t >= ntiles) break;
+    const int slot = blockIdx.x * SORT_TILES_PER_CTA + u;
+    if (slot >= ntiles) break;
+    const int t = sort_tile_of(slot, ntiles, mult);
     const int begin = offsets[t], end = offsets[t + 1];
     const int n = end - begin;
     if (n <= SORT_RANK_MAX || (int64_t)end > capacity) continue;  // (overflowed tiles are not used)
+    __syncthreads();
+    if (n <= 4 * SORT_THREADS) {
+      rank_sort_cta(pairs, begin, n, s_keys);
+      continue;
+    }
     const bool in_smem = n <= SORT_SMEM_ELEMS;
     int* keys = in_smem ? s_keys : pairs + begin;
-    __syncthreads();
     if (in_smem)
       for (int i = threadIdx.x; i < n; i += SORT_THREADS) s_keys[i] = pairs[begin + i];
     __syncthreads();
@@ -215,6 +249,14 @@ static __global__ void __launch_bounds__(SORT_THREADS)
     if (in_smem)
       for (int i = threadIdx.x; i < n; i += SORT_THREADS) pairs[begin + i] = s_keys[i];
   }
+}
+
+// A multiplier coprime with ntiles for sort_tile_of.
+inline int sort_multiplier(int64_t ntiles) {
+  const int primes[] = {7919, 7907, 7901, 7883, 7879, 104729};
+  for (int p : primes)
+    if (ntiles % p != 0) return p;
+  return 1;
 }
 
 // Workspace carving (all int32 / uint2 arrays, 16B-aligned sections).

@@ -827,7 +827,7 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
   }
   if (ntiles > 0) {
     tile_sort_kernel<<<(unsigned)((ntiles + SORT_TILES_PER_CTA - 1) / SORT_TILES_PER_CTA), SORT_THREADS, 0, stream>>>(
-        ws.tile_offset, ws.pairs, ws.capacity, (int)ntiles);
+        ws.tile_offset, ws.pairs, ws.capacity, (int)ntiles, sort_multiplier(ntiles));
     B200R_LAUNCHED("tile_sort_kernel");
   }
   if (prof) phase_timer().record(1, stream);

@@ -373,7 +373,7 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
     B200R_LAUNCHED("tile_fill_kernel");
   }
   tile_sort_kernel<<<(unsigned)((ntiles + SORT_TILES_PER_CTA - 1) / SORT_TILES_PER_CTA), SORT_THREADS, 0, stream>>>(
-        ws.tile_offset, ws.pairs, ws.capacity, (int)ntiles);
+        ws.tile_offset, ws.pairs, ws.capacity, (int)ntiles, sort_multiplier(ntiles));
   B200R_LAUNCHED("tile_sort_kernel");
   if (prof) phase_timer().record(1, stream);
   PointFineParams p;
