@@ -127,7 +127,6 @@ static __global__ void __launch_bounds__(256)
 // partners beyond the end are treated as +inf and skipped.
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_TILES_PER_CTA = SORT_THREADS / 32;  // one warp per tile on the fast path
-constexpr int SORT_RANK_MAX = 256;                      // fast path: segments of up to 8 keys per lane
 constexpr int SORT_SMEM_ELEMS = 4096;
 
 // One compare-exchange sweep of the bitonic network over keys[0..n) by the whole CTA.
@@ -145,96 +144,119 @@ __device__ __forceinline__ void sort_sweep(int* keys, int n, int d) {
   }
 }
 
-// Rank sort of one short segment by one warp: every key's final position is the number of smaller keys
-// (keys are unique), counted with independent compares against a broadcast shared-memory copy -- no
-// network, no barriers.  COLS = keys held per lane.
-template <int COLS>
-__device__ __forceinline__ void rank_sort_warp(int* __restrict__ pairs, int begin, int n, int* keys, int lane) {
-  int mine[COLS], rank[COLS];
+// Bitonic sort of 32*C keys held C per lane (element index = lane * C + r), entirely in registers: all
+// compare-exchanges are ascending ("normalised" network: each merge starts with a mirror step e ^ (k-1) and
+// continues with half-cleaners e ^ d); partners closer than C are register pairs, the others are reached with
+// one shuffle.  No shared memory, no barriers.
+template <int C>
+__device__ __forceinline__ void warp_bitonic_sort(int (&x)[C], int lane) {
 #pragma unroll
-  for (int u = 0; u < COLS; ++u) {
-    const int i = lane + 32 * u;
-    mine[u] = i < n ? pairs[begin + i] : 0x7fffffff;
-    rank[u] = 0;
-    if (i < n) keys[i] = mine[u];
+  for (int k = 2; k <= 32 * C; k <<= 1) {
+    if (k <= C) {  // mirror step inside a lane
+#pragma unroll
+      for (int r = 0; r < C; ++r) {
+        const int pr = r ^ (k - 1);
+        if (r < pr) {
+          const int a = x[r], b = x[pr];
+          x[r] = min(a, b);
+          x[pr] = max(a, b);
+        }
+      }
+    } else {  // mirror step across lanes: partner lane ^ (k/C - 1), registers reversed
+      const int lm = k / C - 1;
+      int y[C];
+#pragma unroll
+      for (int r = 0; r < C; ++r) y[r] = __shfl_xor_sync(0xffffffffu, x[C - 1 - r], lm);
+      const bool lower = (lane & ((lm + 1) >> 1)) == 0;  // the top flipped lane bit decides who is lower
+#pragma unroll
+      for (int r = 0; r < C; ++r) x[r] = lower ? min(x[r], y[r]) : max(x[r], y[r]);
+    }
+#pragma unroll
+    for (int d = k >> 2; d > 0; d >>= 1) {
+      if (d < C) {
+#pragma unroll
+        for (int r = 0; r < C; ++r) {
+          const int pr = r ^ d;
+          if (r < pr) {
+            const int a = x[r], b = x[pr];
+            x[r] = min(a, b);
+            x[pr] = max(a, b);
+          }
+        }
+      } else {
+        const int ld = d / C;
+        const bool lower = (lane & ld) == 0;
+#pragma unroll
+        for (int r = 0; r < C; ++r) {
+          const int v = __shfl_xor_sync(0xffffffffu, x[r], ld);
+          x[r] = lower ? min(x[r], v) : max(x[r], v);
+        }
+      }
+    }
   }
-  __syncwarp();
-  for (int i = 0; i < n; ++i) {
-    const int k = keys[i];
-#pragma unroll
-    for (int u = 0; u < COLS; ++u) rank[u] += k < mine[u] ? 1 : 0;
-  }
-#pragma unroll
-  for (int u = 0; u < COLS; ++u)
-    if (lane + 32 * u < n) pairs[begin + rank[u]] = mine[u];
 }
 
-// Rank sort of one medium segment (n <= 4 * SORT_THREADS) by the whole CTA, same idea, keys in shared memory.
-__device__ __forceinline__ void rank_sort_cta(int* __restrict__ pairs, int begin, int n, int* keys) {
-  constexpr int C = 4;
-  int mine[C], rank[C];
+// One warp sorts one tile segment of up to 32*C keys.
+template <int C>
+__device__ __forceinline__ void sort_segment_warp(int* __restrict__ pairs, int begin, int n, int lane) {
+  int x[C];
 #pragma unroll
-  for (int u = 0; u < C; ++u) {
-    const int i = threadIdx.x + SORT_THREADS * u;
-    mine[u] = i < n ? pairs[begin + i] : 0x7fffffff;
-    rank[u] = 0;
-    if (i < n) keys[i] = mine[u];
+  for (int r = 0; r < C; ++r) {
+    const int e = lane * C + r;
+    x[r] = e < n ? pairs[begin + e] : 0x7fffffff;  // padding sorts to the end
   }
-  __syncthreads();
-  for (int i = 0; i < n; ++i) {
-    const int k = keys[i];
+  warp_bitonic_sort<C>(x, lane);
 #pragma unroll
-    for (int u = 0; u < C; ++u) rank[u] += k < mine[u] ? 1 : 0;
+  for (int r = 0; r < C; ++r) {
+    const int e = lane * C + r;
+    if (e < n) pairs[begin + e] = x[r];
   }
-#pragma unroll
-  for (int u = 0; u < C; ++u)
-    if (threadIdx.x + SORT_THREADS * u < n) pairs[begin + rank[u]] = mine[u];
 }
 
-// Tiles are dealt to CTAs through a multiplicative permutation of the tile index, so that the heavy tiles of
-// a silhouette (neighbours in tile order, and at the same place in every frame of a batch) end up in
-// different CTAs.
+// Tiles are dealt to warps through a multiplicative permutation of the tile index, so that the heavy tiles of
+// a silhouette (neighbours in tile order, and at the same place in every frame of a batch) spread over the SMs.
 __device__ __forceinline__ int sort_tile_of(int slot, int ntiles, int mult) {
   return (int)(((long long)slot * mult) % ntiles);
 }
+
+constexpr int SORT_WARP_MAX = 1024;  // longest segment a single warp sorts in registers
 
 static __global__ void __launch_bounds__(SORT_THREADS)
     tile_sort_kernel(const int* __restrict__ offsets, int* __restrict__ pairs, int64_t capacity, int ntiles,
                      int mult) {
   __shared__ int s_keys[SORT_SMEM_ELEMS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  {  // short segments (the common case): one tile per warp
+  {  // segments of up to 1024 keys: one tile per warp
     const int slot = blockIdx.x * SORT_TILES_PER_CTA + warp;
     const int t = slot < ntiles ? sort_tile_of(slot, ntiles, mult) : -1;
     const int begin = t >= 0 ? offsets[t] : 0, end = t >= 0 ? offsets[t + 1] : 0;
     const int n = end - begin;
-    if (n >= 2 && n <= SORT_RANK_MAX && (int64_t)end <= capacity) {
-      int* keys = s_keys + warp * SORT_RANK_MAX;
+    if (n >= 2 && n <= SORT_WARP_MAX && (int64_t)end <= capacity) {
       if (n <= 32)
-        rank_sort_warp<1>(pairs, begin, n, keys, lane);
+        sort_segment_warp<1>(pairs, begin, n, lane);
       else if (n <= 64)
-        rank_sort_warp<2>(pairs, begin, n, keys, lane);
+        sort_segment_warp<2>(pairs, begin, n, lane);
       else if (n <= 128)
-        rank_sort_warp<4>(pairs, begin, n, keys, lane);
+        sort_segment_warp<4>(pairs, begin, n, lane);
+      else if (n <= 256)
+        sort_segment_warp<8>(pairs, begin, n, lane);
+      else if (n <= 512)
+        sort_segment_warp<16>(pairs, begin, n, lane);
       else
-        rank_sort_warp<8>(pairs, begin, n, keys, lane);
+        sort_segment_warp<32>(pairs, begin, n, lane);
     }
   }
-  // longer segments: the whole CTA, one tile after the other (rank sort up to 1024 keys, bitonic beyond)
+  // longer segments: bitonic network by the whole CTA in shared (or, beyond 4096 keys, global) memory
   for (int u = 0; u < SORT_TILES_PER_CTA; ++u) {
     const int slot = blockIdx.x * SORT_TILES_PER_CTA + u;
     if (slot >= ntiles) break;
     const int t = sort_tile_of(slot, ntiles, mult);
     const int begin = offsets[t], end = offsets[t + 1];
     const int n = end - begin;
-    if (n <= SORT_RANK_MAX || (int64_t)end > capacity) continue;  // (overflowed tiles are not used)
-    __syncthreads();
-    if (n <= 4 * SORT_THREADS) {
-      rank_sort_cta(pairs, begin, n, s_keys);
-      continue;
-    }
+    if (n <= SORT_WARP_MAX || (int64_t)end > capacity) continue;  // (overflowed tiles are not used)
     const bool in_smem = n <= SORT_SMEM_ELEMS;
     int* keys = in_smem ? s_keys : pairs + begin;
+    __syncthreads();
     if (in_smem)
       for (int i = threadIdx.x; i < n; i += SORT_THREADS) s_keys[i] = pairs[begin + i];
     __syncthreads();
