@@ -55,7 +55,7 @@ def measured_peak_gbs():
 
 def ncu_traffic_bytes(kernel):
     """dram read+write bytes per launch of `kernel` from the committed ncu capture summary, or None."""
-    path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    path = os.path.join(ROOT, "profiles", "ncu_r01_ns_metrics.json")
     try:
         with open(path) as fh:
             return json.load(fh)["kernels"][kernel]["dram_bytes_per_launch"]
