@@ -17,37 +17,29 @@ namespace b200r {
 
 constexpr uint32_t RECT_EMPTY_X = 0x0000FFFFu;  // tx0 = 0xFFFF > tx1 = 0
 
-// Smallest pixel index i in [0, S] whose centre satisfies pix(i) >= v (S if none).
-__device__ __forceinline__ int first_pix_ge(float v, int S, float range) {
-  const float off = range * 0.5f;
-  float est = (v + off) * (float)S / range - 0.5f;
-  est = fminf(fmaxf(est, -1.0f), (float)S + 1.0f);  // also maps NaN to -1
-  int i = (int)ceilf(est);
-  i = max(0, min(S, i));
-  while (i > 0 && pix_to_ndc(i - 1, S, range) >= v) --i;
-  while (i < S && pix_to_ndc(i, S, range) < v) ++i;
-  return i;
+// Pixel-index range [lo, hi] that contains every pixel i of an S-pixel axis whose centre pix(i) (as evaluated
+// by pix_to_ndc) lies in [vmin, vmax].  The inverse map is evaluated in plain float with a safety margin of
+// 1e-3 + 1e-6*S pixels (the float error of either direction is < 2e-4 pixels at S = 512), so the range is a
+// superset by at most that margin: binning only has to be conservative, the exact box test happens per
+// pixel in the fine pass.  Boxes that contain no pixel centre (most sub-pixel triangles) give lo > hi.
+__device__ __forceinline__ void pixel_range(float vmin, float vmax, int S, float range, int& lo, int& hi) {
+  const float off = range * 0.5f, scale = (float)S / range, margin = 1e-3f + 1e-6f * (float)S;
+  float a = (vmin + off) * scale - 0.5f - margin;
+  float b = (vmax + off) * scale - 0.5f + margin;
+  a = fminf(fmaxf(a, -1.0f), (float)S + 1.0f);  // also maps NaN to -1 / S+1 (conservative)
+  b = fminf(fmaxf(b, -2.0f), (float)S);
+  lo = max(0, (int)ceilf(a));
+  hi = min(S - 1, (int)floorf(b));
 }
 
-// Largest pixel index i in [-1, S-1] whose centre satisfies pix(i) <= v (-1 if none).
-__device__ __forceinline__ int last_pix_le(float v, int S, float range) {
-  const float off = range * 0.5f;
-  float est = (v + off) * (float)S / range - 0.5f;
-  est = fminf(fmaxf(est, -2.0f), (float)S);
-  int i = (int)floorf(est);
-  i = max(-1, min(S - 1, i));
-  while (i < S - 1 && pix_to_ndc(i + 1, S, range) <= v) ++i;
-  while (i >= 0 && pix_to_ndc(i, S, range) > v) --i;
-  return i;
-}
-
-// Tile rectangle (in OUTPUT pixel coordinates: xo = W-1-xi, yo = H-1-yi) of the pixels whose centres
-// lie inside [xmin,xmax] x [ymin,ymax] (closed, exactly the reference's per-pixel box test
+// Tile rectangle (in OUTPUT pixel coordinates: xo = W-1-xi, yo = H-1-yi) covering the pixels whose centres
+// lie inside [xmin,xmax] x [ymin,ymax] (the reference's per-pixel box test
 // `px > xmax || px < xmin || py > ymax || py < ymin`, rasterize_meshes.cu:94-97).
 __device__ __forceinline__ uint2 bbox_to_tile_rect(float xmin, float xmax, float ymin, float ymax, int H, int W,
                                                    float rx, float ry) {
-  const int ix_lo = first_pix_ge(xmin, W, rx), ix_hi = last_pix_le(xmax, W, rx);
-  const int iy_lo = first_pix_ge(ymin, H, ry), iy_hi = last_pix_le(ymax, H, ry);
+  int ix_lo, ix_hi, iy_lo, iy_hi;
+  pixel_range(xmin, xmax, W, rx, ix_lo, ix_hi);
+  pixel_range(ymin, ymax, H, ry, iy_lo, iy_hi);
   if (ix_lo > ix_hi || iy_lo > iy_hi) return make_uint2(RECT_EMPTY_X, 0u);
   const uint32_t tx0 = (uint32_t)(W - 1 - ix_hi) / TILE, tx1 = (uint32_t)(W - 1 - ix_lo) / TILE;
   const uint32_t ty0 = (uint32_t)(H - 1 - iy_hi) / TILE, ty1 = (uint32_t)(H - 1 - iy_lo) / TILE;
@@ -62,59 +54,71 @@ __device__ __forceinline__ void count_rect(uint2 r, int n, int TY, int TX, int* 
     for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(tile_count + (n * TY + ty) * TX + tx, 1);
 }
 
-// Exclusive scan of `counts[0..n)` into `offsets[0..n]` by one CTA; zeroes `counts` (they become the
-// fill cursors).
+// Exclusive scan of `counts[0..n)` into `offsets[0..n]` by one CTA of 1024 threads, 8192 elements per sweep
+// (eight coalesced loads in flight per thread, then eight block-wide shuffle scans).  `counts` is overwritten
+// with the segment starts as well: it becomes the array of fill cursors.
 static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict__ counts, int* __restrict__ offsets, int n) {
   __shared__ int warp_sums[32];
+  __shared__ int carry_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int per = (n + 1023) / 1024;
-  const int b = min(n, tid * per), e = min(n, b + per);
-  int s = 0;
-  for (int i = b; i < e; ++i) s += counts[i];
-  int inc = s;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += t;
-  }
-  if (lane == 31) warp_sums[wid] = inc;
+  if (tid == 0) carry_s = 0;
   __syncthreads();
-  if (wid == 0) {
-    int w = warp_sums[lane];
+  for (int base = 0; base < n; base += 8192) {
+    int v[8];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, w, d);
-      if (lane >= d) w += t;
+    for (int it = 0; it < 8; ++it) {
+      const int i = base + it * 1024 + tid;
+      v[it] = i < n ? counts[i] : 0;
     }
-    warp_sums[lane] = w;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      int inc = v[it];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (lane == 31) warp_sums[wid] = inc;
+      __syncthreads();
+      if (wid == 0) {
+        int w = warp_sums[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, w, d);
+          if (lane >= d) w += t;
+        }
+        warp_sums[lane] = w;
+      }
+      __syncthreads();
+      const int carry = carry_s;
+      const int excl = carry + inc - v[it] + (wid > 0 ? warp_sums[wid - 1] : 0);
+      const int i = base + it * 1024 + tid;
+      if (i < n) {
+        offsets[i] = excl;
+        counts[i] = excl;
+      }
+      __syncthreads();
+      if (tid == 0) carry_s = carry + warp_sums[31];
+      __syncthreads();
+    }
   }
-  __syncthreads();
-  int run = inc - s + (wid > 0 ? warp_sums[wid - 1] : 0);
-  for (int i = b; i < e; ++i) {
-    const int c = counts[i];
-    offsets[i] = run;
-    run += c;
-    counts[i] = 0;
-  }
-  if (tid == 1023) offsets[n] = warp_sums[31];
+  if (tid == 0) offsets[n] = carry_s;
 }
 
-// Pass 3: scatter element ids into the tile segments.
+// Pass 3: scatter element ids into the tile segments (`cursor` starts at each segment's begin).
 static __global__ void __launch_bounds__(256)
-    tile_fill_kernel(const uint2* __restrict__ rect, int64_t E, const int64_t* __restrict__ first,
-                     const int64_t* __restrict__ num, int N, int TY, int TX, const int* __restrict__ offsets,
-                     int* __restrict__ cursor, int* __restrict__ pairs, int64_t capacity) {
+    tile_fill_kernel(const uint4* __restrict__ rect, int64_t E, int TY, int TX, int* __restrict__ cursor,
+                     int* __restrict__ pairs, int64_t capacity) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
-  const uint2 r = rect[e];
+  const uint4 r4 = __ldg(rect + e);
+  const uint2 r = make_uint2(r4.x, r4.y);
   if (rect_empty(r)) return;
-  const int n = find_owner(first, num, N, e);
-  if (n < 0) return;
+  const int n = (int)r4.z;
   const int tx0 = r.x & 0xFFFF, tx1 = r.x >> 16, ty0 = r.y & 0xFFFF, ty1 = r.y >> 16;
   for (int ty = ty0; ty <= ty1; ++ty)
     for (int tx = tx0; tx <= tx1; ++tx) {
-      const int t = (n * TY + ty) * TX + tx;
-      const int64_t pos = (int64_t)offsets[t] + atomicAdd(cursor + t, 1);
+      const int64_t pos = atomicAdd(cursor + (n * TY + ty) * TX + tx, 1);
       if (pos < capacity) pairs[pos] = (int)e;
     }
 }
@@ -283,9 +287,9 @@ inline int sort_multiplier(int64_t ntiles) {
 
 // Workspace carving (all int32 / uint2 arrays, 16B-aligned sections).
 struct BinWorkspace {
-  int* tile_count;  // [ntiles]   counts, then fill cursors
+  int* tile_count;  // [ntiles]   counts, then fill cursors (absolute positions)
   int* tile_offset; // [ntiles+1] exclusive offsets; [ntiles] = total pairs
-  uint2* rect;      // [E]
+  uint4* rect;      // [E] tile rectangle (x: tx0|tx1<<16, y: ty0|ty1<<16), z: owning mesh / cloud
   int* pairs;       // [capacity]
   int64_t capacity;
   size_t bytes;
@@ -312,8 +316,8 @@ inline BinWorkspace carve_workspace(void* base, int64_t E, int N, int H, int W, 
   off = align_up(off + sizeof(int) * (size_t)ntiles, 16);
   ws.tile_offset = reinterpret_cast<int*>(p + off);
   off = align_up(off + sizeof(int) * (size_t)(ntiles + 1), 16);
-  ws.rect = reinterpret_cast<uint2*>(p + off);
-  off = align_up(off + sizeof(uint2) * (size_t)(E > 0 ? E : 1), 16);
+  ws.rect = reinterpret_cast<uint4*>(p + off);
+  off = align_up(off + sizeof(uint4) * (size_t)(E > 0 ? E : 1), 16);
   ws.pairs = reinterpret_cast<int*>(p + off);
   off = align_up(off + sizeof(int) * (size_t)capacity, 16);
   ws.bytes = off;

@@ -48,7 +48,7 @@ __device__ __forceinline__ void face_box(const Face& f, float sqrt_blur, float& 
 __global__ void __launch_bounds__(SETUP_FACES)
     mesh_setup_count_kernel(const float* __restrict__ face_verts, int64_t F, const int64_t* __restrict__ first,
                             const int64_t* __restrict__ num, int N, int H, int W, int TY, int TX, float rx,
-                            float ry, float sqrt_blur, int cull_backfaces, uint2* __restrict__ rect,
+                            float ry, float sqrt_blur, int cull_backfaces, uint4* __restrict__ rect,
                             int* __restrict__ tile_count) {
   __shared__ __align__(16) float s_fv[SETUP_FACES * 9];
   __shared__ __align__(8) uint64_t bar;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(SETUP_FACES)
     r = bbox_to_tile_rect(xmin, xmax, ymin, ymax, H, W, rx, ry);
     if (!rect_empty(r)) count_rect(r, n, TY, TX, tile_count);
   }
-  rect[fi] = r;
+  rect[fi] = make_uint4(r.x, r.y, (uint32_t)max(n, 0), 0u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -353,6 +353,28 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParam
       m0 = warp_transpose_bits(m0, lane);
       if (sub + 32 < nc) m1 = warp_transpose_bits(m1, lane);
       unsigned long long mine = valid ? (((unsigned long long)m1 << 32) | m0) : 0ull;
+      if (!(blur_radius > 0.0f)) {
+        // ---- pass B0 (no blur band): a hit requires the pixel to be strictly inside the face, i.e. all three
+        //      w_i = E_i / den > 0, which implies that every edge function E_i is non-zero and has the sign of
+        //      den.  Testing that needs no division; candidates that fail can never be hits and are dropped
+        //      before the expensive pass (typically 2 of 3 for pixel-sized triangles).
+        unsigned long long todo = mine, keep = 0ull;
+        while (__any_sync(0xffffffffu, todo != 0ull)) {
+          if (todo != 0ull) {
+            const unsigned long long bit = todo & (~todo + 1ull);
+            const int j = sub + __ffsll((long long)todo) - 1;
+            todo ^= bit;
+            const float4 fa = s.a[j], fb = s.b[j];
+            const float e0 = edge_fn(px, py, fa.z, fa.w, fb.x, fb.y);  // E(p; v1, v2)
+            const float e1 = edge_fn(px, py, fb.x, fb.y, fa.x, fa.y);  // E(p; v2, v0)
+            const float e2 = edge_fn(px, py, fa.x, fa.y, fa.z, fa.w);  // E(p; v0, v1)
+            const bool pos = fb.z > 0.0f;
+            const bool ok = pos ? (e0 > 0.0f && e1 > 0.0f && e2 > 0.0f) : (e0 < 0.0f && e1 < 0.0f && e2 < 0.0f);
+            if (ok) keep |= bit;
+          }
+        }
+        mine = keep;
+      }
       // ---- pass B: every lane evaluates its own candidates, in ascending face order
       while (__any_sync(0xffffffffu, mine != 0ull)) {
         if (mine != 0ull) {
@@ -820,8 +842,7 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
   tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles);
   B200R_LAUNCHED("tile_scan_kernel");
   if (F > 0) {
-    tile_fill_kernel<<<(unsigned)((F + 255) / 256), 256, 0, stream>>>(ws.rect, F, first, num, N, TY, TX,
-                                                                    ws.tile_offset, ws.tile_count, ws.pairs,
+    tile_fill_kernel<<<(unsigned)((F + 255) / 256), 256, 0, stream>>>(ws.rect, F, TY, TX, ws.tile_count, ws.pairs,
                                                                     ws.capacity);
     B200R_LAUNCHED("tile_fill_kernel");
   }

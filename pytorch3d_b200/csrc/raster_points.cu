@@ -24,7 +24,7 @@ constexpr int PCHUNK = 512;  // points staged per round (2 per thread)
 __global__ void __launch_bounds__(SETUP_POINTS)
     points_setup_count_kernel(const float* __restrict__ points, const float* __restrict__ radius, int64_t P,
                               const int64_t* __restrict__ first, const int64_t* __restrict__ num, int N, int H,
-                              int W, int TY, int TX, float rx, float ry, uint2* __restrict__ rect,
+                              int W, int TY, int TX, float rx, float ry, uint4* __restrict__ rect,
                               int* __restrict__ tile_count) {
   __shared__ __align__(16) float s_pts[SETUP_POINTS * 3];
   __shared__ __align__(8) uint64_t bar;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(SETUP_POINTS)
     rc = bbox_to_tile_rect(fsub(x, r), fadd(x, r), fsub(y, r), fadd(y, r), H, W, rx, ry);
     if (!rect_empty(rc)) count_rect(rc, n, TY, TX, tile_count);
   }
-  rect[pi] = rc;
+  rect[pi] = make_uint4(rc.x, rc.y, (uint32_t)max(n, 0), 0u);
 }
 
 // The K nearest points of one pixel: the reference's queue (rasterize_points.cu:61-79) restated for
@@ -367,8 +367,7 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
   tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles);
   B200R_LAUNCHED("tile_scan_kernel");
   if (P > 0) {
-    tile_fill_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(ws.rect, P, first, num, N, TY, TX,
-                                                                    ws.tile_offset, ws.tile_count, ws.pairs,
+    tile_fill_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(ws.rect, P, TY, TX, ws.tile_count, ws.pairs,
                                                                     ws.capacity);
     B200R_LAUNCHED("tile_fill_kernel");
   }
