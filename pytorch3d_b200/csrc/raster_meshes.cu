@@ -306,7 +306,7 @@ __device__ __forceinline__ float warp_max(float v) {
 constexpr int ROUND = 64;
 
 template <int KMAX, bool NB>
-__global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParams p) {
+__global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FineParams p) {
   __shared__ FaceChunk s;
   const int tid = threadIdx.x, lane = tid & 31;
   const int t = blockIdx.x;
@@ -318,13 +318,6 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParam
   const bool valid = xo < p.W && yo < p.H;
   const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
   const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
-  // the footprint's 8 column and 4 row coordinates (lane = row * 8 + column)
-  float col[8], row[4];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) col[c] = __shfl_sync(0xffffffffu, px, c);
-#pragma unroll
-  for (int r = 0; r < 4; ++r) row[r] = __shfl_sync(0xffffffffu, py, 8 * r);
-
   // the tile's face list; tiles whose segment did not fit the pair buffer test every face of the mesh
   const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
   const bool overflow = (int64_t)seg_end > p.capacity;
@@ -348,8 +341,17 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_kernel(const FineParam
     for (int sub = 0; sub < nc; sub += ROUND) {
       // ---- pass A: 64-bit mask of the faces of this round whose box contains my pixel
       unsigned m0 = 0, m1 = 0;
-      if (sub + lane < nc) m0 = box_pixel_mask(s.box[sub + lane], col, row);
-      if (sub + 32 + lane < nc) m1 = box_pixel_mask(s.box[sub + 32 + lane], col, row);
+      {
+        // the footprint's 8 column and 4 row coordinates (lane = row * 8 + column); re-gathered per round so
+        // that they do not occupy 12 registers during pass B and the epilogue
+        float col[8], row[4];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) col[c] = __shfl_sync(0xffffffffu, px, c);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) row[r] = __shfl_sync(0xffffffffu, py, 8 * r);
+        if (sub + lane < nc) m0 = box_pixel_mask(s.box[sub + lane], col, row);
+        if (sub + 32 + lane < nc) m1 = box_pixel_mask(s.box[sub + 32 + lane], col, row);
+      }
       m0 = warp_transpose_bits(m0, lane);
       if (sub + 32 < nc) m1 = warp_transpose_bits(m1, lane);
       unsigned long long mine = valid ? (((unsigned long long)m1 << 32) | m0) : 0ull;
