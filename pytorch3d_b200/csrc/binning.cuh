@@ -2,14 +2,17 @@
 //
 // Role of the reference's coarse stage (pytorch3d/csrc/rasterize_coarse/rasterize_coarse.cu:76-219),
 // redesigned: instead of a dense (N, BH, BW, M) table pre-filled with -1 and a brute-force
-// element x bin overlap test, every element (face / point) computes the exact range of pixel
-// centres its bounding box can cover, converts it to a rectangle of 16x16-pixel tiles, and
+// element x bin overlap test, every element (face / point) computes the range of pixel centres
+// its bounding box can cover (tight to 1e-3 pixel), converts it to a rectangle of 16x16-pixel tiles, and
 //   pass 1 (setup+count)  atomically counts elements per tile,
 //   pass 2 (scan)         exclusive-scans the counts into segment offsets,
-//   pass 3 (fill)         writes element ids into each tile's compact segment.
+//   pass 3 (fill)         writes element ids into each tile's compact segment,
+//   pass 4 (sort)         puts every segment in ascending element order.
 // No M cap, no overflow drop, no -1 fill; elements whose box contains no pixel centre (most
 // sub-pixel triangles) are never binned at all.
 #pragma once
+#include <climits>
+
 #include "common.cuh"
 #include "raster_math.cuh"
 
@@ -58,11 +61,13 @@ __device__ __forceinline__ void count_rect(uint2 r, int n, int TY, int TX, int* 
 // (eight coalesced loads in flight per thread, then eight block-wide shuffle scans).  `counts` is overwritten
 // with the segment starts as well: it becomes the array of fill cursors.
 static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict__ counts, int* __restrict__ offsets, int n) {
-  __shared__ int warp_sums[32];
-  __shared__ int carry_s;
+  __shared__ long long warp_sums[32];
+  __shared__ long long carry_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) carry_s = 0;
   __syncthreads();
+  // 64-bit running sums, saturated to INT_MAX on output: a batch whose (tile, element) pairs would overflow
+  // int32 simply marks the remaining tiles as "does not fit" (they rasterise from the whole mesh range).
   for (int base = 0; base < n; base += 8192) {
     int v[8];
 #pragma unroll
@@ -72,37 +77,38 @@ static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict_
     }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-      int inc = v[it];
+      long long inc = v[it];
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        const long long t = __shfl_up_sync(0xffffffffu, inc, d);
         if (lane >= d) inc += t;
       }
       if (lane == 31) warp_sums[wid] = inc;
       __syncthreads();
       if (wid == 0) {
-        int w = warp_sums[lane];
+        long long w = warp_sums[lane];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, w, d);
+          const long long t = __shfl_up_sync(0xffffffffu, w, d);
           if (lane >= d) w += t;
         }
         warp_sums[lane] = w;
       }
       __syncthreads();
-      const int carry = carry_s;
-      const int excl = carry + inc - v[it] + (wid > 0 ? warp_sums[wid - 1] : 0);
+      const long long carry = carry_s;
+      const long long excl = carry + inc - v[it] + (wid > 0 ? warp_sums[wid - 1] : 0);
       const int i = base + it * 1024 + tid;
       if (i < n) {
-        offsets[i] = excl;
-        counts[i] = excl;
+        const int e32 = (int)min(excl, (long long)INT_MAX);
+        offsets[i] = e32;
+        counts[i] = e32;
       }
       __syncthreads();
       if (tid == 0) carry_s = carry + warp_sums[31];
       __syncthreads();
     }
   }
-  if (tid == 0) offsets[n] = carry_s;
+  if (tid == 0) offsets[n] = (int)min(carry_s, (long long)INT_MAX);
 }
 
 // Pass 3: scatter element ids into the tile segments (`cursor` starts at each segment's begin).
@@ -118,8 +124,8 @@ static __global__ void __launch_bounds__(256)
   const int tx0 = r.x & 0xFFFF, tx1 = r.x >> 16, ty0 = r.y & 0xFFFF, ty1 = r.y >> 16;
   for (int ty = ty0; ty <= ty1; ++ty)
     for (int tx = tx0; tx <= tx1; ++tx) {
-      const int64_t pos = atomicAdd(cursor + (n * TY + ty) * TX + tx, 1);
-      if (pos < capacity) pairs[pos] = (int)e;
+      const int pos = atomicAdd(cursor + (n * TY + ty) * TX + tx, 1);
+      if (pos >= 0 && (int64_t)pos < capacity) pairs[pos] = (int)e;  // (pos < 0: saturated / wrapped cursor)
     }
 }
 
@@ -235,7 +241,7 @@ static __global__ void __launch_bounds__(SORT_THREADS)
     const int t = slot < ntiles ? sort_tile_of(slot, ntiles, mult) : -1;
     const int begin = t >= 0 ? offsets[t] : 0, end = t >= 0 ? offsets[t + 1] : 0;
     const int n = end - begin;
-    if (n >= 2 && n <= SORT_WARP_MAX && (int64_t)end <= capacity) {
+    if (n >= 2 && n <= SORT_WARP_MAX && (int64_t)end <= capacity && end != INT_MAX) {
       if (n <= 32)
         sort_segment_warp<1>(pairs, begin, n, lane);
       else if (n <= 64)
@@ -257,7 +263,7 @@ static __global__ void __launch_bounds__(SORT_THREADS)
     const int t = sort_tile_of(slot, ntiles, mult);
     const int begin = offsets[t], end = offsets[t + 1];
     const int n = end - begin;
-    if (n <= SORT_WARP_MAX || (int64_t)end > capacity) continue;  // (overflowed tiles are not used)
+    if (n <= SORT_WARP_MAX || (int64_t)end > capacity || end == INT_MAX) continue;  // (overflowed: not used)
     const bool in_smem = n <= SORT_SMEM_ELEMS;
     int* keys = in_smem ? s_keys : pairs + begin;
     __syncthreads();

@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
   const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
   // the tile's face list; tiles whose segment did not fit the pair buffer test every face of the mesh
   const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
-  const bool overflow = (int64_t)seg_end > p.capacity;
+  const bool overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
   const int64_t mesh_first = p.first[n];
   const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
 
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const Fine
   const float fx_lo = warp_min(valid ? px : FLT_MAX), fx_hi = warp_max(valid ? px : -FLT_MAX);
   const float fy_lo = warp_min(valid ? py : FLT_MAX), fy_hi = warp_max(valid ? py : -FLT_MAX);
   const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
-  const bool overflow = (int64_t)seg_end > p.capacity;
+  const bool overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
   const int64_t mesh_first = p.first[n];
   const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
   const bool persp = p.persp != 0, clip = p.clip != 0, cull = p.cull != 0;

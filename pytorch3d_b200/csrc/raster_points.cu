@@ -168,17 +168,6 @@ __device__ __forceinline__ void pthread_pixel(int tile_x, int tile_y, int& xo, i
   yo = tile_y * TILE + (w >> 1) * 4 + (lane >> 3);
 }
 
-__device__ __forceinline__ float pwarp_min(float v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, d));
-  return v;
-}
-__device__ __forceinline__ float pwarp_max(float v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
-  return v;
-}
-
 // KMAX > 0: register top-K; KMAX == 0: thread-local arrays for K up to 150.
 template <int KMAX>
 __global__ void __launch_bounds__(TILE_THREADS) points_fine_kernel(const PointFineParams p) {
@@ -199,7 +188,7 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_kernel(const PointFi
   for (int r = 0; r < 4; ++r) row[r] = __shfl_sync(0xffffffffu, py, 8 * r);
 
   const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
-  const bool overflow = (int64_t)seg_end > p.capacity;
+  const bool overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
   const int64_t cloud_first = p.first[n];
   const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
   const int K = p.K;
