@@ -51,10 +51,29 @@ __device__ __forceinline__ uint2 bbox_to_tile_rect(float xmin, float xmax, float
 
 __device__ __forceinline__ bool rect_empty(uint2 r) { return (r.x & 0xFFFFu) > (r.x >> 16); }
 
-__device__ __forceinline__ void count_rect(uint2 r, int n, int TY, int TX, int* __restrict__ tile_count) {
+// Count one element per tile of its rectangle.  Called by ALL 32 lanes of a warp (lanes without work pass an
+// empty rectangle): consecutive elements of a packed mesh are neighbours on screen, so most lanes of a warp
+// target the same few tiles -- the lanes that agree are found with __match_any_sync and only one of them issues
+// the atomic, with the group's population.  This removes the serialisation of thousands of atomics on the hot
+// tiles of a silhouette.
+__device__ __forceinline__ void warp_count_rect(uint2 r, int n, int TY, int TX, int* __restrict__ tile_count,
+                                                int lane) {
+  const bool empty = rect_empty(r);
   const int tx0 = r.x & 0xFFFF, tx1 = r.x >> 16, ty0 = r.y & 0xFFFF, ty1 = r.y >> 16;
-  for (int ty = ty0; ty <= ty1; ++ty)
-    for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(tile_count + (n * TY + ty) * TX + tx, 1);
+  const int w = empty ? 1 : tx1 - tx0 + 1;
+  const int ntile = empty ? 0 : w * (ty1 - ty0 + 1);
+  const int rounds = (int)__reduce_max_sync(0xffffffffu, (unsigned)ntile);
+  int tx = tx0, ty = ty0;
+  for (int i = 0; i < rounds; ++i) {
+    const bool act = i < ntile;
+    const int t = act ? (n * TY + ty) * TX + tx : -1 - lane;  // inactive lanes get unique keys
+    const unsigned grp = __match_any_sync(0xffffffffu, t);
+    if (act && lane == __ffs(grp) - 1) atomicAdd(tile_count + t, __popc(grp));
+    if (++tx > tx1) {
+      tx = tx0;
+      ++ty;
+    }
+  }
 }
 
 // Exclusive scan of `counts[0..n)` into `offsets[0..n]` by one CTA of 1024 threads, 8192 elements per sweep
@@ -111,22 +130,41 @@ static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict_
   if (tid == 0) offsets[n] = (int)min(carry_s, (long long)INT_MAX);
 }
 
-// Pass 3: scatter element ids into the tile segments (`cursor` starts at each segment's begin).
+// Pass 3: scatter element ids into the tile segments (`cursor` starts at each segment's begin).  Same warp
+// aggregation as in the count pass: one returning atomic per (warp, tile); the lanes of a group take
+// consecutive positions in lane (= element) order.
 static __global__ void __launch_bounds__(256)
     tile_fill_kernel(const uint4* __restrict__ rect, int64_t E, int TY, int TX, int* __restrict__ cursor,
                      int* __restrict__ pairs, int64_t capacity) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  const uint4 r4 = __ldg(rect + e);
+  const int lane = threadIdx.x & 31;
+  uint4 r4 = make_uint4(RECT_EMPTY_X, 0u, 0u, 0u);
+  if (e < E) r4 = __ldg(rect + e);
   const uint2 r = make_uint2(r4.x, r4.y);
-  if (rect_empty(r)) return;
+  const bool empty = rect_empty(r);
   const int n = (int)r4.z;
   const int tx0 = r.x & 0xFFFF, tx1 = r.x >> 16, ty0 = r.y & 0xFFFF, ty1 = r.y >> 16;
-  for (int ty = ty0; ty <= ty1; ++ty)
-    for (int tx = tx0; tx <= tx1; ++tx) {
-      const int pos = atomicAdd(cursor + (n * TY + ty) * TX + tx, 1);
+  const int w = empty ? 1 : tx1 - tx0 + 1;
+  const int ntile = empty ? 0 : w * (ty1 - ty0 + 1);
+  const int rounds = (int)__reduce_max_sync(0xffffffffu, (unsigned)ntile);
+  int tx = tx0, ty = ty0;
+  for (int i = 0; i < rounds; ++i) {
+    const bool act = i < ntile;
+    const int t = act ? (n * TY + ty) * TX + tx : -1 - lane;
+    const unsigned grp = __match_any_sync(0xffffffffu, t);
+    const int leader = __ffs(grp) - 1;
+    int base = 0;
+    if (act && lane == leader) base = atomicAdd(cursor + t, __popc(grp));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (act) {
+      const int pos = base + __popc(grp & ((1u << lane) - 1u));
       if (pos >= 0 && (int64_t)pos < capacity) pairs[pos] = (int)e;  // (pos < 0: saturated / wrapped cursor)
     }
+    if (++tx > tx1) {
+      tx = tx0;
+      ++ty;
+    }
+  }
 }
 
 // Pass 4: sort every tile segment into ascending element order (one CTA per tile).  The fill pass

@@ -61,19 +61,21 @@ __global__ void __launch_bounds__(SETUP_FACES)
   }
   __syncthreads();
   cta_load_words(s_fv, face_verts + f0 * 9, nf * 9, &bar, 0);
-  if (tid >= nf) return;
-  const float* v = s_fv + tid * 9;  // stride 9 words: conflict-free across a warp
-  const Face f = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]};
-  const int64_t fi = f0 + tid;
   uint2 r = make_uint2(RECT_EMPTY_X, 0u);
-  const int n = find_owner(first, num, N, fi);
-  if (n >= 0 && face_is_drawable(f, cull_backfaces != 0)) {
-    float xmin, xmax, ymin, ymax;
-    face_box(f, sqrt_blur, xmin, xmax, ymin, ymax);
-    r = bbox_to_tile_rect(xmin, xmax, ymin, ymax, H, W, rx, ry);
-    if (!rect_empty(r)) count_rect(r, n, TY, TX, tile_count);
+  int n = -1;
+  const int64_t fi = f0 + tid;
+  if (tid < nf) {
+    const float* v = s_fv + tid * 9;  // stride 9 words: conflict-free across a warp
+    const Face f = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]};
+    n = find_owner(first, num, N, fi);
+    if (n >= 0 && face_is_drawable(f, cull_backfaces != 0)) {
+      float xmin, xmax, ymin, ymax;
+      face_box(f, sqrt_blur, xmin, xmax, ymin, ymax);
+      r = bbox_to_tile_rect(xmin, xmax, ymin, ymax, H, W, rx, ry);
+    }
+    rect[fi] = make_uint4(r.x, r.y, (uint32_t)max(n, 0), 0u);
   }
-  rect[fi] = make_uint4(r.x, r.y, (uint32_t)max(n, 0), 0u);
+  warp_count_rect(r, n, TY, TX, tile_count, tid & 31);  // all lanes participate
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -665,7 +667,7 @@ __device__ __forceinline__ void backward_one(const BackwardParams& p, float px, 
       gsc = 0.0f;
       sum = 1e-5f;
     }
-    const float inv = 1.0f / sum, inv2 = gsc / (sum * sum);
+    const float inv = __frcp_rn(sum), inv2 = gsc * inv * inv;
     const float s0 = -m0 * inv2, s1 = -m1 * inv2, s2 = -m2 * inv2;
     const float cross = g0 * s0 + g1 * s1 + g2 * s2;
     const float n0 = c0 < 0.0f ? 0.0f : g0 * inv + cross;
@@ -679,8 +681,9 @@ __device__ __forceinline__ void backward_one(const BackwardParams& p, float px, 
   if (persp) {  // BarycentricPerspectiveCorrectionBackward (geometry_utils.cuh:200-228)
     const float t0 = w0 * f.z1 * f.z2, t1 = f.z0 * w1 * f.z2, t2 = f.z0 * f.z1 * w2;
     const float dn = fmaxf(t0 + t1 + t2, 1e-8f);
-    const float gdn = (-t0 * g0 - t1 * g1 - t2 * g2) / (dn * dn);
-    const float h0 = gdn + g0 / dn, h1 = gdn + g1 / dn, h2 = gdn + g2 / dn;
+    const float rdn = __frcp_rn(dn);
+    const float gdn = (-t0 * g0 - t1 * g1 - t2 * g2) * rdn * rdn;
+    const float h0 = gdn + g0 * rdn, h1 = gdn + g1 * rdn, h2 = gdn + g2 * rdn;
     g0 = h0 * f.z1 * f.z2;
     g1 = h1 * f.z0 * f.z2;
     g2 = h2 * f.z0 * f.z1;
@@ -691,13 +694,13 @@ __device__ __forceinline__ void backward_one(const BackwardParams& p, float px, 
   // BarycentricCoordsBackward (geometry_utils.cuh:101-161)
   float2 bv0 = make_float2(0.f, 0.f), bv1 = bv0, bv2 = bv0;
   {
-    const float area2 = den * den, rden = 1.0f / den;
+    const float rden = __frcp_rn(den);
     const float e0 = edge_fn(px, py, f.x1, f.y1, f.x2, f.y2);
     const float e1 = edge_fn(px, py, f.x2, f.y2, f.x0, f.y0);
     const float e2 = edge_fn(px, py, f.x0, f.y0, f.x1, f.y1);
     float2 dp, da, db, ap, aa, ab;
     // every w_i = e_i / area also depends on area = E(v2; v0, v1)
-    const float garea = g0 * (-e0 / area2) + g1 * (-e1 / area2) + g2 * (-e2 / area2);
+    const float garea = -(g0 * e0 + g1 * e1 + g2 * e2) * rden * rden;
     edge_bwd(f.x2, f.y2, f.x0, f.y0, f.x1, f.y1, garea, ap, aa, ab);  // (p=v2, a=v0, b=v1)
     bv2.x += ap.x; bv2.y += ap.y;
     bv0.x += aa.x; bv0.y += aa.y;
@@ -750,7 +753,7 @@ __device__ __forceinline__ void warp_scatter(float* __restrict__ grad_face_verts
 // KV > 0: K == KV (a multiple of 4) and the pixel's KV face indices are fetched up front with 16-byte loads
 // (a pixel with no face costs nothing else); KV == 0: any K, scalar loads.
 template <int KV>
-__global__ void __launch_bounds__(TILE_THREADS) mesh_backward_kernel(const BackwardParams p) {
+__global__ void __launch_bounds__(TILE_THREADS, 4) mesh_backward_kernel(const BackwardParams p) {
   const int t = blockIdx.x;
   const int lane = threadIdx.x & 31;
   const int n = t / (p.TY * p.TX);

@@ -37,17 +37,17 @@ __global__ void __launch_bounds__(SETUP_POINTS)
   }
   __syncthreads();
   cta_load_words(s_pts, points + p0 * 3, np * 3, &bar, 0);
-  if (tid >= np) return;
-  const float x = s_pts[tid * 3 + 0], y = s_pts[tid * 3 + 1], z = s_pts[tid * 3 + 2];  // stride 3: conflict-free
-  const int64_t pi = p0 + tid;
-  const float r = __ldg(radius + pi);
   uint2 rc = make_uint2(RECT_EMPTY_X, 0u);
-  const int n = find_owner(first, num, N, pi);
-  if (n >= 0 && !(z < 0.0f)) {
-    rc = bbox_to_tile_rect(fsub(x, r), fadd(x, r), fsub(y, r), fadd(y, r), H, W, rx, ry);
-    if (!rect_empty(rc)) count_rect(rc, n, TY, TX, tile_count);
+  int n = -1;
+  const int64_t pi = p0 + tid;
+  if (tid < np) {
+    const float x = s_pts[tid * 3 + 0], y = s_pts[tid * 3 + 1], z = s_pts[tid * 3 + 2];  // stride 3: conflict-free
+    const float r = __ldg(radius + pi);
+    n = find_owner(first, num, N, pi);
+    if (n >= 0 && !(z < 0.0f)) rc = bbox_to_tile_rect(fsub(x, r), fadd(x, r), fsub(y, r), fadd(y, r), H, W, rx, ry);
+    rect[pi] = make_uint4(rc.x, rc.y, (uint32_t)max(n, 0), 0u);
   }
-  rect[pi] = make_uint4(rc.x, rc.y, (uint32_t)max(n, 0), 0u);
+  warp_count_rect(rc, n, TY, TX, tile_count, tid & 31);  // all lanes participate
 }
 
 // The K nearest points of one pixel: the reference's queue (rasterize_points.cu:61-79) restated for
