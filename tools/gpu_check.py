@@ -175,6 +175,13 @@ if __name__ == "__main__":
         tf = timeit(lambda: _C.rasterize_meshes(fv, first, num, nb, (512, 512), blur, 8, 0, 0, False, False, False))
         tb = timeit(lambda: _C.rasterize_meshes_backward(fv, out[0], gz, gb, gd, False, False))
         hits = int((out[0] >= 0).sum())
+        import ctypes
+        from pytorch3d_b200 import _lib
+        lib = _lib.load(); lib.b200r_set_profiling(1); buf = (ctypes.c_float * 3)()
+        torch.cuda._sleep(2000000)
+        _C.rasterize_meshes(fv, first, num, nb, (512, 512), blur, 8, 0, 0, False, False, False)
+        lib.b200r_last_phase_ms(buf); lib.b200r_set_profiling(0)
+        print("   phases: binning %.3f ms  fine %.3f ms" % (buf[0], buf[1]), flush=True)
         print("NS 8x%d faces 512^2 K=8 blur=%g: fwd %.3f ms  bwd %.3f ms  -> %.1f frames/s ; hits %d" % (
             int(num[0]), blur, tf, tb, 8e3 / (tf + tb), hits), flush=True)
         if ref is not None and not quick:
