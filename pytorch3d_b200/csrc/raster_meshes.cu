@@ -110,43 +110,18 @@ __device__ __forceinline__ bool key_less(float za, int ia, float zb, int ib) {
   return za < zb || (za == zb && ia < ib);  // operator< of the reference's Pixel (rasterize_meshes.cu:30-32)
 }
 
-// Hit test of the fine loop: same decisions as eval_pixel_face, but only the depth (and, when it is needed
-// to decide, the distance) is produced; barycentrics and distance of the final winners are recomputed once
-// at the end by eval_pixel_face (identical arithmetic => identical values).
-template <bool ALWAYS_DIST>
-__device__ __forceinline__ bool test_pixel_face(float px, float py, const Face& f, float den, float blur_radius,
-                                                bool persp, bool clip, float& pz_out, float& dist_out) {
-  float w0, w1, w2;
-  bary_coords(px, py, f, den, w0, w1, w2);
-  if (persp) bary_persp(w0, w1, w2, f.z0, f.z1, f.z2);
-  const bool inside = w0 > 0.0f && w1 > 0.0f && w2 > 0.0f;
-  if (!inside && !(blur_radius > 0.0f)) return false;
-  float c0 = w0, c1 = w1, c2 = w2;
-  if (clip) bary_clip(c0, c1, c2);
-  const float pz = ffma(f.z2, c2, ffma(f.z0, c0, fmul(f.z1, c1)));
-  if (!(pz >= 0.0f)) return false;
-  if (ALWAYS_DIST || !inside) {
-    const float dist = point_tri_dist(px, py, f);
-    if (!inside && dist >= blur_radius) return false;
-    dist_out = dist;
-  }
-  pz_out = pz;
-  return true;
-}
-
-// The K nearest hits of one pixel.  This is the reference's per-pixel queue (rasterize_meshes.cu:179-237)
-// restated for registers: an UNSORTED array of K slots plus the tracked maximum (q_max_z, q_max_idx); a new
-// hit fills the next free slot, or -- when the queue is full and pz < q_max_z -- overwrites the tracked
-// maximum, after which the maximum is searched again (first slot with a strictly larger z wins).  Faces
-// reach the queue in ascending index order (sorted tile lists), so ties are resolved exactly as by the
-// reference's naive kernel.  Only the keys (z, face) are queued (plus |dist| when clipped-face neighbours
-// are in play); all array indices are compile-time constants (predicated updates), so the queue never
-// leaves the register file.
-template <int KMAX, bool NB>
+// The K nearest hits of one pixel.  This is the reference's per-pixel queue (rasterize_meshes.cu:179-237):
+// an UNSORTED array of K slots plus the tracked maximum (q_max_z, q_max_idx); a new hit fills the next free
+// slot, or -- when the queue is full and pz < q_max_z -- overwrites the tracked maximum, after which the
+// maximum is searched again (first slot with a strictly larger z wins).  Faces reach the queue in ascending
+// index order (sorted tile lists), so ties are resolved exactly as by the reference's naive kernel.
+// The keys (z, face) live in registers with compile-time indices only (predicated updates); the payload
+// (signed distance + barycentrics) of slot k lives in shared memory at pay[k * TILE_THREADS + thread], where
+// a dynamic slot index costs nothing.
+template <int KMAX>
 struct TopK {
   float z[KMAX];
   int id[KMAX];
-  float d[NB ? KMAX : 1];
   int size;
   float max_z;
   int max_idx;
@@ -156,33 +131,32 @@ struct TopK {
     for (int i = 0; i < KMAX; ++i) {
       z[i] = -1.0f;
       id[i] = -1;
-      if (NB) d[i] = 0.0f;
     }
     size = 0;
     max_z = -1000.0f;  // (:292)
     max_idx = -1;
   }
-  __device__ __forceinline__ void put(int slot, float pz, int f, float dist) {
+  __device__ __forceinline__ void put(int slot, const Hit& h, int f, float4* pay) {
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
       const bool w = i == slot;
-      z[i] = w ? pz : z[i];
+      z[i] = w ? h.z : z[i];
       id[i] = w ? f : id[i];
-      if (NB) d[i] = w ? dist : d[i];
     }
+    pay[slot * TILE_THREADS] = make_float4(h.dist, h.b0, h.b1, h.b2);
   }
   // Handle a face that covers the pixel (the `else` branch at :216-236).
-  __device__ __forceinline__ void offer(float pz, int f, float dist, int K) {
+  __device__ __forceinline__ void offer(const Hit& h, int f, int K, float4* pay) {
     if (size < K) {
-      put(size, pz, f, dist);
-      if (pz > max_z) {
-        max_z = pz;
+      put(size, h, f, pay);
+      if (h.z > max_z) {
+        max_z = h.z;
         max_idx = size;
       }
       ++size;
-    } else if (pz < max_z) {
-      put(max_idx, pz, f, dist);
-      max_z = pz;
+    } else if (h.z < max_z) {
+      put(max_idx, h, f, pay);
+      max_z = h.z;
 #pragma unroll
       for (int i = 0; i < KMAX; ++i) {
         if (i < K && z[i] > max_z) {
@@ -194,29 +168,28 @@ struct TopK {
   }
   // Clipped-face neighbour handling (:186-215): if the other half of a clipped quad is already queued,
   // keep whichever half is closer to the pixel.  Returns true if the hit was consumed here.
-  __device__ __forceinline__ bool offer_neighbor(float pz, int f, float dist, int neighbor) {
+  __device__ __forceinline__ bool offer_neighbor(const Hit& h, int f, int neighbor, float4* pay) {
     int at = -1;
 #pragma unroll
     for (int i = KMAX - 1; i >= 0; --i)
       if (i < size && id[i] == neighbor) at = i;  // first match
     if (at < 0) return false;
-    float nd = 0.0f;
-#pragma unroll
-    for (int i = 0; i < KMAX; ++i) nd = i == at ? d[NB ? i : 0] : nd;
-    if (dist < nd) {
-      put(at, pz, f, dist);
-      if (pz > max_z) {
-        max_z = pz;
+    if (fabsf(h.dist) < fabsf(pay[at * TILE_THREADS].x)) {
+      put(at, h, f, pay);
+      if (h.z > max_z) {
+        max_z = h.z;
         max_idx = at;
       }
     }
     return true;
   }
   // BubbleSort(q, q_size) on (z, idx) (:322 / rasterization_utils.cuh:52-66).  Keys are unique, so any
-  // sorting network gives the same result; unfilled slots are pushed to the end.
-  __device__ __forceinline__ void sort() {
+  // sorting network gives the same result; unfilled slots are pushed to the end.  slot[k] = queue slot (and
+  // payload row) of the k-th nearest hit.
+  __device__ __forceinline__ void sort(int (&slot)[KMAX]) {
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
+      slot[i] = i;
       if (i >= size) {
         z[i] = FLT_MAX;
         id[i] = INT_MAX;
@@ -230,9 +203,12 @@ struct TopK {
           const float t = z[i];
           z[i] = z[i + 1];
           z[i + 1] = t;
-          const int ti = id[i];
+          int ti = id[i];
           id[i] = id[i + 1];
           id[i + 1] = ti;
+          ti = slot[i];
+          slot[i] = slot[i + 1];
+          slot[i + 1] = ti;
         }
       }
     }
@@ -310,7 +286,9 @@ constexpr int ROUND = 64;
 template <int KMAX, bool NB>
 __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FineParams p) {
   __shared__ FaceChunk s;
+  __shared__ float4 s_pay[KMAX * TILE_THREADS];  // queue payload: (signed dist, bary0, bary1, bary2) per slot
   const int tid = threadIdx.x, lane = tid & 31;
+  float4* pay = s_pay + tid;
   const int t = blockIdx.x;
   const int n = t / (p.TY * p.TX);
   const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
@@ -326,7 +304,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
   const int64_t mesh_first = p.first[n];
   const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
 
-  TopK<KMAX, NB> q;
+  TopK<KMAX> q;
   q.init();
   const bool persp = p.persp != 0, clip = p.clip != 0, cull = p.cull != 0;
   const int K = p.K;
@@ -386,15 +364,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
           mine &= mine - 1ull;
           const float4 fa = s.a[j], fb = s.b[j], fc = s.c[j];
           const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
-          float pz, dist = 0.0f;
-          if (test_pixel_face<NB>(px, py, f, fb.z, blur_radius, persp, clip, pz, dist)) {
+          Hit h;
+          if (eval_pixel_face(px, py, f, fb.z, blur_radius, persp, clip, h)) {
             const int fi = __float_as_int(fb.w);
             bool consumed = false;
             if (NB) {
               const int nb = __float_as_int(fc.w);
-              if (nb != -1) consumed = q.offer_neighbor(pz, fi, dist, nb);
+              if (nb != -1) consumed = q.offer_neighbor(h, fi, nb, pay);
             }
-            if (!consumed) q.offer(pz, fi, dist, K);
+            if (!consumed) q.offer(h, fi, K, pay);
           }
         }
       }
@@ -402,12 +380,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
   }
 
   if (!valid) return;
-  q.sort();
-  // ---- epilogue: barycentrics / distance of the winners are recomputed, four slots at a time, and every
-  //      output is written with 16-byte stores (all K slots, including the -1 padding)
+  int slot[KMAX];
+  q.sort(slot);
+  // ---- epilogue: every output is written with 16-byte stores (all K slots, including the -1 padding)
   const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
-  const bool vec = K == KMAX && (KMAX % 4) == 0;
-  if (vec) {
+  if (K == KMAX && (KMAX % 4) == 0) {
     longlong2* pf = reinterpret_cast<longlong2*>(p.pix_to_face + o);
 #pragma unroll
     for (int k = 0; k < KMAX; k += 2) {
@@ -415,49 +392,35 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
       const long long i1 = k + 1 >= q.size ? -1ll : (long long)q.id[k + 1];
       pf[k / 2] = make_longlong2(i0, i1);
     }
-  }
 #pragma unroll
-  for (int k0 = 0; k0 < KMAX; k0 += 4) {
-    float od[4], ob0[4], ob1[4], ob2[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int k = k0 + u;
-      od[u] = ob0[u] = ob1[u] = ob2[u] = -1.0f;
-      if (k < KMAX && k < q.size) {
-        const float* v = p.face_verts + (int64_t)q.id[k < KMAX ? k : 0] * 9;
-        const Face f = {__ldg(v + 0), __ldg(v + 1), __ldg(v + 2), __ldg(v + 3), __ldg(v + 4),
-                        __ldg(v + 5), __ldg(v + 6), __ldg(v + 7), __ldg(v + 8)};
-        Hit h;
-        eval_pixel_face(px, py, f, bary_denominator(f), blur_radius, persp, clip, h);
-        od[u] = h.dist;
-        ob0[u] = h.b0;
-        ob1[u] = h.b1;
-        ob2[u] = h.b2;
-      }
-    }
-    if (vec) {
+    for (int k0 = 0; k0 + 3 < KMAX; k0 += 4) {
+      float4 w[4];
       float zz[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) zz[u] = (k0 + u) >= q.size ? -1.0f : q.z[(k0 + u) < KMAX ? k0 + u : 0];
-      reinterpret_cast<float4*>(p.zbuf + o)[k0 / 4] = make_float4(zz[0], zz[1], zz[2], zz[3]);
-      reinterpret_cast<float4*>(p.dists + o)[k0 / 4] = make_float4(od[0], od[1], od[2], od[3]);
-      float4* pb = reinterpret_cast<float4*>(p.bary + o * 3) + 3 * (k0 / 4);
-      pb[0] = make_float4(ob0[0], ob1[0], ob2[0], ob0[1]);
-      pb[1] = make_float4(ob1[1], ob2[1], ob0[2], ob1[2]);
-      pb[2] = make_float4(ob2[2], ob0[3], ob1[3], ob2[3]);
-    } else {
-#pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int k = k0 + u;
-        if (k < KMAX && k < K) {
-          const bool e = k >= q.size;
-          p.pix_to_face[o + k] = e ? -1ll : (long long)q.id[k < KMAX ? k : 0];
-          p.zbuf[o + k] = e ? -1.0f : q.z[k < KMAX ? k : 0];
-          p.dists[o + k] = od[u];
-          p.bary[(o + k) * 3 + 0] = ob0[u];
-          p.bary[(o + k) * 3 + 1] = ob1[u];
-          p.bary[(o + k) * 3 + 2] = ob2[u];
-        }
+        const bool e = k0 + u >= q.size;
+        w[u] = e ? make_float4(-1.f, -1.f, -1.f, -1.f) : pay[slot[k0 + u] * TILE_THREADS];
+        zz[u] = e ? -1.0f : q.z[k0 + u];
+      }
+      reinterpret_cast<float4*>(p.zbuf + o)[k0 / 4] = make_float4(zz[0], zz[1], zz[2], zz[3]);
+      reinterpret_cast<float4*>(p.dists + o)[k0 / 4] = make_float4(w[0].x, w[1].x, w[2].x, w[3].x);
+      float4* pb = reinterpret_cast<float4*>(p.bary + o * 3) + 3 * (k0 / 4);
+      pb[0] = make_float4(w[0].y, w[0].z, w[0].w, w[1].y);
+      pb[1] = make_float4(w[1].z, w[1].w, w[2].y, w[2].z);
+      pb[2] = make_float4(w[2].w, w[3].y, w[3].z, w[3].w);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < K) {
+        const bool e = k >= q.size;
+        const float4 w = e ? make_float4(-1.f, -1.f, -1.f, -1.f) : pay[slot[k] * TILE_THREADS];
+        p.pix_to_face[o + k] = e ? -1ll : (long long)q.id[k];
+        p.zbuf[o + k] = e ? -1.0f : q.z[k];
+        p.dists[o + k] = w.x;
+        p.bary[(o + k) * 3 + 0] = w.y;
+        p.bary[(o + k) * 3 + 1] = w.z;
+        p.bary[(o + k) * 3 + 2] = w.w;
       }
     }
   }
