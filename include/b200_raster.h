@@ -121,6 +121,32 @@ int b200r_rasterize_points_backward(const float* points, int64_t P, const int32_
                                     const float* grad_dists, int32_t N, int32_t H, int32_t W, int32_t K,
                                     float* grad_points, void* stream);
 
+/* ------------------------------------------------------------------ compositing ------------- */
+
+/*
+ * Replaces pytorch3d._C.accum_alphacomposite
+ *   (alphaCompositeForward, pytorch3d/csrc/compositing/alpha_composite.h:59-82;
+ *    call site pytorch3d/renderer/compositing.py:47-49).
+ *  features float32 (C,P) contiguous; alphas float32 and points_idx int64, logical shape (N,K,H,W), addressed
+ *  through the four ELEMENT strides given (the renderer passes permuted views of (N,H,W,K) tensors);
+ *  result float32 (N,C,H,W) contiguous, fully written.
+ */
+int b200r_alpha_composite_forward(const float* features, int64_t C, int64_t P, const float* alphas,
+                                  const int64_t* alpha_strides, const int64_t* points_idx,
+                                  const int64_t* idx_strides, int32_t N, int32_t K, int32_t H, int32_t W,
+                                  float* result, void* stream);
+
+/*
+ * Replaces pytorch3d._C.accum_alphacomposite_backward
+ *   (alphaCompositeBackward, alpha_composite.h:84-116; call site compositing.py:58-60).
+ *  grad_out (N,C,H,W) contiguous; grad_features (C,P) is zeroed and accumulated; grad_alphas (N,K,H,W)
+ *  contiguous, fully written.
+ */
+int b200r_alpha_composite_backward(const float* grad_out, const float* features, int64_t C, int64_t P,
+                                   const float* alphas, const int64_t* alpha_strides, const int64_t* points_idx,
+                                   const int64_t* idx_strides, int32_t N, int32_t K, int32_t H, int32_t W,
+                                   float* grad_features, float* grad_alphas, void* stream);
+
 /* ------------------------------------------------------------------ host-buffer entry points - */
 
 /*

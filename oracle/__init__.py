@@ -132,6 +132,31 @@ def rasterize_points_backward(points, idxs, grad_zbuf, grad_dists, arith=ARITH_C
     return out
 
 
+def alpha_composite(features, alphas, points_idx, arith=ARITH_CPU):
+    """features (C,P), alphas / points_idx (N,K,H,W) -> (N,C,H,W)."""
+    f, a = _f32(features), _f32(alphas)
+    idx = _i64(points_idx)
+    C, P = f.shape
+    N, K, H, W = idx.shape
+    out = np.zeros((N, C, H, W), np.float32)
+    lib().oracle_alpha_composite_forward(_p(f, ctypes.c_float), ctypes.c_int64(C), ctypes.c_int64(P),
+                                         _p(a, ctypes.c_float), _p(idx, ctypes.c_int64), N, K, H, W, int(arith),
+                                         _p(out, ctypes.c_float))
+    return out
+
+
+def alpha_composite_backward(grad_out, features, alphas, points_idx):
+    g, f, a = _f32(grad_out), _f32(features), _f32(alphas)
+    idx = _i64(points_idx)
+    C, P = f.shape
+    N, K, H, W = idx.shape
+    gf, ga = np.zeros_like(f), np.zeros_like(a)
+    lib().oracle_alpha_composite_backward(_p(g, ctypes.c_float), _p(f, ctypes.c_float), ctypes.c_int64(C),
+                                          ctypes.c_int64(P), _p(a, ctypes.c_float), _p(idx, ctypes.c_int64), N, K, H,
+                                          W, _p(gf, ctypes.c_float), _p(ga, ctypes.c_float))
+    return gf, ga
+
+
 def load_reference(cuda=False):
     """Import the UNMODIFIED reference ops built by oracle/build_ref.py (None if absent)."""
     import importlib.util

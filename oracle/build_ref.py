@@ -3,6 +3,7 @@
 Compiles, from the sources where they lie under /root/reference (never copied):
   pytorch3d/csrc/rasterize_meshes/rasterize_meshes_cpu.cpp
   pytorch3d/csrc/rasterize_points/rasterize_points_cpu.cpp
+  pytorch3d/csrc/compositing/alpha_composite_cpu.cpp  (+ alpha_composite.cu)
   pytorch3d/csrc/rasterize_meshes/rasterize_meshes.cu      (sm_100a)
   pytorch3d/csrc/rasterize_coarse/rasterize_coarse.cu      (sm_100a)
   pytorch3d/csrc/rasterize_points/rasterize_points.cu      (sm_100a)
@@ -33,11 +34,13 @@ CSRC = os.path.join(REF, "pytorch3d", "csrc")
 CPU_SOURCES = [
     os.path.join(CSRC, "rasterize_meshes", "rasterize_meshes_cpu.cpp"),
     os.path.join(CSRC, "rasterize_points", "rasterize_points_cpu.cpp"),
+    os.path.join(CSRC, "compositing", "alpha_composite_cpu.cpp"),
 ]
 CUDA_SOURCES = [
     os.path.join(CSRC, "rasterize_meshes", "rasterize_meshes.cu"),
     os.path.join(CSRC, "rasterize_coarse", "rasterize_coarse.cu"),
     os.path.join(CSRC, "rasterize_points", "rasterize_points.cu"),
+    os.path.join(CSRC, "compositing", "alpha_composite.cu"),
 ]
 SHIM = os.path.join(HERE, "ref_shim.cpp")
 

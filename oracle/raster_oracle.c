@@ -724,3 +724,57 @@ int oracle_rasterize_points_backward(const float* points, int64_t P, const int32
     }
   return 0;
 }
+
+/* ------------------------------------------------------------------ alpha compositing */
+/* Restates pytorch3d/csrc/compositing/alpha_composite_cpu.cpp:17-60 (forward) and :62-130 (backward), and the
+ * CUDA kernels' product order (alpha_composite.cu:63-64: features * cum_alpha * alpha; CPU: cum_alpha * alpha *
+ * features).  Layouts: features (C,P), alphas / points_idx (N,K,H,W) contiguous, result (N,C,H,W). */
+int oracle_alpha_composite_forward(const float* features, int64_t C, int64_t P, const float* alphas,
+                                   const int64_t* points_idx, int N, int K, int H, int W, int arith, float* result) {
+  const int64_t plane = (int64_t)H * W;
+  for (int b = 0; b < N; ++b)
+    for (int64_t c = 0; c < C; ++c)
+      for (int64_t px = 0; px < plane; ++px) {
+        float cum = 1.0f, acc = 0.0f;
+        for (int k = 0; k < K; ++k) {
+          const int64_t id = points_idx[((int64_t)b * K + k) * plane + px];
+          if (id < 0) continue;
+          const float a = alphas[((int64_t)b * K + k) * plane + px];
+          const float f = features[c * P + id];
+          const float term = (arith == ARITH_CUDA) ? (f * cum) * a : (cum * a) * f;
+          acc += term;
+          cum = cum * (1 - a);
+        }
+        result[((int64_t)b * C + c) * plane + px] = acc;
+      }
+  return 0;
+}
+
+int oracle_alpha_composite_backward(const float* grad_out, const float* features, int64_t C, int64_t P,
+                                    const float* alphas, const int64_t* points_idx, int N, int K, int H, int W,
+                                    float* grad_features, float* grad_alphas) {
+  const int64_t plane = (int64_t)H * W;
+  const float eps = 1e-9f;
+  memset(grad_features, 0, sizeof(float) * (size_t)(C * P));
+  memset(grad_alphas, 0, sizeof(float) * (size_t)N * K * plane);
+  for (int b = 0; b < N; ++b)
+    for (int64_t c = 0; c < C; ++c)
+      for (int64_t px = 0; px < plane; ++px) {
+        const float g = grad_out[((int64_t)b * C + c) * plane + px];
+        float cum = 1.0f;
+        for (int k = 0; k < K; ++k) {
+          const int64_t id = points_idx[((int64_t)b * K + k) * plane + px];
+          if (id < 0) continue;
+          const float a = alphas[((int64_t)b * K + k) * plane + px];
+          grad_alphas[((int64_t)b * K + k) * plane + px] += g * features[c * P + id] * cum;
+          grad_features[c * P + id] += g * cum * a;
+          for (int t = 0; t < k; ++t) {
+            if (points_idx[((int64_t)b * K + t) * plane + px] < 0) continue;
+            const float at = alphas[((int64_t)b * K + t) * plane + px];
+            grad_alphas[((int64_t)b * K + t) * plane + px] -= g * features[c * P + id] * cum * a / (1 - at + eps);
+          }
+          cum = cum * (1 - a);
+        }
+      }
+  return 0;
+}

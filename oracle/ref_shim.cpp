@@ -15,6 +15,7 @@
 #include <torch/extension.h>
 #include "rasterize_meshes/rasterize_meshes.h"
 #include "rasterize_points/rasterize_points.h"
+#include "compositing/alpha_composite.h"  // alphaCompositeForward :59, alphaCompositeBackward :84 (ext.cpp:75-76)
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rasterize_meshes", &RasterizeMeshes);
@@ -26,6 +27,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("_rasterize_meshes_fine", &RasterizeMeshesFine);
   m.def("_rasterize_points_coarse", &RasterizePointsCoarse);
   m.def("_rasterize_points_naive", &RasterizePointsNaive);
+  m.def("accum_alphacomposite", &alphaCompositeForward);
+  m.def("accum_alphacomposite_backward", &alphaCompositeBackward);
 #ifdef WITH_CUDA
   m.attr("with_cuda") = true;
 #else

@@ -213,3 +213,55 @@ def rasterize_points_backward(points: torch.Tensor, idxs: torch.Tensor, grad_zbu
         _lib.check(lib.b200r_rasterize_points_backward(
             _ptr(pts), P, _ptr(idx), _ptr(gz), _ptr(gd), N, H, W, K, _ptr(grad_points), _stream_ptr(dev)))
     return grad_points
+
+
+def _strides4(t):
+    import ctypes
+    return (ctypes.c_int64 * 4)(*[int(v) for v in t.stride()])
+
+
+def accum_alphacomposite(features: torch.Tensor, alphas: torch.Tensor, points_idx: torch.Tensor):
+    """pytorch3d._C.accum_alphacomposite (alphaCompositeForward, csrc/compositing/alpha_composite.h:59-82).
+
+    features (C,P) f32, alphas (N,K,H,W) f32, points_idx (N,K,H,W) i64 (any strides) -> (N,C,H,W) f32."""
+    dev = _require_cuda(("features", features), ("alphas", alphas), ("points_idx", points_idx))
+    if features.dtype != torch.float32 or alphas.dtype != torch.float32:
+        raise RuntimeError("expected scalar type Float")
+    if points_idx.dtype != torch.int64:
+        raise RuntimeError("expected scalar type Long but found %s" % points_idx.dtype)
+    if features.dim() != 2 or alphas.dim() != 4 or points_idx.dim() != 4 or alphas.shape != points_idx.shape:
+        raise RuntimeError("features must be (C, P); alphas and points_idx must both be (N, K, H, W)")
+    lib = _lib.load()
+    C, P = (int(v) for v in features.shape)
+    N, K, H, W = (int(v) for v in points_idx.shape)
+    feat = features.contiguous()
+    with torch.cuda.device(dev):
+        result = torch.empty((N, C, H, W), dtype=torch.float32, device=dev)
+        if result.numel() == 0:
+            return result
+        if K == 0:
+            return result.zero_()
+        _lib.check(lib.b200r_alpha_composite_forward(
+            _ptr(feat), C, P, alphas.data_ptr(), _strides4(alphas), points_idx.data_ptr(), _strides4(points_idx),
+            N, K, H, W, _ptr(result), _stream_ptr(dev)))
+    return result
+
+
+def accum_alphacomposite_backward(grad_outputs: torch.Tensor, features: torch.Tensor, alphas: torch.Tensor,
+                                  points_idx: torch.Tensor):
+    """pytorch3d._C.accum_alphacomposite_backward (alpha_composite.h:84-116) -> (grad_features, grad_alphas)."""
+    dev = _require_cuda(("grad_outputs", grad_outputs), ("features", features), ("alphas", alphas),
+                        ("points_idx", points_idx))
+    lib = _lib.load()
+    C, P = (int(v) for v in features.shape)
+    N, K, H, W = (int(v) for v in points_idx.shape)
+    feat, go = features.contiguous(), grad_outputs.contiguous()
+    with torch.cuda.device(dev):
+        grad_features = torch.empty((C, P), dtype=torch.float32, device=dev)
+        grad_alphas = torch.empty((N, K, H, W), dtype=torch.float32, device=dev)
+        if C * P == 0 or grad_alphas.numel() == 0:
+            return grad_features.zero_(), grad_alphas.zero_()
+        _lib.check(lib.b200r_alpha_composite_backward(
+            _ptr(go), _ptr(feat), C, P, alphas.data_ptr(), _strides4(alphas), points_idx.data_ptr(),
+            _strides4(points_idx), N, K, H, W, _ptr(grad_features), _ptr(grad_alphas), _stream_ptr(dev)))
+    return grad_features, grad_alphas

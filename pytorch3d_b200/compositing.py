@@ -1,0 +1,65 @@
+"""Alpha compositing of point features, same API as the reference:
+pytorch3d/renderer/compositing.py:19-96 (`alpha_composite`) and points/compositor.py:22-66 (`AlphaCompositor`).
+"""
+import torch
+import torch.nn as nn
+
+from . import _C
+
+
+class _CompositeAlphaPoints(torch.autograd.Function):
+    """weighted_fs[b,c,i,j] = sum_k cum_alpha_k * features[c, pointsidx[b,k,i,j]],
+    cum_alpha_k = alphas[b,k,i,j] * prod_{l<k} (1 - alphas[b,l,i,j])   (compositing.py:19-63 of the reference)."""
+
+    @staticmethod
+    def forward(ctx, features, alphas, points_idx):
+        pt_cld = _C.accum_alphacomposite(features, alphas, points_idx)
+        ctx.save_for_backward(features.clone(), alphas.clone(), points_idx.clone())
+        return pt_cld
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        features, alphas, points_idx = ctx.saved_tensors
+        grad_features, grad_alphas = _C.accum_alphacomposite_backward(grad_output, features, alphas, points_idx)
+        return grad_features, grad_alphas, None
+
+
+def alpha_composite(pointsidx, alphas, pt_clds) -> torch.Tensor:
+    """pointsidx (N,K,H,W) int64, alphas (N,K,H,W) in [0,1], pt_clds (C,P) packed features -> (N,C,H,W)."""
+    return _CompositeAlphaPoints.apply(pt_clds, alphas, pointsidx)
+
+
+class AlphaCompositor(nn.Module):
+    """Accumulate points using alpha compositing (points/compositor.py:22-66 of the reference)."""
+
+    def __init__(self, background_color=None) -> None:
+        super().__init__()
+        self.background_color = background_color
+
+    def forward(self, fragments, alphas, ptclds, **kwargs) -> torch.Tensor:
+        background_color = kwargs.get("background_color", self.background_color)
+        images = alpha_composite(fragments, alphas, ptclds)
+        if background_color is not None:
+            images = _add_background_color_to_images(fragments, images, background_color)
+        return images
+
+
+def _add_background_color_to_images(pix_idxs, images, background_color):
+    """Pixels that no point covers take the background colour (points/compositor.py:119-160 of the reference)."""
+    background_mask = pix_idxs[:, 0] < 0  # (N, H, W)
+    if not torch.is_tensor(background_color):
+        background_color = images.new_tensor(background_color)
+    background_color = background_color.to(images)
+    if background_color.ndim == 0:
+        background_color = background_color.expand(images.shape[1])
+    if background_color.ndim > 1:
+        raise ValueError("Wrong shape of background_color")
+    if background_color.shape[0] + 1 == images.shape[1]:
+        alpha = images.new_ones(1)
+        background_color = torch.cat([background_color, alpha])
+    elif background_color.shape[0] != images.shape[1]:
+        raise ValueError("Background color has %s channels not %s" % (background_color.shape[0], images.shape[1]))
+    num_background_pixels = background_mask.sum()
+    masked_images = images.permute(0, 2, 3, 1).masked_scatter(
+        background_mask[..., None], background_color[None, :].expand(num_background_pixels, -1))
+    return masked_images.permute(0, 3, 1, 2)

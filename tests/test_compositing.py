@@ -1,0 +1,107 @@
+"""Alpha compositing: oracle pinned to the reference CPU op; CUDA path against oracle/reference."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+
+def scene(N, K, H, W, C, P, seed, frac_empty=0.3):
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.rand(C, P, generator=g)
+    alphas = torch.rand(N, K, H, W, generator=g)
+    idx = torch.randint(0, P, (N, K, H, W), generator=g)
+    # z-buffer style padding: once a slot is empty all later slots of that pixel are empty too
+    n_valid = (torch.rand(N, 1, H, W, generator=g) * (K + 1) * (1 + frac_empty)).long().clamp(max=K)
+    empty = torch.arange(K).view(1, K, 1, 1) >= n_valid
+    idx[empty] = -1
+    return feats, alphas, idx
+
+
+@pytest.fixture(scope="module")
+def ref_cpu():
+    m = oracle.load_reference(cuda=False)
+    if m is None or not hasattr(m, "accum_alphacomposite"):
+        pytest.skip("reference CPU build without compositing not present")
+    return m
+
+
+@pytest.mark.parametrize("N,K,H,W,C,P", [(2, 5, 9, 11, 3, 40), (1, 1, 4, 4, 1, 5), (1, 10, 16, 8, 4, 100)])
+def test_oracle_equals_reference_cpu(ref_cpu, N, K, H, W, C, P):
+    feats, alphas, idx = scene(N, K, H, W, C, P, seed=K)
+    want = ref_cpu.accum_alphacomposite(feats, alphas, idx)
+    got = oracle.alpha_composite(feats.numpy(), alphas.numpy(), idx.numpy(), arith=oracle.ARITH_CPU)
+    assert np.array_equal(got, want.numpy())
+    go = torch.rand(want.shape, generator=torch.Generator().manual_seed(1))
+    rf, ra = ref_cpu.accum_alphacomposite_backward(go, feats, alphas, idx)
+    of, oa = oracle.alpha_composite_backward(go.numpy(), feats.numpy(), alphas.numpy(), idx.numpy())
+    assert np.array_equal(of, rf.numpy()) and np.array_equal(oa, ra.numpy())
+
+
+def test_oracle_closed_form():
+    """Single pixel, two points: result = a0 f0 + (1-a0) a1 f1; an empty first slot is skipped."""
+    feats = torch.tensor([[2.0, 3.0]])
+    alphas = torch.tensor([0.25, 0.5]).view(1, 2, 1, 1)
+    idx = torch.tensor([0, 1]).view(1, 2, 1, 1)
+    out = oracle.alpha_composite(feats.numpy(), alphas.numpy(), idx.numpy())
+    assert out.item() == pytest.approx(0.25 * 2 + 0.75 * 0.5 * 3)
+    idx2 = torch.tensor([-1, 1]).view(1, 2, 1, 1)
+    assert oracle.alpha_composite(feats.numpy(), alphas.numpy(), idx2.numpy()).item() == pytest.approx(0.5 * 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,K,H,W,C,P,permuted", [(2, 5, 9, 11, 3, 40, False), (2, 10, 33, 17, 4, 500, True),
+                                                  (1, 1, 4, 4, 1, 5, False), (3, 8, 20, 20, 8, 300, True)])
+def test_cuda_forward_backward(built_lib, N, K, H, W, C, P, permuted):
+    from pytorch3d_b200 import _C, compositing
+    dev = torch.device("cuda:0")
+    feats, alphas, idx = scene(N, K, H, W, C, P, seed=N + K)
+    fd = feats.to(dev)
+    if permuted:  # the renderer's layout: (N,H,W,K) tensors viewed as (N,K,H,W)
+        ad = alphas.permute(0, 2, 3, 1).contiguous().to(dev).permute(0, 3, 1, 2)
+        idd = idx.permute(0, 2, 3, 1).contiguous().to(dev).permute(0, 3, 1, 2)
+        assert not ad.is_contiguous()
+    else:
+        ad, idd = alphas.to(dev), idx.to(dev)
+    out = _C.accum_alphacomposite(fd, ad, idd)
+    want = oracle.alpha_composite(feats.numpy(), alphas.numpy(), idx.numpy(), arith=oracle.ARITH_CUDA)
+    assert np.array_equal(out.cpu().numpy(), want), "forward must be bit-identical to the CUDA-form oracle"
+    ref = oracle.load_reference(cuda=True)
+    if ref is not None and hasattr(ref, "accum_alphacomposite"):
+        r = ref.accum_alphacomposite(fd, alphas.to(dev), idx.to(dev))
+        assert torch.equal(out, r), "forward must be bit-identical to the reference CUDA kernel"
+    go = torch.rand(out.shape, generator=torch.Generator().manual_seed(1))
+    gf, ga = _C.accum_alphacomposite_backward(go.to(dev), fd, ad, idd)
+    of, oa = oracle.alpha_composite_backward(go.numpy(), feats.numpy(), alphas.numpy(), idx.numpy())
+    np.testing.assert_allclose(gf.cpu().numpy(), of, rtol=1e-4, atol=1e-5)
+    # the reference formula divides by (1 - alpha_t + 1e-9): near alpha = 1 it is ill-conditioned, so compare
+    # where alphas stay away from 1 and require everything finite
+    ok = (alphas < 0.99).all(1, keepdim=True).expand_as(alphas).numpy()
+    np.testing.assert_allclose(ga.cpu().numpy()[ok], oa[ok], rtol=2e-3, atol=1e-4)
+    assert torch.isfinite(ga).all()
+    # autograd wrapper
+    fa = fd.clone().requires_grad_(True)
+    aa = ad.clone().requires_grad_(True)
+    img = compositing.alpha_composite(idd, aa, fa)
+    (img * go.to(dev)).sum().backward()
+    np.testing.assert_allclose(fa.grad.cpu().numpy(), of, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_points_renderer_pipeline(built_lib):
+    """rasterize_points -> weights 1 - d/r^2 -> alpha_composite, as PointsRenderer does (points/renderer.py:56-76)."""
+    import pytorch3d_b200 as p3b
+    from pytorch3d_b200 import compositing, synthetic
+    dev = torch.device("cuda:0")
+    pc = synthetic.random_pointclouds(2, 5000, seed=3, device=dev)
+    r = 0.05
+    idx, zbuf, dists = p3b.rasterize_points(pc, (48, 64), radius=r, points_per_pixel=6)
+    weights = (1 - dists / (r * r)).permute(0, 3, 1, 2)
+    feats = torch.rand(4, pc.points_packed().shape[0], device=dev)
+    img = compositing.AlphaCompositor(background_color=(0.0, 0.0, 0.0))(idx.long().permute(0, 3, 1, 2), weights, feats)
+    want = oracle.alpha_composite(feats.cpu().numpy(), weights.contiguous().cpu().numpy(),
+                                  idx.long().permute(0, 3, 1, 2).contiguous().cpu().numpy(), arith=oracle.ARITH_CUDA)
+    covered = (idx[..., 0] >= 0).cpu().numpy()
+    got = img.cpu().numpy()
+    assert np.array_equal(got.transpose(0, 2, 3, 1)[covered][:, :4], want.transpose(0, 2, 3, 1)[covered])
+    assert (got.transpose(0, 2, 3, 1)[~covered][:, :3] == 0).all()
