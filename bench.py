@@ -395,6 +395,13 @@ def run_ours(args, rank, local_rank, world):
                "sample": "rows [%d,%d) of frame 0 (%d of %d rows, all %d faces), fwd+bwd, %.1f s of CPU work" % (
                    (H - rows) // 2, (H - rows) // 2 + rows, rows, H, F1, dtc)}
 
+    others = None
+    if rank == 0 and world == 1 and not args.skip_others:
+        try:
+            others = other_workloads(dev)
+        except Exception as ex:
+            others = {"error": str(ex)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -402,9 +409,66 @@ def run_ours(args, rank, local_rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(name, world, nm, F1, H, W, K, blur),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline,
-            "cpu_baseline": cpu, "e2e_host_abi": e2e_abi, "impl": "pytorch3d_b200",
+            "cpu_baseline": cpu, "e2e_host_abi": e2e_abi, "other_workloads": others, "impl": "pytorch3d_b200",
         }
         print(json.dumps(line), flush=True)
+
+
+def _time_ms(fn, steps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def other_workloads(dev):
+    """Device-resident fwd+bwd throughput of the other BASELINE configs that fit one GPU (context, not the metric)."""
+    from pytorch3d_b200 import _C, synthetic
+    out = {}
+    # config 2: 8 x ~6k-face meshes, 256^2, K=8, blur 1e-4
+    meshes, (nm, F1, H, W, K, blur) = build_workload("c2", 0)
+    fv = synthetic.face_verts_of(meshes).to(dev)
+    first, num = meshes.mesh_to_faces_packed_first_idx().to(dev), meshes.num_faces_per_mesh().to(dev)
+    nb = torch.full((fv.shape[0],), -1, dtype=torch.int64, device=dev)
+    nb._b200_all_minus_one = True
+    frag = _C.rasterize_meshes(fv, first, num, nb, (H, W), blur, K, 0, 0, False, False, False)
+    gz, gb, gd = torch.randn_like(frag[1]), torch.randn_like(frag[2]), torch.randn_like(frag[3])
+
+    def step_c2():
+        f = _C.rasterize_meshes(fv, first, num, nb, (H, W), blur, K, 0, 0, False, False, False)
+        _C.rasterize_meshes_backward(fv, f[0], gz, gb, gd, False, False)
+
+    ms = _time_ms(step_c2)
+    out["config2_meshes_8x%d_faces_%d2_K%d_blur%g" % (F1, H, K, blur)] = {"ms_per_step": ms, "frames_per_s": nm * 1e3 / ms}
+    # config 3: 8 x 100k points, 512^2, K=10, r=0.01, + alpha_composite (4 channels), fwd+bwd
+    pc = synthetic.random_pointclouds(8, 100000, seed=0)
+    pts = pc.points_packed().to(dev)
+    pf, pn = pc.cloud_to_packed_first_idx().to(dev), pc.num_points_per_cloud().to(dev)
+    r = 0.01
+    rad = torch.full((pts.shape[0],), r, device=dev)
+    feats = torch.rand(4, pts.shape[0], device=dev)
+    idx, zb, d2 = _C.rasterize_points(pts, pf, pn, (512, 512), rad, 10, 0, 0)
+    g_img = torch.randn(8, 4, 512, 512, device=dev)
+    g_z = torch.randn_like(zb)
+
+    def step_c3():
+        i, z, d = _C.rasterize_points(pts, pf, pn, (512, 512), rad, 10, 0, 0)
+        w = (1 - d / (r * r)).permute(0, 3, 1, 2)
+        il = i.long().permute(0, 3, 1, 2)
+        _C.accum_alphacomposite(feats, w, il)
+        gf, ga = _C.accum_alphacomposite_backward(g_img, feats, w, il)
+        g_d = (ga * (-1.0 / (r * r))).permute(0, 2, 3, 1).contiguous()
+        _C.rasterize_points_backward(pts, i, g_z, g_d)
+
+    ms = _time_ms(step_c3)
+    out["config3_points_8x100k_512_K10_r0.01_alpha_composite"] = {"ms_per_step": ms, "frames_per_s": 8e3 / ms}
+    return out
 
 
 def host_abi_e2e(lib, fv_host, meshes, nm, F1, H, W, K, blur, steps=3):
@@ -454,6 +518,7 @@ def main():
     ap.add_argument("--workload", default="ns", choices=sorted(WORKLOADS))
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-host-abi", action="store_true")
+    ap.add_argument("--skip-others", action="store_true", help="skip the config-2 / config-3 context numbers")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

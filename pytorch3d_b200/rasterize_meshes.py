@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 from . import _C
+from .clip import ClipFrustum, clip_faces, convert_clipped_rasterization_to_original_faces
 
 # kMaxItemsPerBin (rasterization_utils.cuh:50); mirrored by rasterize_meshes.py:24-27 of the reference
 kMaxFacesPerBin = 22
@@ -60,14 +61,24 @@ def rasterize_meshes(
     im_size = parse_image_size(image_size)
     max_image_size = max(*im_size)
 
+    clipped_faces_neighbor_idx = None
+    clipped_faces = None
     if z_clip_value is not None or cull_to_frustum:
-        # clip.py (frustum culling / z-clipping) is the next row of the scope table
-        raise NotImplementedError(
-            "z_clip_value / cull_to_frustum (pytorch3d/renderer/mesh/clip.py) are not part of this build yet")
+        # Cull faces outside the view frustum and clip faces that are partially behind the camera to
+        # z >= z_clip_value; this may change the number of faces (rasterize_meshes.py:160-183 of the reference)
+        frustum = ClipFrustum(left=-1, right=1, top=-1, bottom=1, perspective_correct=perspective_correct,
+                              z_clip_value=z_clip_value, cull=cull_to_frustum)
+        clipped_faces = clip_faces(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, frustum=frustum)
+        face_verts = clipped_faces.face_verts
+        mesh_to_face_first_idx = clipped_faces.mesh_to_face_first_idx
+        num_faces_per_mesh = clipped_faces.num_faces_per_mesh
+        # the two halves of a face that was clipped to a quad name each other: only one may enter the top K
+        clipped_faces_neighbor_idx = clipped_faces.clipped_faces_neighbor_idx
 
-    clipped_faces_neighbor_idx = torch.full(
-        size=(face_verts.shape[0],), fill_value=-1, device=face_verts.device, dtype=torch.int64)
-    clipped_faces_neighbor_idx._b200_all_minus_one = True  # lets the op skip its device-side check
+    if clipped_faces_neighbor_idx is None:
+        clipped_faces_neighbor_idx = torch.full(
+            size=(face_verts.shape[0],), fill_value=-1, device=face_verts.device, dtype=torch.int64)
+        clipped_faces_neighbor_idx._b200_all_minus_one = True  # selects the kernel variant without that logic
 
     if bin_size is None:
         if max_image_size <= 64:
@@ -83,9 +94,16 @@ def rasterize_meshes(
     if max_faces_per_bin is None:
         max_faces_per_bin = int(max(10000, getattr(meshes, "_F", 0) / 5))
 
-    return _RasterizeFaceVerts.apply(
+    pix_to_face, zbuf, barycentric_coords, dists = _RasterizeFaceVerts.apply(
         face_verts, mesh_to_face_first_idx, num_faces_per_mesh, clipped_faces_neighbor_idx, im_size, blur_radius,
         faces_per_pixel, bin_size, max_faces_per_bin, perspective_correct, clip_barycentric_coords, cull_backfaces)
+
+    if clipped_faces is not None:
+        # express face indices and barycentrics in terms of the original, unclipped faces
+        # (rasterize_meshes.py:239-249 of the reference)
+        pix_to_face, barycentric_coords = convert_clipped_rasterization_to_original_faces(
+            pix_to_face, barycentric_coords, clipped_faces)
+    return pix_to_face, zbuf, barycentric_coords, dists
 
 
 class _RasterizeFaceVerts(torch.autograd.Function):

@@ -167,10 +167,55 @@ def random_scenes():
         store[k + "/grad_zbuf"], store[k + "/grad_dists"], store[k + "/grad_points"] = _np(gz), _np(gd), _np(grad)
 
 
+def clip_scenes():
+    """clip_faces (renderer/mesh/clip.py:324-615) and the end-to-end rasterize_meshes(z_clip_value, cull_to_frustum)
+    of the reference's C++ CPU path, on seeded scenes with faces crossing the clipping plane."""
+    from pytorch3d.renderer.mesh import clip as rclip
+    from pytorch3d.structures import Meshes
+
+    def scene(F, seed):
+        g = torch.Generator().manual_seed(seed)
+        c = torch.rand(F, 1, 3, generator=g) * 2.4 - 1.2
+        v = c + (torch.rand(F, 3, 3, generator=g) - 0.5) * 0.9
+        v[..., 2] = torch.rand(F, 3, generator=g) * 3 - 0.8
+        return v
+
+    ci = 0
+    for persp in (False, True):
+        for cull in (False, True):
+            for zc in (None, 0.3):
+                if zc is None and not cull:
+                    continue
+                fv = scene(300, 40 + ci)
+                first, num = torch.tensor([0, 120, 120]), torch.tensor([120, 0, 180])
+                fr = rclip.ClipFrustum(left=-1, right=1, top=-1, bottom=1, perspective_correct=persp,
+                                       z_clip_value=zc, cull=cull)
+                r = rclip.clip_faces(fv, first, num, fr)
+                k = "clip/faces_%02d" % ci
+                store[k + "/face_verts"], store[k + "/first"], store[k + "/num"] = _np(fv), _np(first), _np(num)
+                store[k + "/args"] = np.array([int(persp), int(cull), -1 if zc is None else 1], np.int64)
+                store[k + "/z_clip"] = np.array([0.0 if zc is None else zc], np.float64)
+                store[k + "/out_face_verts"] = _np(r.face_verts)
+                store[k + "/out_first"], store[k + "/out_num"] = _np(r.mesh_to_face_first_idx), _np(r.num_faces_per_mesh)
+                store[k + "/out_c2u"] = _np(r.faces_clipped_to_unclipped_idx)
+                if r.clipped_faces_neighbor_idx is not None:
+                    store[k + "/out_neighbor"] = _np(r.clipped_faces_neighbor_idx)
+                # end to end through the reference wrapper (verts == face corners, faces = arange)
+                verts = [fv[:120].reshape(-1, 3), torch.zeros(0, 3), fv[120:].reshape(-1, 3)]
+                faces = [torch.arange(360).reshape(-1, 3), torch.zeros(0, 3, dtype=torch.int64),
+                         torch.arange(540).reshape(-1, 3)]
+                meshes = Meshes(verts=verts, faces=faces)
+                out = rasterize_meshes(meshes, (24, 32), 1e-3, 4, 0, None, persp, False, False, zc, cull)
+                for name, t in zip(("pix_to_face", "zbuf", "bary", "dists"), out):
+                    store[k + "/e2e_" + name] = _np(t)
+                ci += 1
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     reference_scenes()
     random_scenes()
+    clip_scenes()
     path = os.path.join(OUT, "raster_golden.npz")
     np.savez_compressed(path, **store)
     cases = sorted({k.rsplit("/", 1)[0] for k in store})
