@@ -389,7 +389,7 @@ def run_ours(args, rank, local_rank, world):
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         ref, kind, cores = load_cpu_reference()
-        rows = pick_strip_rows(fv_host, F1, H, W, K, blur, ref, budget_s=15.0, steps=1)
+        rows = pick_strip_rows(fv_host, F1, H, W, K, blur, ref, budget_s=40.0, steps=1)
         dtc, fr = cpu_sample(fv_host, F1, H, W, K, blur, rows, ref)
         cpu = {"value": fr / dtc, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": "rows [%d,%d) of frame 0 (%d of %d rows, all %d faces), fwd+bwd, %.1f s of CPU work" % (
