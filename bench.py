@@ -395,6 +395,35 @@ def run_ours(args, rank, local_rank, world):
                "sample": "rows [%d,%d) of frame 0 (%d of %d rows, all %d faces), fwd+bwd, %.1f s of CPU work" % (
                    (H - rows) // 2, (H - rows) // 2 + rows, rows, H, F1, dtc)}
 
+    # ---------------- optional: all-gather of the rendered frames over NCCL (the only collective the path has)
+    gather = None
+    if world > 1:
+        p2f, zb, ba, di = fwd()
+        tensors = [p2f, zb, ba, di]
+        bufs = [t.new_empty((world,) + tuple(t.shape)) for t in tensors]
+        def gather_step():
+            f = fwd()
+            for t, b in zip(f, bufs):
+                dist.all_gather_into_tensor(b, t)
+            return _C.rasterize_meshes_backward(fv, f[0], gz, gb, gd, False, False)
+        for _ in range(3):
+            gather_step()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_g = max(3, min(args.steps, 20))
+        g0.record()
+        for _ in range(n_g):
+            gather_step()
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        bytes_per_rank = sum(t.numel() * t.element_size() for t in tensors)
+        gather = {"value": world * nm * n_g / (float(tg.item()) * 1e-3), "unit": UNIT, "steps": n_g,
+                  "bytes_gathered_per_rank_per_step": int(bytes_per_rank * world),
+                  "what": "same step with every rank all-gathering all four Fragments tensors of all ranks "
+                          "(all_gather_into_tensor, NCCL) between forward and backward"}
+
     others = None
     if rank == 0 and world == 1 and not args.skip_others:
         try:
@@ -409,7 +438,8 @@ def run_ours(args, rank, local_rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(name, world, nm, F1, H, W, K, blur),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline,
-            "cpu_baseline": cpu, "e2e_host_abi": e2e_abi, "other_workloads": others, "impl": "pytorch3d_b200",
+            "cpu_baseline": cpu, "e2e_host_abi": e2e_abi, "other_workloads": others, "with_frame_gather": gather,
+            "impl": "pytorch3d_b200",
         }
         print(json.dumps(line), flush=True)
 
