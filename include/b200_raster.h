@@ -147,6 +147,28 @@ int b200r_alpha_composite_backward(const float* grad_out, const float* features,
                                    const int64_t* idx_strides, int32_t N, int32_t K, int32_t H, int32_t W,
                                    float* grad_features, float* grad_alphas, void* stream);
 
+/* ------------------------------------------------------------------ face attribute interpolation */
+
+/*
+ * Replaces pytorch3d._C.interp_face_attrs_forward
+ *   (InterpFaceAttrsForward, pytorch3d/csrc/interp_face_attrs/interp_face_attrs.h:45-66;
+ *    call site pytorch3d/ops/interp_face_attrs.py:66).
+ *  pix_to_face int64 (P,); barycentric_coords float32 (P,3); face_attrs float32 (F,3,D); pix_attrs float32 (P,D),
+ *  fully written (0 where pix_to_face < 0).
+ */
+int b200r_interp_face_attrs_forward(const int64_t* pix_to_face, const float* barycentric_coords,
+                                    const float* face_attrs, int64_t P, int64_t F, int64_t D, float* pix_attrs,
+                                    void* stream);
+
+/*
+ * Replaces pytorch3d._C.interp_face_attrs_backward
+ *   (InterpFaceAttrsBackward, interp_face_attrs.h:88-118; call site interp_face_attrs.py:74).
+ *  grad_barycentric_coords (P,3) fully written; grad_face_attrs (F,3,D) zeroed and accumulated.
+ */
+int b200r_interp_face_attrs_backward(const int64_t* pix_to_face, const float* barycentric_coords,
+                                     const float* face_attrs, const float* grad_pix_attrs, int64_t P, int64_t F,
+                                     int64_t D, float* grad_barycentric_coords, float* grad_face_attrs, void* stream);
+
 /* ------------------------------------------------------------------ host-buffer entry points - */
 
 /*

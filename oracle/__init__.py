@@ -157,6 +157,26 @@ def alpha_composite_backward(grad_out, features, alphas, points_idx):
     return gf, ga
 
 
+def interp_face_attrs(pix_to_face, bary, attrs, arith=ARITH_CPU):
+    """pix_to_face (P,), bary (P,3), attrs (F,3,D) -> (P,D)."""
+    p2f, b, a = _i64(pix_to_face).reshape(-1), _f32(bary).reshape(-1, 3), _f32(attrs)
+    P, D = p2f.shape[0], a.shape[2]
+    out = np.zeros((P, D), np.float32)
+    lib().oracle_interp_face_attrs_forward(_p(p2f, ctypes.c_int64), _p(b, ctypes.c_float), _p(a, ctypes.c_float),
+                                           ctypes.c_int64(P), ctypes.c_int64(D), int(arith), _p(out, ctypes.c_float))
+    return out
+
+
+def interp_face_attrs_backward(pix_to_face, bary, attrs, grad_out):
+    p2f, b, a, g = _i64(pix_to_face).reshape(-1), _f32(bary).reshape(-1, 3), _f32(attrs), _f32(grad_out)
+    P, (F, _, D) = p2f.shape[0], a.shape
+    gb, ga = np.zeros((P, 3), np.float32), np.zeros_like(a)
+    lib().oracle_interp_face_attrs_backward(_p(p2f, ctypes.c_int64), _p(b, ctypes.c_float), _p(a, ctypes.c_float),
+                                            _p(g, ctypes.c_float), ctypes.c_int64(P), ctypes.c_int64(F),
+                                            ctypes.c_int64(D), _p(gb, ctypes.c_float), _p(ga, ctypes.c_float))
+    return gb, ga
+
+
 def load_reference(cuda=False):
     """Import the UNMODIFIED reference ops built by oracle/build_ref.py (None if absent)."""
     import importlib.util

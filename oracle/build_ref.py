@@ -41,6 +41,7 @@ CUDA_SOURCES = [
     os.path.join(CSRC, "rasterize_coarse", "rasterize_coarse.cu"),
     os.path.join(CSRC, "rasterize_points", "rasterize_points.cu"),
     os.path.join(CSRC, "compositing", "alpha_composite.cu"),
+    os.path.join(CSRC, "interp_face_attrs", "interp_face_attrs.cu"),
 ]
 SHIM = os.path.join(HERE, "ref_shim.cpp")
 

@@ -778,3 +778,46 @@ int oracle_alpha_composite_backward(const float* grad_out, const float* features
       }
   return 0;
 }
+
+/* ------------------------------------------------------------------ face attribute interpolation */
+/* Restates InterpFaceAttrsForwardKernel / BackwardKernel (pytorch3d/csrc/interp_face_attrs/interp_face_attrs.cu:15-49,
+ * 86-124) and the CPU path interpolate_face_attributes_python (pytorch3d/ops/interp_face_attrs.py:83-102).
+ * ARITH_CUDA: fma(w2,a2, fma(w1,a1, fma(w0,a0,0))) as compiled; ARITH_CPU: (w0*a0 + w1*a1) + w2*a2. */
+int oracle_interp_face_attrs_forward(const int64_t* pix_to_face, const float* bary, const float* attrs, int64_t P,
+                                     int64_t D, int arith, float* out) {
+  for (int64_t p = 0; p < P; ++p) {
+    const int64_t f = pix_to_face[p];
+    for (int64_t d = 0; d < D; ++d) {
+      float v = 0.0f;
+      if (f >= 0) {
+        const float* a = attrs + f * 3 * D + d;
+        const float w0 = bary[p * 3], w1 = bary[p * 3 + 1], w2 = bary[p * 3 + 2];
+        if (arith == ARITH_CUDA)
+          v = fmaf(w2, a[2 * D], fmaf(w1, a[D], fmaf(w0, a[0], 0.0f)));
+        else
+          v = (w0 * a[0] + w1 * a[D]) + w2 * a[2 * D];
+      }
+      out[p * D + d] = v;
+    }
+  }
+  return 0;
+}
+
+int oracle_interp_face_attrs_backward(const int64_t* pix_to_face, const float* bary, const float* attrs,
+                                      const float* grad_out, int64_t P, int64_t F, int64_t D, float* grad_bary,
+                                      float* grad_attrs) {
+  memset(grad_bary, 0, sizeof(float) * 3 * (size_t)P);
+  memset(grad_attrs, 0, sizeof(float) * 3 * (size_t)(F * D));
+  for (int64_t p = 0; p < P; ++p) {
+    const int64_t f = pix_to_face[p];
+    if (f < 0) continue;
+    for (int64_t d = 0; d < D; ++d) {
+      const float u = grad_out[p * D + d];
+      for (int i = 0; i < 3; ++i) {
+        grad_bary[p * 3 + i] += attrs[f * 3 * D + i * D + d] * u;
+        grad_attrs[f * 3 * D + i * D + d] += bary[p * 3 + i] * u;
+      }
+    }
+  }
+  return 0;
+}

@@ -15,6 +15,7 @@
 #include <torch/extension.h>
 #include "rasterize_meshes/rasterize_meshes.h"
 #include "rasterize_points/rasterize_points.h"
+#include "interp_face_attrs/interp_face_attrs.h"  // CUDA only in the reference (ext.cpp:49-50)
 #include "compositing/alpha_composite.h"  // alphaCompositeForward :59, alphaCompositeBackward :84 (ext.cpp:75-76)
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -30,6 +31,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("accum_alphacomposite", &alphaCompositeForward);
   m.def("accum_alphacomposite_backward", &alphaCompositeBackward);
 #ifdef WITH_CUDA
+  m.def("interp_face_attrs_forward", &InterpFaceAttrsForward);
+  m.def("interp_face_attrs_backward", &InterpFaceAttrsBackward);
   m.attr("with_cuda") = true;
 #else
   m.attr("with_cuda") = false;

@@ -265,3 +265,43 @@ def accum_alphacomposite_backward(grad_outputs: torch.Tensor, features: torch.Te
             _ptr(go), _ptr(feat), C, P, alphas.data_ptr(), _strides4(alphas), points_idx.data_ptr(),
             _strides4(points_idx), N, K, H, W, _ptr(grad_features), _ptr(grad_alphas), _stream_ptr(dev)))
     return grad_features, grad_alphas
+
+
+def interp_face_attrs_forward(pix_to_face: torch.Tensor, barycentric_coords: torch.Tensor, face_attrs: torch.Tensor):
+    """pytorch3d._C.interp_face_attrs_forward (csrc/interp_face_attrs/interp_face_attrs.h:45-66):
+    pix_to_face (P,) i64, barycentric_coords (P,3) f32, face_attrs (F,3,D) f32 -> (P,D) f32."""
+    dev = _require_cuda(("pix_to_face", pix_to_face), ("barycentric_coords", barycentric_coords),
+                        ("face_attributes", face_attrs))
+    if barycentric_coords.dtype != torch.float32 or face_attrs.dtype != torch.float32:
+        raise RuntimeError("expected scalar type Float")
+    if pix_to_face.dtype != torch.int64:
+        raise RuntimeError("expected scalar type Long but found %s" % pix_to_face.dtype)
+    lib = _lib.load()
+    P, (F, _, D) = int(pix_to_face.shape[0]), (int(v) for v in face_attrs.shape)
+    p2f, bary, attrs = pix_to_face.contiguous(), barycentric_coords.contiguous(), face_attrs.contiguous()
+    with torch.cuda.device(dev):
+        out = torch.empty((P, D), dtype=torch.float32, device=dev)
+        if out.numel() == 0:
+            return out
+        _lib.check(lib.b200r_interp_face_attrs_forward(_ptr(p2f), _ptr(bary), _ptr(attrs), P, F, D, _ptr(out),
+                                                       _stream_ptr(dev)))
+    return out
+
+
+def interp_face_attrs_backward(pix_to_face: torch.Tensor, barycentric_coords: torch.Tensor, face_attrs: torch.Tensor,
+                               grad_pix_attrs: torch.Tensor):
+    """pytorch3d._C.interp_face_attrs_backward (interp_face_attrs.h:88-118) -> (grad_bary (P,3), grad_attrs (F,3,D))."""
+    dev = _require_cuda(("pix_to_face", pix_to_face), ("barycentric_coords", barycentric_coords),
+                        ("face_attributes", face_attrs), ("pix_attrs", grad_pix_attrs))
+    lib = _lib.load()
+    P, (F, _, D) = int(pix_to_face.shape[0]), (int(v) for v in face_attrs.shape)
+    p2f, bary, attrs = pix_to_face.contiguous(), barycentric_coords.contiguous(), face_attrs.contiguous()
+    gp = grad_pix_attrs.contiguous()
+    with torch.cuda.device(dev):
+        grad_bary = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        grad_attrs = torch.empty((F, 3, D), dtype=torch.float32, device=dev)
+        if grad_attrs.numel() == 0 or P == 0:
+            return grad_bary.zero_(), grad_attrs.zero_()
+        _lib.check(lib.b200r_interp_face_attrs_backward(_ptr(p2f), _ptr(bary), _ptr(attrs), _ptr(gp), P, F, D,
+                                                        _ptr(grad_bary), _ptr(grad_attrs), _stream_ptr(dev)))
+    return grad_bary, grad_attrs

@@ -283,12 +283,26 @@ __device__ __forceinline__ float warp_max(float v) {
 // lie in a given face's box.
 constexpr int ROUND = 64;
 
+// Candidate slots per pixel and chunk in the scan-conversion path (more -> the chunk falls back to pass A/B).
+constexpr int SCAN_CAP = 16;
+
+// Dynamic shared memory of the fine kernel (54 KB for KMAX = 8: four CTAs per SM).
+template <int KMAX>
+struct FineShared {
+  FaceChunk s;
+  float4 pay[KMAX * TILE_THREADS];            // queue payload: (signed dist, bary0, bary1, bary2) per slot
+  int cand_count[TILE_THREADS];               // scan conversion: candidates recorded for each pixel (thread)
+  unsigned char cand[SCAN_CAP][TILE_THREADS]; // ... their chunk slots
+  float col[TILE], row[TILE];                 // NDC coordinates of the tile's 16 pixel columns / rows
+};
+
 template <int KMAX, bool NB>
 __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FineParams p) {
-  __shared__ FaceChunk s;
-  __shared__ float4 s_pay[KMAX * TILE_THREADS];  // queue payload: (signed dist, bary0, bary1, bary2) per slot
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FineShared<KMAX>& sh = *reinterpret_cast<FineShared<KMAX>*>(smem_raw);
+  FaceChunk& s = sh.s;
   const int tid = threadIdx.x, lane = tid & 31;
-  float4* pay = s_pay + tid;
+  float4* pay = sh.pay + tid;
   const int t = blockIdx.x;
   const int n = t / (p.TY * p.TX);
   const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
@@ -298,6 +312,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
   const bool valid = xo < p.W && yo < p.H;
   const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
   const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
+  {  // coordinate tables of the tile (local column c = xo - 16*tile_x, local row r = yo - 16*tile_y)
+    const int c = xo - tile_x * TILE, r = yo - tile_y * TILE;
+    if (r == 0) sh.col[c] = px;
+    if (c == 0) sh.row[r] = py;
+  }
   // the tile's face list; tiles whose segment did not fit the pair buffer test every face of the mesh
   const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
   const bool overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
@@ -318,6 +337,74 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
       stage_face(s, tid, p.face_verts, p.neighbor, f, p.sqrt_blur, cull);
     }
     __syncthreads();
+    if (!(blur_radius > 0.0f)) {
+      // ---- scan conversion (no blur band): one thread per FACE walks the pixels of the face's box inside this
+      //      tile and records, for every pixel that passes the division-free inside test (all three edge
+      //      functions non-zero and of the sign of the barycentric denominator -- a necessary condition for a
+      //      hit, see pass B0 below), the face's chunk slot in that pixel's candidate list.  The search then
+      //      costs ~(pixels in the box) per face instead of ~(faces in the tile) per pixel.
+      sh.cand_count[tid] = 0;
+      __syncthreads();
+      if (tid < nc) {
+        const float4 bx = s.box[tid];
+        if (bx.x <= bx.y) {  // drawable
+          int ix_lo, ix_hi, iy_lo, iy_hi;
+          pixel_range(bx.x, bx.y, p.W, p.rx, ix_lo, ix_hi);
+          pixel_range(bx.z, bx.w, p.H, p.ry, iy_lo, iy_hi);
+          // local column c <-> NDC pixel index xi = (W-1 - 16*tile_x) - c, same for rows
+          const int cx = p.W - 1 - tile_x * TILE, cy = p.H - 1 - tile_y * TILE;
+          const int c_lo = max(0, cx - ix_hi), c_hi = min(TILE - 1, cx - ix_lo);
+          const int r_lo = max(0, cy - iy_hi), r_hi = min(TILE - 1, cy - iy_lo);
+          const float4 fa = s.a[tid], fb = s.b[tid];
+          const bool pos = fb.z > 0.0f;
+          for (int r = r_lo; r <= r_hi; ++r) {
+            const float qy = sh.row[r];
+            if (qy > bx.w || qy < bx.z) continue;  // exact box test (:94-97)
+            for (int c = c_lo; c <= c_hi; ++c) {
+              const float qx = sh.col[c];
+              if (qx > bx.y || qx < bx.x) continue;
+              const float e0 = edge_fn(qx, qy, fa.z, fa.w, fb.x, fb.y);  // E(p; v1, v2)
+              const float e1 = edge_fn(qx, qy, fb.x, fb.y, fa.x, fa.y);  // E(p; v2, v0)
+              const float e2 = edge_fn(qx, qy, fa.x, fa.y, fa.z, fa.w);  // E(p; v0, v1)
+              const bool ok = pos ? (e0 > 0.0f && e1 > 0.0f && e2 > 0.0f) : (e0 < 0.0f && e1 < 0.0f && e2 < 0.0f);
+              if (ok) {
+                const int owner = ((r >> 2) * 2 + (c >> 3)) * 32 + (r & 3) * 8 + (c & 7);  // thread of pixel (r, c)
+                const int at = atomicAdd(&sh.cand_count[owner], 1);
+                if (at < SCAN_CAP) sh.cand[at][owner] = (unsigned char)tid;
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      const int ncand = sh.cand_count[tid];
+      if (!__syncthreads_or(ncand > SCAN_CAP)) {
+        // every pixel walks its own candidates in ascending slot (= ascending face) order
+        int last = -1;
+        for (int it = 0; it < ncand; ++it) {
+          int j = 256;
+          for (int u = 0; u < ncand; ++u) {
+            const int v = sh.cand[u][tid];
+            if (v > last && v < j) j = v;
+          }
+          last = j;
+          const float4 fa = s.a[j], fb = s.b[j], fc = s.c[j];
+          const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
+          Hit h;
+          if (valid && eval_pixel_face(px, py, f, fb.z, blur_radius, persp, clip, h)) {
+            const int fi = __float_as_int(fb.w);
+            bool consumed = false;
+            if (NB) {
+              const int nb = __float_as_int(fc.w);
+              if (nb != -1) consumed = q.offer_neighbor(h, fi, nb, pay);
+            }
+            if (!consumed) q.offer(h, fi, K, pay);
+          }
+        }
+        continue;  // chunk done
+      }
+      // (a pixel collected more than SCAN_CAP candidates: fall through to the generic passes for this chunk)
+    }
     for (int sub = 0; sub < nc; sub += ROUND) {
       // ---- pass A: 64-bit mask of the faces of this round whose box contains my pixel
       unsigned m0 = 0, m1 = 0;
@@ -833,12 +920,25 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
   p.persp = perspective_correct; p.clip = clip_barycentric_coords; p.cull = cull_backfaces;
   p.pix_to_face = pix_to_face; p.zbuf = zbuf; p.bary = bary; p.dists = dists;
   const unsigned grid = (unsigned)ntiles;
-#define B200R_FINE(KM)                                                          \
-  do {                                                                         \
-    if (neighbor)                                                              \
-      mesh_fine_kernel<KM, true><<<grid, TILE_THREADS, 0, stream>>>(p);        \
-    else                                                                       \
-      mesh_fine_kernel<KM, false><<<grid, TILE_THREADS, 0, stream>>>(p);       \
+#define B200R_FINE_ONE(KM, NBV)                                                                          \
+  do {                                                                                                   \
+    static bool configured[64] = {}; /* > 48 KB of dynamic shared memory: opt-in per kernel and device */ \
+    int dev_ = 0;                                                                                        \
+    B200R_CUDA_OK(cudaGetDevice(&dev_));                                                                 \
+    if (dev_ < 0 || dev_ >= 64 || !configured[dev_]) {                                                   \
+      B200R_CUDA_OK(cudaFuncSetAttribute(mesh_fine_kernel<KM, NBV>,                                      \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,                    \
+                                         (int)sizeof(FineShared<KM>)));                                  \
+      if (dev_ >= 0 && dev_ < 64) configured[dev_] = true;                                               \
+    }                                                                                                    \
+    mesh_fine_kernel<KM, NBV><<<grid, TILE_THREADS, sizeof(FineShared<KM>), stream>>>(p);                \
+  } while (0)
+#define B200R_FINE(KM)            \
+  do {                            \
+    if (neighbor)                 \
+      B200R_FINE_ONE(KM, true);   \
+    else                          \
+      B200R_FINE_ONE(KM, false);  \
   } while (0)
   if (K <= 1)
     B200R_FINE(1);
@@ -851,6 +951,7 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
   else
     mesh_fine_bigk_kernel<<<grid, TILE_THREADS, 0, stream>>>(p);
 #undef B200R_FINE
+#undef B200R_FINE_ONE
   B200R_LAUNCHED("mesh_fine_kernel");
   if (prof) {
     phase_timer().record(2, stream);

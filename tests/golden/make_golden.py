@@ -211,11 +211,26 @@ def clip_scenes():
                 ci += 1
 
 
+def interp_scenes():
+    """interpolate_face_attributes through the reference's CPU path (ops/interp_face_attrs.py:83-102)."""
+    from pytorch3d.ops.interp_face_attrs import interpolate_face_attributes
+    for ci, (N, H, W, K, F, D) in enumerate([(2, 5, 7, 3, 40, 3), (1, 4, 4, 1, 6, 1), (1, 6, 5, 2, 30, 8)]):
+        g = torch.Generator().manual_seed(300 + ci)
+        p2f = torch.randint(-1, F, (N, H, W, K), generator=g)
+        bary = torch.rand(N, H, W, K, 3, generator=g)
+        attrs = torch.randn(F, 3, D, generator=g)
+        out = interpolate_face_attributes(p2f, bary, attrs)
+        k = "interp/case_%02d" % ci
+        store[k + "/pix_to_face"], store[k + "/bary"], store[k + "/attrs"] = _np(p2f), _np(bary), _np(attrs)
+        store[k + "/out"] = _np(out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     reference_scenes()
     random_scenes()
     clip_scenes()
+    interp_scenes()
     path = os.path.join(OUT, "raster_golden.npz")
     np.savez_compressed(path, **store)
     cases = sorted({k.rsplit("/", 1)[0] for k in store})
