@@ -292,6 +292,7 @@ struct FineShared {
   FaceChunk s;
   float4 pay[KMAX * TILE_THREADS];            // queue payload: (signed dist, bary0, bary1, bary2) per slot
   int cand_count[TILE_THREADS];               // scan conversion: candidates recorded for each pixel (thread)
+  int cand_overflow;                          // ... some pixel collected more than SCAN_CAP of them
   unsigned char cand[SCAN_CAP][TILE_THREADS]; // ... their chunk slots
   float col[TILE], row[TILE];                 // NDC coordinates of the tile's 16 pixel columns / rows
 };
@@ -336,6 +337,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
       const int f = overflow ? (int)(mesh_first + base + tid) : p.pairs[seg_begin + base + tid];
       stage_face(s, tid, p.face_verts, p.neighbor, f, p.sqrt_blur, cull);
     }
+    sh.cand_count[tid] = 0;
+    if (tid == 0) sh.cand_overflow = 0;
     __syncthreads();
     if (!(blur_radius > 0.0f)) {
       // ---- scan conversion (no blur band): one thread per FACE walks the pixels of the face's box inside this
@@ -343,10 +346,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
       //      functions non-zero and of the sign of the barycentric denominator -- a necessary condition for a
       //      hit, see pass B0 below), the face's chunk slot in that pixel's candidate list.  The search then
       //      costs ~(pixels in the box) per face instead of ~(faces in the tile) per pixel.
-      sh.cand_count[tid] = 0;
-      __syncthreads();
-      if (tid < nc) {
-        const float4 bx = s.box[tid];
+      // threads per face: the largest power of two with nc * tpf <= 256, so that short face lists still occupy
+      // the whole CTA (the rows of a face's box are dealt round-robin to its threads)
+      int tpf_log = 0;
+      while (tpf_log < 4 && (nc << (tpf_log + 1)) <= TILE_THREADS) ++tpf_log;
+      const int fslot = tid >> tpf_log, fsub = tid & ((1 << tpf_log) - 1);
+      if (fslot < nc) {
+        const float4 bx = s.box[fslot];
         if (bx.x <= bx.y) {  // drawable
           int ix_lo, ix_hi, iy_lo, iy_hi;
           pixel_range(bx.x, bx.y, p.W, p.rx, ix_lo, ix_hi);
@@ -355,9 +361,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
           const int cx = p.W - 1 - tile_x * TILE, cy = p.H - 1 - tile_y * TILE;
           const int c_lo = max(0, cx - ix_hi), c_hi = min(TILE - 1, cx - ix_lo);
           const int r_lo = max(0, cy - iy_hi), r_hi = min(TILE - 1, cy - iy_lo);
-          const float4 fa = s.a[tid], fb = s.b[tid];
+          const float4 fa = s.a[fslot], fb = s.b[fslot];
           const bool pos = fb.z > 0.0f;
-          for (int r = r_lo; r <= r_hi; ++r) {
+          for (int r = r_lo + fsub; r <= r_hi; r += 1 << tpf_log) {
             const float qy = sh.row[r];
             if (qy > bx.w || qy < bx.z) continue;  // exact box test (:94-97)
             for (int c = c_lo; c <= c_hi; ++c) {
@@ -370,7 +376,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
               if (ok) {
                 const int owner = ((r >> 2) * 2 + (c >> 3)) * 32 + (r & 3) * 8 + (c & 7);  // thread of pixel (r, c)
                 const int at = atomicAdd(&sh.cand_count[owner], 1);
-                if (at < SCAN_CAP) sh.cand[at][owner] = (unsigned char)tid;
+                if (at < SCAN_CAP)
+                  sh.cand[at][owner] = (unsigned char)fslot;
+                else
+                  sh.cand_overflow = 1;
               }
             }
           }
@@ -378,7 +387,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
       }
       __syncthreads();
       const int ncand = sh.cand_count[tid];
-      if (!__syncthreads_or(ncand > SCAN_CAP)) {
+      if (sh.cand_overflow == 0) {  // (CTA-uniform: written before the barrier, not modified after it)
         // every pixel walks its own candidates in ascending slot (= ascending face) order
         int last = -1;
         for (int it = 0; it < ncand; ++it) {
