@@ -290,6 +290,117 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_kernel(const PointFi
   }
 }
 
+// Medium K (5..32): the queue lives in dynamic shared memory as three [K][256] arrays (slot-major, one column
+// per thread), where the dynamic slot index of the reference's queue costs nothing: appending a hit is three
+// stores instead of 3*KMAX predicated register moves, the kernel needs ~50 registers instead of 117 (K = 10),
+// and the final stable sort on z is an insertion sort over the thread's own column.
+__global__ void __launch_bounds__(TILE_THREADS) points_fine_smem_kernel(const PointFineParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PointChunk& s = *reinterpret_cast<PointChunk*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int K = p.K;
+  float* qz = reinterpret_cast<float*>(smem_raw + sizeof(PointChunk)) + tid;  // qz[k * 256]
+  int* qi = reinterpret_cast<int*>(qz - tid + K * TILE_THREADS) + tid;
+  float* qd = reinterpret_cast<float*>(qi - tid + K * TILE_THREADS) + tid;
+  const int t = blockIdx.x;
+  const int n = t / (p.TY * p.TX);
+  const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
+  int xo, yo;
+  pthread_pixel(tile_x, tile_y, xo, yo);
+  const bool valid = xo < p.W && yo < p.H;
+  const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
+  const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
+
+  const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
+  const bool overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
+  const int64_t cloud_first = p.first[n];
+  const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
+
+  int size = 0, max_idx = -1;
+  float max_z = -1000.0f;
+
+  for (int base = 0; base < count; base += PCHUNK) {
+    const int nc = min(PCHUNK, count - base);
+    __syncthreads();
+    for (int j = tid; j < nc; j += TILE_THREADS) {
+      const int pi = overflow ? (int)(cloud_first + base + j) : p.pairs[seg_begin + base + j];
+      stage_point(s, j, p.points, p.radius, pi);
+    }
+    __syncthreads();
+    for (int sub = 0; sub < nc; sub += 64) {
+      unsigned m0 = 0, m1 = 0;
+      {
+        float col[8], row[4];  // the footprint's 8 column and 4 row coordinates (lane = row * 8 + column)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) col[c] = __shfl_sync(0xffffffffu, px, c);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) row[r] = __shfl_sync(0xffffffffu, py, 8 * r);
+        if (sub + lane < nc) m0 = box_pixel_mask(s.box[sub + lane], col, row);
+        if (sub + 32 + lane < nc) m1 = box_pixel_mask(s.box[sub + 32 + lane], col, row);
+      }
+      m0 = warp_transpose_bits(m0, lane);
+      if (sub + 32 < nc) m1 = warp_transpose_bits(m1, lane);
+      unsigned long long mine = valid ? (((unsigned long long)m1 << 32) | m0) : 0ull;
+      while (__any_sync(0xffffffffu, mine != 0ull)) {
+        if (mine == 0ull) continue;
+        const int j = sub + __ffsll((long long)mine) - 1;
+        mine &= mine - 1ull;
+        const float4 r = s.rec[j];
+        // CheckPixelInsidePoint (rasterize_points.cu:49-60): dist2 = fma(dy, dy, rn(dx*dx)) < rn(r*r)
+        const float dx = fsub(px, r.x), dy = fsub(py, r.y);
+        const float d2 = sqnorm2(dx, dy);
+        if (r.z < 0.0f || !(d2 < r.w)) continue;
+        const int pi = s.id[j];
+        if (size < K) {  // (:61-67)
+          qz[size * TILE_THREADS] = r.z;
+          qi[size * TILE_THREADS] = pi;
+          qd[size * TILE_THREADS] = d2;
+          if (r.z > max_z) {
+            max_z = r.z;
+            max_idx = size;
+          }
+          ++size;
+        } else if (r.z < max_z) {  // (:68-78)
+          qz[max_idx * TILE_THREADS] = r.z;
+          qi[max_idx * TILE_THREADS] = pi;
+          qd[max_idx * TILE_THREADS] = d2;
+          max_z = r.z;
+          for (int i = 0; i < K; ++i) {
+            const float v = qz[i * TILE_THREADS];
+            if (v > max_z) {
+              max_z = v;
+              max_idx = i;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!valid) return;
+  // BubbleSort on z only (rasterize_points.cu:26-28): stable -> insertion sort over the thread's own column
+  for (int i = 1; i < size; ++i) {
+    const float tz = qz[i * TILE_THREADS], td = qd[i * TILE_THREADS];
+    const int ti = qi[i * TILE_THREADS];
+    int j = i - 1;
+    while (j >= 0 && tz < qz[j * TILE_THREADS]) {
+      qz[(j + 1) * TILE_THREADS] = qz[j * TILE_THREADS];
+      qi[(j + 1) * TILE_THREADS] = qi[j * TILE_THREADS];
+      qd[(j + 1) * TILE_THREADS] = qd[j * TILE_THREADS];
+      --j;
+    }
+    qz[(j + 1) * TILE_THREADS] = tz;
+    qi[(j + 1) * TILE_THREADS] = ti;
+    qd[(j + 1) * TILE_THREADS] = td;
+  }
+  const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
+  for (int k = 0; k < K; ++k) {
+    const bool e = k >= size;
+    p.idx[o + k] = e ? -1 : qi[k * TILE_THREADS];
+    p.zbuf[o + k] = e ? -1.0f : qz[k * TILE_THREADS];
+    p.dists[o + k] = e ? -1.0f : qd[k * TILE_THREADS];
+  }
+}
+
 // Backward: one thread per (pixel, k) slot, coalesced over the (N,H,W,K) arrays
 // (rasterize_points.cu:366-411): grad_xy = 2 * grad_dist * (p_xy - pix_xy), grad_z = grad_zbuf.
 __global__ void __launch_bounds__(256)
@@ -376,12 +487,18 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
     points_fine_kernel<2><<<grid, TILE_THREADS, 0, stream>>>(p);
   else if (K <= 4)
     points_fine_kernel<4><<<grid, TILE_THREADS, 0, stream>>>(p);
-  else if (K <= 8)
-    points_fine_kernel<8><<<grid, TILE_THREADS, 0, stream>>>(p);
-  else if (K <= 16)
-    points_fine_kernel<16><<<grid, TILE_THREADS, 0, stream>>>(p);
-  else if (K <= 32)
-    points_fine_kernel<32><<<grid, TILE_THREADS, 0, stream>>>(p);
+  else if (K <= 32) {
+    const size_t smem = sizeof(PointChunk) + (size_t)K * TILE_THREADS * 12;
+    static bool configured[64] = {}; /* > 48 KB of dynamic shared memory: opt-in per kernel and device */
+    int dev_ = 0;
+    B200R_CUDA_OK(cudaGetDevice(&dev_));
+    if (dev_ < 0 || dev_ >= 64 || !configured[dev_]) {
+      B200R_CUDA_OK(cudaFuncSetAttribute(points_fine_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(PointChunk) + 32 * TILE_THREADS * 12)));
+      if (dev_ >= 0 && dev_ < 64) configured[dev_] = true;
+    }
+    points_fine_smem_kernel<<<grid, TILE_THREADS, smem, stream>>>(p);
+  }
   else
     points_fine_kernel<0><<<grid, TILE_THREADS, 0, stream>>>(p);
   B200R_LAUNCHED("points_fine_kernel");
