@@ -95,6 +95,36 @@ int b200r_rasterize_meshes_backward(const float* face_verts, int64_t F, const in
                                     int32_t N, int32_t H, int32_t W, int32_t K, int32_t perspective_correct,
                                     int32_t clip_barycentric_coords, float* grad_face_verts, void* stream);
 
+/*
+ * Fused gather entry points: the same rasterization, but taking the packed mesh itself.
+ * Replace the `face_verts = verts_packed[faces_packed]` autograd node of the reference's wrapper
+ * (pytorch3d/renderer/mesh/rasterize_meshes.py:144-148) together with the op it feeds: the setup pass gathers
+ * the vertices of each face, and the backward adds the per-face gradient straight into the vertices.
+ *
+ *  verts  float32 (V,3) packed vertices;  faces int64 (F,3) packed vertex indices (0 <= index < V; a face with
+ *         an out-of-range index is rasterized as NaN, i.e. never hit -- the reference raises a device assert)
+ *  face_verts_out  float32 (F,3,3), written by the forward call: the gathered faces, to be passed to the
+ *         backward call (what the reference's autograd saves)
+ *  grad_verts      float32 (V,3), zeroed and accumulated by the backward call
+ *  grad_face_verts_scratch float32 (F,3,3) scratch of the backward call
+ * All other arguments as in b200r_rasterize_meshes_forward / _backward (same workspace size).
+ */
+int b200r_rasterize_meshes_forward_indexed(const float* verts, int64_t V, const int64_t* faces, int64_t F,
+                                           const int64_t* mesh_to_face_first_idx, const int64_t* num_faces_per_mesh,
+                                           const int64_t* clipped_faces_neighbor_idx, int32_t N, int32_t H,
+                                           int32_t W, float blur_radius, int32_t faces_per_pixel,
+                                           int32_t perspective_correct, int32_t clip_barycentric_coords,
+                                           int32_t cull_backfaces, int64_t* pix_to_face, float* zbuf, float* bary,
+                                           float* dists, float* face_verts_out, void* workspace,
+                                           size_t workspace_bytes, int64_t pair_capacity, void* stream);
+
+int b200r_rasterize_meshes_backward_indexed(const float* face_verts, const int64_t* faces, int64_t F, int64_t V,
+                                            const int64_t* pix_to_face, const float* grad_zbuf,
+                                            const float* grad_bary, const float* grad_dists, int32_t N, int32_t H,
+                                            int32_t W, int32_t K, int32_t perspective_correct,
+                                            int32_t clip_barycentric_coords, float* grad_verts,
+                                            float* grad_face_verts_scratch, void* stream);
+
 /* ------------------------------------------------------------------ points ------------------ */
 
 size_t b200r_rasterize_points_workspace_bytes(int64_t P, int32_t N, int32_t H, int32_t W, int64_t pair_capacity);

@@ -144,6 +144,102 @@ def rasterize_meshes_backward(
     return grad_face_verts
 
 
+def rasterize_meshes_indexed(
+    verts_packed: torch.Tensor,
+    faces_packed: torch.Tensor,
+    mesh_to_face_first_idx: torch.Tensor,
+    num_faces_per_mesh: torch.Tensor,
+    image_size: Tuple[int, int],
+    blur_radius: float,
+    faces_per_pixel: int,
+    perspective_correct: bool,
+    clip_barycentric_coords: bool,
+    cull_backfaces: bool,
+):
+    """Fused `rasterize_meshes(verts_packed[faces_packed], ...)` (no counterpart in pytorch3d._C).
+
+    Returns (pix_to_face, zbuf, bary, dists, face_verts): the four Fragments buffers and the gathered (F,3,3)
+    faces that `rasterize_meshes_backward_indexed` needs.
+    """
+    if verts_packed.dim() != 2 or verts_packed.shape[1] != 3:
+        raise RuntimeError("verts_packed must have dimensions (num_verts, 3)")
+    if faces_packed.dim() != 2 or faces_packed.shape[1] != 3:
+        raise RuntimeError("faces_packed must have dimensions (num_faces, 3)")
+    if num_faces_per_mesh.shape[0] != mesh_to_face_first_idx.shape[0]:
+        raise RuntimeError(
+            "num_faces_per_mesh must have save size first dimension as mesh_to_faces_packed_first_idx")
+    if faces_per_pixel > kMaxPointsPerPixel:
+        raise RuntimeError("Must have points_per_pixel <= %d" % kMaxPointsPerPixel)
+    if verts_packed.dtype != torch.float32:
+        raise RuntimeError("expected scalar type Float but found %s" % verts_packed.dtype)
+    dev = _require_cuda(("verts_packed", verts_packed), ("faces_packed", faces_packed),
+                        ("mesh_to_faces_packed_first_idx", mesh_to_face_first_idx),
+                        ("num_faces_per_mesh", num_faces_per_mesh))
+    lib = _lib.load()
+    H, W = int(image_size[0]), int(image_size[1])
+    K = int(faces_per_pixel)
+    N, F, V = int(num_faces_per_mesh.shape[0]), int(faces_packed.shape[0]), int(verts_packed.shape[0])
+    verts = verts_packed.contiguous()
+    faces = faces_packed.contiguous().to(torch.int64)
+    first = mesh_to_face_first_idx.contiguous().to(torch.int64)
+    num = num_faces_per_mesh.contiguous().to(torch.int64)
+    with torch.cuda.device(dev):
+        pix_to_face = torch.empty((N, H, W, K), dtype=torch.int64, device=dev)
+        zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
+        dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        face_verts = torch.empty((F, 3, 3), dtype=torch.float32, device=dev)
+        ws_bytes = lib.b200r_rasterize_meshes_workspace_bytes(F, N, H, W, PAIR_CAPACITY)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        _lib.check(lib.b200r_rasterize_meshes_forward_indexed(
+            _ptr(verts), V, _ptr(faces), F, _ptr(first), _ptr(num), None, N, H, W, float(blur_radius), K,
+            int(bool(perspective_correct)), int(bool(clip_barycentric_coords)), int(bool(cull_backfaces)),
+            _ptr(pix_to_face), _ptr(zbuf), _ptr(bary), _ptr(dists), _ptr(face_verts), _ptr(ws), ws_bytes,
+            PAIR_CAPACITY, _stream_ptr(dev)))
+        ws.record_stream(torch.cuda.current_stream(dev))
+    return pix_to_face, zbuf, bary, dists, face_verts
+
+
+def rasterize_meshes_backward_indexed(
+    face_verts: torch.Tensor,
+    faces_packed: torch.Tensor,
+    num_verts: int,
+    pix_to_face: torch.Tensor,
+    grad_zbuf: torch.Tensor,
+    grad_bary: torch.Tensor,
+    grad_dists: torch.Tensor,
+    perspective_correct: bool,
+    clip_barycentric_coords: bool,
+):
+    """Backward of `rasterize_meshes_indexed`: the gradient w.r.t. verts_packed, (V, 3)."""
+    dev = _require_cuda(("face_verts", face_verts), ("faces_packed", faces_packed), ("pix_to_face", pix_to_face),
+                        ("grad_zbuf", grad_zbuf), ("grad_bary", grad_bary), ("grad_dists", grad_dists))
+    for name, t in (("face_verts", face_verts), ("grad_zbuf", grad_zbuf), ("grad_bary", grad_bary),
+                    ("grad_dists", grad_dists)):
+        if t.dtype != torch.float32:
+            raise RuntimeError("Expected tensor for %s to have scalar type Float; but got %s" % (name, t.dtype))
+    if torch.are_deterministic_algorithms_enabled() and not torch.is_deterministic_algorithms_warn_only_enabled():
+        raise RuntimeError(
+            "RasterizeMeshesBackwardCuda does not have a deterministic implementation, but you set "
+            "'torch.use_deterministic_algorithms(True)'.")
+    lib = _lib.load()
+    N, H, W, K = (int(s) for s in pix_to_face.shape)
+    F, V = int(face_verts.shape[0]), int(num_verts)
+    fv = face_verts.contiguous()
+    faces = faces_packed.contiguous().to(torch.int64)
+    p2f = pix_to_face.contiguous()
+    gz, gb, gd = grad_zbuf.contiguous(), grad_bary.contiguous(), grad_dists.contiguous()
+    with torch.cuda.device(dev):
+        grad_verts = torch.empty((V, 3), dtype=torch.float32, device=dev)
+        scratch = torch.empty((F, 3, 3), dtype=torch.float32, device=dev)
+        _lib.check(lib.b200r_rasterize_meshes_backward_indexed(
+            _ptr(fv), _ptr(faces), F, V, _ptr(p2f), _ptr(gz), _ptr(gb), _ptr(gd), N, H, W, K,
+            int(bool(perspective_correct)), int(bool(clip_barycentric_coords)), _ptr(grad_verts), _ptr(scratch),
+            _stream_ptr(dev)))
+        scratch.record_stream(torch.cuda.current_stream(dev))
+    return grad_verts
+
+
 def rasterize_points(
     points: torch.Tensor,
     cloud_to_packed_first_idx: torch.Tensor,

@@ -45,22 +45,70 @@ __device__ __forceinline__ void face_box(const Face& f, float sqrt_blur, float& 
   ymax = fadd(fmaxf(fmaxf(f.y0, f.y1), f.y2), sqrt_blur);
 }
 
+// Per-face records (workspace, written once per forward call by the setup pass, read by the fine pass): the
+// constants of a face that every (tile, face) pair would otherwise recompute.  One 16-byte word per array.
+struct FaceRecords {
+  float4* a;    // x0, y0, x1, y1
+  float4* b;    // x2, y2, barycentric denominator, face index (int bits)
+  float4* c;    // z0, z1, z2, clipped-face neighbour index (int bits, -1 = none)
+  float4* box;  // xmin, xmax, ymin, ymax (blur-expanded; empty = never hit)
+  int4* rng;    // xo_lo, xo_hi, yo_lo, yo_hi: the OUTPUT pixels whose centre passes the reference's box test
+};
+constexpr size_t FACE_RECORD_BYTES = 5 * 16;
+
+// Exact pixel range of the box test `p > vmax || p < vmin` (rasterize_meshes.cu:94-97): pix_to_ndc is monotonic
+// in the pixel index, so the passing pixels are contiguous; start from the conservative range and trim the ends.
+__device__ __forceinline__ void exact_pixel_range(float vmin, float vmax, int S, float range, int& lo, int& hi) {
+  pixel_range(vmin, vmax, S, range, lo, hi);
+  while (lo <= hi) {
+    const float v = pix_to_ndc(lo, S, range);
+    if (!(v > vmax || v < vmin)) break;
+    ++lo;
+  }
+  while (hi >= lo) {
+    const float v = pix_to_ndc(hi, S, range);
+    if (!(v > vmax || v < vmin)) break;
+    --hi;
+  }
+}
+
+// INDEXED (the fused entry point): the faces are given as (verts, faces); the kernel gathers the three vertices
+// of each face itself -- what `verts_packed[faces_packed]` does in the reference's wrapper
+// (rasterize_meshes.py:144-148) -- and also writes the gathered (F,3,3) array for the backward pass.
+template <bool INDEXED>
 __global__ void __launch_bounds__(SETUP_FACES)
-    mesh_setup_count_kernel(const float* __restrict__ face_verts, int64_t F, const int64_t* __restrict__ first,
-                            const int64_t* __restrict__ num, int N, int H, int W, int TY, int TX, float rx,
-                            float ry, float sqrt_blur, int cull_backfaces, uint4* __restrict__ rect,
-                            int* __restrict__ tile_count) {
+    mesh_setup_count_kernel(const float* __restrict__ face_verts, const float* __restrict__ verts, int64_t V,
+                            const int64_t* __restrict__ faces, float* __restrict__ face_verts_out,
+                            const int64_t* __restrict__ neighbor, int64_t F, const int64_t* __restrict__ first,
+                            const int64_t* __restrict__ num, int N, int H, int W, int TY, int TX, float rx, float ry,
+                            float sqrt_blur, int cull_backfaces, uint4* __restrict__ rect,
+                            int* __restrict__ tile_count, const FaceRecords rec) {
   __shared__ __align__(16) float s_fv[SETUP_FACES * 9];
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x;
   const int64_t f0 = (int64_t)blockIdx.x * SETUP_FACES;
   const int nf = (int)min((int64_t)SETUP_FACES, F - f0);
-  if (tid == 0) {
-    mbar_init(&bar, 1);
-    fence_mbar_init();
+  if (INDEXED) {
+    // one (face, corner) per step and thread: coalesced index reads, 12-byte vertex gathers (the vertex array
+    // is small and L2-resident), then the gathered block is written out as 9 * nf contiguous floats
+    for (int e = tid; e < nf * 3; e += SETUP_FACES) {
+      const int64_t vi = __ldg(faces + f0 * 3 + e);
+      const bool ok = vi >= 0 && vi < V;  // out-of-range indices (an error in the reference) give a NaN face
+      const float* v = verts + vi * 3;
+      s_fv[e * 3 + 0] = ok ? __ldg(v + 0) : __int_as_float(0x7fc00000);
+      s_fv[e * 3 + 1] = ok ? __ldg(v + 1) : __int_as_float(0x7fc00000);
+      s_fv[e * 3 + 2] = ok ? __ldg(v + 2) : __int_as_float(0x7fc00000);
+    }
+    __syncthreads();
+    for (int e = tid; e < nf * 9; e += SETUP_FACES) face_verts_out[f0 * 9 + e] = s_fv[e];
+  } else {
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    cta_load_words(s_fv, face_verts + f0 * 9, nf * 9, &bar, 0);
   }
-  __syncthreads();
-  cta_load_words(s_fv, face_verts + f0 * 9, nf * 9, &bar, 0);
   uint2 r = make_uint2(RECT_EMPTY_X, 0u);
   int n = -1;
   const int64_t fi = f0 + tid;
@@ -68,12 +116,27 @@ __global__ void __launch_bounds__(SETUP_FACES)
     const float* v = s_fv + tid * 9;  // stride 9 words: conflict-free across a warp
     const Face f = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]};
     n = find_owner(first, num, N, fi);
+    float4 box = make_float4(FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX);
+    int4 rng = make_int4(1, 0, 1, 0);
     if (n >= 0 && face_is_drawable(f, cull_backfaces != 0)) {
-      float xmin, xmax, ymin, ymax;
-      face_box(f, sqrt_blur, xmin, xmax, ymin, ymax);
-      r = bbox_to_tile_rect(xmin, xmax, ymin, ymax, H, W, rx, ry);
+      face_box(f, sqrt_blur, box.x, box.y, box.z, box.w);
+      int ix_lo, ix_hi, iy_lo, iy_hi;
+      exact_pixel_range(box.x, box.y, W, rx, ix_lo, ix_hi);
+      exact_pixel_range(box.z, box.w, H, ry, iy_lo, iy_hi);
+      if (ix_lo <= ix_hi && iy_lo <= iy_hi) {
+        rng = make_int4(W - 1 - ix_hi, W - 1 - ix_lo, H - 1 - iy_hi, H - 1 - iy_lo);
+        r = make_uint2((uint32_t)(rng.x / TILE) | ((uint32_t)(rng.y / TILE) << 16),
+                       (uint32_t)(rng.z / TILE) | ((uint32_t)(rng.w / TILE) << 16));
+      }
     }
     rect[fi] = make_uint4(r.x, r.y, (uint32_t)max(n, 0), 0u);
+    // the reference reads the int64 neighbour index into an int (rasterize_meshes.cu:186)
+    const int nb = neighbor ? (int)__ldg(neighbor + fi) : -1;
+    rec.a[fi] = make_float4(f.x0, f.y0, f.x1, f.y1);
+    rec.b[fi] = make_float4(f.x2, f.y2, bary_denominator(f), __int_as_float((int)fi));
+    rec.c[fi] = make_float4(f.z0, f.z1, f.z2, __int_as_float(nb));
+    rec.box[fi] = box;
+    rec.rng[fi] = rng;
   }
   warp_count_rect(r, n, TY, TX, tile_count, tid & 31);  // all lanes participate
 }
@@ -187,6 +250,10 @@ struct TopK {
   // sorting network gives the same result; unfilled slots are pushed to the end.  slot[k] = queue slot (and
   // payload row) of the k-th nearest hit.
   __device__ __forceinline__ void sort(int (&slot)[KMAX]) {
+    // only the first `n` slots (n = the largest queue of the warp, so that the branches below are uniform)
+    // can hold hits: n rounds of odd-even transposition over those slots sort them.  Most pixels see a few
+    // layers of surface, so this is typically one or zero compare-exchanges instead of KMAX^2 / 2.
+    const int n = __reduce_max_sync(0xffffffffu, size);
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
       slot[i] = i;
@@ -197,18 +264,20 @@ struct TopK {
     }
 #pragma unroll
     for (int r = 0; r < KMAX; ++r) {
+      if (r >= n) break;
 #pragma unroll
       for (int i = r & 1; i + 1 < KMAX; i += 2) {
-        if (key_less(z[i + 1], id[i + 1], z[i], id[i])) {
-          const float t = z[i];
-          z[i] = z[i + 1];
-          z[i + 1] = t;
-          int ti = id[i];
-          id[i] = id[i + 1];
-          id[i + 1] = ti;
-          ti = slot[i];
-          slot[i] = slot[i + 1];
-          slot[i + 1] = ti;
+        if (i + 1 < n) {
+          const bool sw = key_less(z[i + 1], id[i + 1], z[i], id[i]);
+          const float za = z[i], zb = z[i + 1];
+          z[i] = sw ? zb : za;
+          z[i + 1] = sw ? za : zb;
+          const int ia = id[i], ib = id[i + 1];
+          id[i] = sw ? ib : ia;
+          id[i + 1] = sw ? ia : ib;
+          const int sa = slot[i], sb = slot[i + 1];
+          slot[i] = sw ? sb : sa;
+          slot[i + 1] = sw ? sa : sb;
         }
       }
     }
@@ -239,9 +308,17 @@ __device__ __forceinline__ void stage_face(FaceChunk& s, int slot, const float* 
   s.c[slot] = make_float4(fc.z0, fc.z1, fc.z2, __int_as_float(nb));
 }
 
+// Fragments are written once and read by a later kernel: streaming stores (evict-first) keep them from pushing
+// the tile lists and face records, which the next tiles are about to read, out of L2.
+template <typename T>
+__device__ __forceinline__ void out_store(T* ptr, const T v) {
+  __stcs(ptr, v);
+}
+
 struct FineParams {
   const float* face_verts;
   const int64_t* neighbor;  // clipped_faces_neighbor_idx or nullptr
+  FaceRecords rec;
   const int64_t* first;
   const int64_t* num;
   const int* tile_offset;
@@ -274,8 +351,8 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Faces are consumed in rounds of 64.  Pass A: each lane box-tests one face against the whole footprint and
-// the warp transposes the resulting bit matrix, so that every lane ends up with a 64-bit mask of the faces
+// Blur > 0: faces are consumed in rounds of 64.  Pass A: each lane box-tests one face against the whole footprint
+// and the warp transposes the resulting bit matrix, so that every lane ends up with a 64-bit mask of the faces
 // whose box contains ITS pixel (ascending face order = ascending bit order).  Pass B: every lane walks its
 // own mask.  In pass A the warp does ~80 instructions per 32 faces no matter how many survive; in pass B
 // each lane works on a different face that is known to touch its pixel, so the expensive arithmetic runs on
@@ -283,30 +360,82 @@ __device__ __forceinline__ float warp_max(float v) {
 // lie in a given face's box.
 constexpr int ROUND = 64;
 
-// Candidate slots per pixel and chunk in the scan-conversion path (more -> the chunk falls back to pass A/B).
-constexpr int SCAN_CAP = 16;
-
-// Dynamic shared memory of the fine kernel (54 KB for KMAX = 8: four CTAs per SM).
+// Dynamic shared memory of the fine kernel (53 KB for KMAX = 8: four CTAs per SM).
 template <int KMAX>
 struct FineShared {
-  FaceChunk s;
-  float4 pay[KMAX * TILE_THREADS];            // queue payload: (signed dist, bary0, bary1, bary2) per slot
-  int cand_count[TILE_THREADS];               // scan conversion: candidates recorded for each pixel (thread)
-  int cand_overflow;                          // ... some pixel collected more than SCAN_CAP of them
-  unsigned char cand[SCAN_CAP][TILE_THREADS]; // ... their chunk slots
-  float col[TILE], row[TILE];                 // NDC coordinates of the tile's 16 pixel columns / rows
+  float4 a[CHUNK];  // x0, y0, x1, y1            } the staged chunk: copies of the per-face records
+  float4 b[CHUNK];  // x2, y2, den, face index   }
+  float4 c[CHUNK];  // z0, z1, z2, neighbour     }
+  union {
+    float4 box[CHUNK];                          // blur > 0: blur-expanded boxes (pass A)
+    unsigned mask[CHUNK / 32][TILE_THREADS];    // blur = 0: per pixel (thread), one bit per staged face
+  } u;
+  unsigned rng[CHUNK];                          // blur = 0: tile-local pixel rectangle c_lo | c_hi<<8 | r_lo<<16 | r_hi<<24
+  float4 pay[KMAX * TILE_THREADS];              // queue payload: (signed dist, bary0, bary1, bary2) per slot
+  float col[TILE], row[TILE];                   // NDC coordinates of the tile's 16 pixel columns / rows
 };
 
-template <int KMAX, bool NB>
+// A tile no face touches: all of its outputs are -1.  Full tiles are written as whole 16-pixel row segments
+// (consecutive lanes -> consecutive 16 bytes) without computing anything per pixel.
+template <int KMAX>
+__device__ __forceinline__ void write_empty_tile(const FineParams& p, int n, int tile_x, int tile_y) {
+  const int tid = threadIdx.x;
+  const int x0 = tile_x * TILE, y0 = tile_y * TILE;
+  const int K = p.K;
+  if (K == KMAX && (KMAX % 4) == 0 && x0 + TILE <= p.W && y0 + TILE <= p.H) {
+    const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
+    constexpr int SEG_I = TILE * KMAX / 2;  // longlong2 per row segment of pix_to_face
+    constexpr int SEG_F = TILE * KMAX / 4;  // float4 per row segment of zbuf / dists (x3 for bary)
+#pragma unroll
+    for (int e = tid; e < TILE * SEG_I; e += TILE_THREADS) {
+      const int64_t o = (((int64_t)n * p.H + y0 + e / SEG_I) * p.W + x0) * KMAX;
+      out_store(reinterpret_cast<longlong2*>(p.pix_to_face + o) + e % SEG_I, make_longlong2(-1ll, -1ll));
+    }
+#pragma unroll
+    for (int e = tid; e < TILE * SEG_F; e += TILE_THREADS) {
+      const int64_t o = (((int64_t)n * p.H + y0 + e / SEG_F) * p.W + x0) * KMAX;
+      out_store(reinterpret_cast<float4*>(p.zbuf + o) + e % SEG_F, m1);
+      out_store(reinterpret_cast<float4*>(p.dists + o) + e % SEG_F, m1);
+    }
+#pragma unroll
+    for (int e = tid; e < TILE * SEG_F * 3; e += TILE_THREADS) {
+      const int64_t o = (((int64_t)n * p.H + y0 + e / (SEG_F * 3)) * p.W + x0) * KMAX;
+      out_store(reinterpret_cast<float4*>(p.bary + o * 3) + e % (SEG_F * 3), m1);
+    }
+    return;
+  }
+  int xo, yo;
+  thread_pixel(tile_x, tile_y, xo, yo);
+  if (xo >= p.W || yo >= p.H) return;
+  const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
+  for (int k = 0; k < K; ++k) {
+    p.pix_to_face[o + k] = -1ll;
+    p.zbuf[o + k] = -1.0f;
+    p.dists[o + k] = -1.0f;
+    p.bary[(o + k) * 3 + 0] = -1.0f;
+    p.bary[(o + k) * 3 + 1] = -1.0f;
+    p.bary[(o + k) * 3 + 2] = -1.0f;
+  }
+}
+
+template <int KMAX, bool NB, bool SCAN>
 __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FineParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FineShared<KMAX>& sh = *reinterpret_cast<FineShared<KMAX>*>(smem_raw);
-  FaceChunk& s = sh.s;
   const int tid = threadIdx.x, lane = tid & 31;
   float4* pay = sh.pay + tid;
   const int t = blockIdx.x;
   const int n = t / (p.TY * p.TX);
   const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
+  // the tile's face list; tiles whose segment did not fit the pair buffer test every face of the mesh
+  const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
+  const bool overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
+  const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
+  if (count == 0) {
+    write_empty_tile<KMAX>(p, n, tile_x, tile_y);
+    return;
+  }
+  const int64_t mesh_first = p.first[n];
 
   int xo, yo;
   thread_pixel(tile_x, tile_y, xo, yo);
@@ -318,89 +447,81 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
     if (r == 0) sh.col[c] = px;
     if (c == 0) sh.row[r] = py;
   }
-  // the tile's face list; tiles whose segment did not fit the pair buffer test every face of the mesh
-  const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
-  const bool overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
-  const int64_t mesh_first = p.first[n];
-  const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
 
   TopK<KMAX> q;
   q.init();
-  const bool persp = p.persp != 0, clip = p.clip != 0, cull = p.cull != 0;
+  const bool persp = p.persp != 0, clip = p.clip != 0;
   const int K = p.K;
   const float blur_radius = p.blur_radius;
+  constexpr bool scan = SCAN;  // blur_radius = 0 (host dispatch)
 
   for (int base = 0; base < count; base += CHUNK) {
     const int nc = min(CHUNK, count - base);
+    const int nwords = (nc + 31) >> 5;
     __syncthreads();  // previous chunk fully consumed
     if (tid < nc) {
       const int f = overflow ? (int)(mesh_first + base + tid) : p.pairs[seg_begin + base + tid];
-      stage_face(s, tid, p.face_verts, p.neighbor, f, p.sqrt_blur, cull);
+      const float4 ra = __ldg(p.rec.a + f), rb = __ldg(p.rec.b + f), rc = __ldg(p.rec.c + f);
+      sh.a[tid] = ra;
+      sh.b[tid] = rb;
+      sh.c[tid] = rc;
+      if (scan) {
+        const int4 g = __ldg(p.rec.rng + f);
+        const int c_lo = max(g.x - tile_x * TILE, 0), c_hi = min(g.y - tile_x * TILE, TILE - 1);
+        const int r_lo = max(g.z - tile_y * TILE, 0), r_hi = min(g.w - tile_y * TILE, TILE - 1);
+        sh.rng[tid] = (c_lo > c_hi || r_lo > r_hi) ? 1u  // empty: c_lo = 1 > c_hi = 0
+                                                   : (unsigned)(c_lo | (c_hi << 8) | (r_lo << 16) | (r_hi << 24));
+      } else {
+        sh.u.box[tid] = __ldg(p.rec.box + f);
+      }
     }
-    sh.cand_count[tid] = 0;
-    if (tid == 0) sh.cand_overflow = 0;
+    if (scan) {
+      for (int w = 0; w < nwords; ++w) sh.u.mask[w][tid] = 0u;
+    }
     __syncthreads();
-    if (!(blur_radius > 0.0f)) {
-      // ---- scan conversion (no blur band): one thread per FACE walks the pixels of the face's box inside this
-      //      tile and records, for every pixel that passes the division-free inside test (all three edge
-      //      functions non-zero and of the sign of the barycentric denominator -- a necessary condition for a
-      //      hit, see pass B0 below), the face's chunk slot in that pixel's candidate list.  The search then
-      //      costs ~(pixels in the box) per face instead of ~(faces in the tile) per pixel.
-      // threads per face: the largest power of two with nc * tpf <= 256, so that short face lists still occupy
-      // the whole CTA (the rows of a face's box are dealt round-robin to its threads)
-      int tpf_log = 0;
-      while (tpf_log < 4 && (nc << (tpf_log + 1)) <= TILE_THREADS) ++tpf_log;
-      const int fslot = tid >> tpf_log, fsub = tid & ((1 << tpf_log) - 1);
-      if (fslot < nc) {
-        const float4 bx = s.box[fslot];
-        if (bx.x <= bx.y) {  // drawable
-          int ix_lo, ix_hi, iy_lo, iy_hi;
-          pixel_range(bx.x, bx.y, p.W, p.rx, ix_lo, ix_hi);
-          pixel_range(bx.z, bx.w, p.H, p.ry, iy_lo, iy_hi);
-          // local column c <-> NDC pixel index xi = (W-1 - 16*tile_x) - c, same for rows
-          const int cx = p.W - 1 - tile_x * TILE, cy = p.H - 1 - tile_y * TILE;
-          const int c_lo = max(0, cx - ix_hi), c_hi = min(TILE - 1, cx - ix_lo);
-          const int r_lo = max(0, cy - iy_hi), r_hi = min(TILE - 1, cy - iy_lo);
-          const float4 fa = s.a[fslot], fb = s.b[fslot];
-          const bool pos = fb.z > 0.0f;
-          for (int r = r_lo + fsub; r <= r_hi; r += 1 << tpf_log) {
-            const float qy = sh.row[r];
-            if (qy > bx.w || qy < bx.z) continue;  // exact box test (:94-97)
-            for (int c = c_lo; c <= c_hi; ++c) {
-              const float qx = sh.col[c];
-              if (qx > bx.y || qx < bx.x) continue;
-              const float e0 = edge_fn(qx, qy, fa.z, fa.w, fb.x, fb.y);  // E(p; v1, v2)
-              const float e1 = edge_fn(qx, qy, fb.x, fb.y, fa.x, fa.y);  // E(p; v2, v0)
-              const float e2 = edge_fn(qx, qy, fa.x, fa.y, fa.z, fa.w);  // E(p; v0, v1)
-              const bool ok = pos ? (e0 > 0.0f && e1 > 0.0f && e2 > 0.0f) : (e0 < 0.0f && e1 < 0.0f && e2 < 0.0f);
-              if (ok) {
-                const int owner = ((r >> 2) * 2 + (c >> 3)) * 32 + (r & 3) * 8 + (c & 7);  // thread of pixel (r, c)
-                const int at = atomicAdd(&sh.cand_count[owner], 1);
-                if (at < SCAN_CAP)
-                  sh.cand[at][owner] = (unsigned char)fslot;
-                else
-                  sh.cand_overflow = 1;
-              }
-            }
+    if (scan) {
+      // ---- scan conversion (no blur band): a hit requires the pixel to be strictly inside the face, i.e. all
+      //      three w_i = E_i / den > 0, which implies that every edge function E_i is non-zero and has the sign
+      //      of den -- a test that needs no division.  Four lanes take one face and walk the rows of its pixel
+      //      rectangle (exactly the set of pixels that pass the reference's box test; precomputed per face by
+      //      the setup pass, here clamped to the tile); a pixel that passes gets the face's bit set in its mask.
+      //      The search costs ~(pixels in the box) per face instead of ~(faces in the tile) per pixel, and
+      //      leaves the candidates of every pixel in ascending face order.  (Measured on the NS workload:
+      //      1x2 / 1x4 lanes per face 186 us, 2x2 200 us, 4x4 215 us, 8x2 270 us -- the loop-invariant part of a
+      //      face is amortised over more pixels with fewer lanes.)
+      const int dr = tid & 3;
+      for (int fslot = tid >> 2; fslot < nc; fslot += TILE_THREADS / 4) {
+        const unsigned rg = sh.rng[fslot];
+        const int c_lo = rg & 255, c_hi = (rg >> 8) & 255, r_lo = (rg >> 16) & 255, r_hi = rg >> 24;
+        if (c_lo > c_hi) continue;
+        const float4 fa = sh.a[fslot], fb = sh.b[fslot];
+        const bool pos = fb.z > 0.0f;
+        unsigned* mrow = sh.u.mask[fslot >> 5];
+        const unsigned bit = 1u << (fslot & 31);
+        for (int r = r_lo + dr; r <= r_hi; r += 4) {
+          const float qy = sh.row[r];
+          for (int c = c_lo; c <= c_hi; ++c) {
+            const float qx = sh.col[c];
+            const float e0 = edge_fn(qx, qy, fa.z, fa.w, fb.x, fb.y);  // E(p; v1, v2)
+            const float e1 = edge_fn(qx, qy, fb.x, fb.y, fa.x, fa.y);  // E(p; v2, v0)
+            const float e2 = edge_fn(qx, qy, fa.x, fa.y, fa.z, fa.w);  // E(p; v0, v1)
+            const bool ok = pos ? (e0 > 0.0f && e1 > 0.0f && e2 > 0.0f) : (e0 < 0.0f && e1 < 0.0f && e2 < 0.0f);
+            // thread that owns pixel (r, c): warp = footprint (r / 4, c / 8), lane = (r % 4, c % 8)
+            if (ok) atomicOr(&mrow[((r >> 2) * 2 + (c >> 3)) * 32 + (r & 3) * 8 + (c & 7)], bit);
           }
         }
       }
       __syncthreads();
-      const int ncand = sh.cand_count[tid];
-      if (sh.cand_overflow == 0) {  // (CTA-uniform: written before the barrier, not modified after it)
-        // every pixel walks its own candidates in ascending slot (= ascending face) order
-        int last = -1;
-        for (int it = 0; it < ncand; ++it) {
-          int j = 256;
-          for (int u = 0; u < ncand; ++u) {
-            const int v = sh.cand[u][tid];
-            if (v > last && v < j) j = v;
-          }
-          last = j;
-          const float4 fa = s.a[j], fb = s.b[j], fc = s.c[j];
+      // every pixel walks its own candidates, in ascending face order
+      for (int w = 0; w < nwords; ++w) {
+        unsigned m = sh.u.mask[w][tid];
+        while (m != 0u) {
+          const int j = w * 32 + __ffs((int)m) - 1;
+          m &= m - 1u;
+          const float4 fa = sh.a[j], fb = sh.b[j], fc = sh.c[j];
           const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
           Hit h;
-          if (valid && eval_pixel_face(px, py, f, fb.z, blur_radius, persp, clip, h)) {
+          if (eval_pixel_face(px, py, f, fb.z, blur_radius, persp, clip, h)) {
             const int fi = __float_as_int(fb.w);
             bool consumed = false;
             if (NB) {
@@ -410,9 +531,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
             if (!consumed) q.offer(h, fi, K, pay);
           }
         }
-        continue;  // chunk done
       }
-      // (a pixel collected more than SCAN_CAP candidates: fall through to the generic passes for this chunk)
+      continue;  // chunk done
     }
     for (int sub = 0; sub < nc; sub += ROUND) {
       // ---- pass A: 64-bit mask of the faces of this round whose box contains my pixel
@@ -425,40 +545,18 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
         for (int c = 0; c < 8; ++c) col[c] = __shfl_sync(0xffffffffu, px, c);
 #pragma unroll
         for (int r = 0; r < 4; ++r) row[r] = __shfl_sync(0xffffffffu, py, 8 * r);
-        if (sub + lane < nc) m0 = box_pixel_mask(s.box[sub + lane], col, row);
-        if (sub + 32 + lane < nc) m1 = box_pixel_mask(s.box[sub + 32 + lane], col, row);
+        if (sub + lane < nc) m0 = box_pixel_mask(sh.u.box[sub + lane], col, row);
+        if (sub + 32 + lane < nc) m1 = box_pixel_mask(sh.u.box[sub + 32 + lane], col, row);
       }
       m0 = warp_transpose_bits(m0, lane);
       if (sub + 32 < nc) m1 = warp_transpose_bits(m1, lane);
       unsigned long long mine = valid ? (((unsigned long long)m1 << 32) | m0) : 0ull;
-      if (!(blur_radius > 0.0f)) {
-        // ---- pass B0 (no blur band): a hit requires the pixel to be strictly inside the face, i.e. all three
-        //      w_i = E_i / den > 0, which implies that every edge function E_i is non-zero and has the sign of
-        //      den.  Testing that needs no division; candidates that fail can never be hits and are dropped
-        //      before the expensive pass (typically 2 of 3 for pixel-sized triangles).
-        unsigned long long todo = mine, keep = 0ull;
-        while (__any_sync(0xffffffffu, todo != 0ull)) {
-          if (todo != 0ull) {
-            const unsigned long long bit = todo & (~todo + 1ull);
-            const int j = sub + __ffsll((long long)todo) - 1;
-            todo ^= bit;
-            const float4 fa = s.a[j], fb = s.b[j];
-            const float e0 = edge_fn(px, py, fa.z, fa.w, fb.x, fb.y);  // E(p; v1, v2)
-            const float e1 = edge_fn(px, py, fb.x, fb.y, fa.x, fa.y);  // E(p; v2, v0)
-            const float e2 = edge_fn(px, py, fa.x, fa.y, fa.z, fa.w);  // E(p; v0, v1)
-            const bool pos = fb.z > 0.0f;
-            const bool ok = pos ? (e0 > 0.0f && e1 > 0.0f && e2 > 0.0f) : (e0 < 0.0f && e1 < 0.0f && e2 < 0.0f);
-            if (ok) keep |= bit;
-          }
-        }
-        mine = keep;
-      }
       // ---- pass B: every lane evaluates its own candidates, in ascending face order
       while (__any_sync(0xffffffffu, mine != 0ull)) {
         if (mine != 0ull) {
           const int j = sub + __ffsll((long long)mine) - 1;
           mine &= mine - 1ull;
-          const float4 fa = s.a[j], fb = s.b[j], fc = s.c[j];
+          const float4 fa = sh.a[j], fb = sh.b[j], fc = sh.c[j];
           const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
           Hit h;
           if (eval_pixel_face(px, py, f, fb.z, blur_radius, persp, clip, h)) {
@@ -486,7 +584,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
     for (int k = 0; k < KMAX; k += 2) {
       const long long i0 = k >= q.size ? -1ll : (long long)q.id[k];
       const long long i1 = k + 1 >= q.size ? -1ll : (long long)q.id[k + 1];
-      pf[k / 2] = make_longlong2(i0, i1);
+      out_store(pf + k / 2, make_longlong2(i0, i1));
     }
 #pragma unroll
     for (int k0 = 0; k0 + 3 < KMAX; k0 += 4) {
@@ -498,12 +596,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
         w[u] = e ? make_float4(-1.f, -1.f, -1.f, -1.f) : pay[slot[k0 + u] * TILE_THREADS];
         zz[u] = e ? -1.0f : q.z[k0 + u];
       }
-      reinterpret_cast<float4*>(p.zbuf + o)[k0 / 4] = make_float4(zz[0], zz[1], zz[2], zz[3]);
-      reinterpret_cast<float4*>(p.dists + o)[k0 / 4] = make_float4(w[0].x, w[1].x, w[2].x, w[3].x);
+      out_store(reinterpret_cast<float4*>(p.zbuf + o) + k0 / 4, make_float4(zz[0], zz[1], zz[2], zz[3]));
+      out_store(reinterpret_cast<float4*>(p.dists + o) + k0 / 4, make_float4(w[0].x, w[1].x, w[2].x, w[3].x));
       float4* pb = reinterpret_cast<float4*>(p.bary + o * 3) + 3 * (k0 / 4);
-      pb[0] = make_float4(w[0].y, w[0].z, w[0].w, w[1].y);
-      pb[1] = make_float4(w[1].z, w[1].w, w[2].y, w[2].z);
-      pb[2] = make_float4(w[2].w, w[3].y, w[3].z, w[3].w);
+      out_store(pb + 0, make_float4(w[0].y, w[0].z, w[0].w, w[1].y));
+      out_store(pb + 1, make_float4(w[1].z, w[1].w, w[2].y, w[2].z));
+      out_store(pb + 2, make_float4(w[2].w, w[3].y, w[3].z, w[3].w));
     }
   } else {
 #pragma unroll
@@ -858,6 +956,33 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_backward_kernel(const Backw
 
 }  // namespace b200r
 
+// The face gather alone (only used when there is no image to rasterize) and the scatter-add of the per-face
+// gradient into the vertices: what autograd does for `verts_packed[faces_packed]` (rasterize_meshes.py:144-148).
+__global__ void __launch_bounds__(256) mesh_gather_kernel(const float* __restrict__ verts, int64_t V,
+                                                          const int64_t* __restrict__ faces, int64_t F,
+                                                          float* __restrict__ face_verts_out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (face, corner)
+  if (e >= F * 3) return;
+  const int64_t vi = __ldg(faces + e);
+  const bool ok = vi >= 0 && vi < V;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) face_verts_out[e * 3 + c] = ok ? __ldg(verts + vi * 3 + c) : __int_as_float(0x7fc00000);
+}
+
+__global__ void __launch_bounds__(256) mesh_scatter_kernel(const float* __restrict__ grad_face_verts,
+                                                           const int64_t* __restrict__ faces, int64_t F, int64_t V,
+                                                           float* __restrict__ grad_verts) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (face, corner)
+  if (e >= F * 3) return;
+  const int64_t vi = __ldg(faces + e);
+  if (vi < 0 || vi >= V) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float g = grad_face_verts[e * 3 + c];
+    if (g != 0.0f) atomicAdd(grad_verts + vi * 3 + c, g);
+  }
+}
+
 // ================================================================================================
 // C ABI
 // ================================================================================================
@@ -866,19 +991,15 @@ using namespace b200r;
 extern "C" size_t b200r_rasterize_meshes_workspace_bytes(int64_t F, int32_t N, int32_t H, int32_t W,
                                                          int64_t pair_capacity) {
   if (F < 0 || N < 0 || H < 0 || W < 0) return 0;
-  return carve_workspace(nullptr, F, N, H, W, pair_capacity).bytes;
+  return carve_workspace(nullptr, F, N, H, W, pair_capacity).bytes + FACE_RECORD_BYTES * (size_t)(F > 0 ? F : 1);
 }
 
-extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F, const int64_t* first,
-                                              const int64_t* num, const int64_t* neighbor, int32_t N, int32_t H,
-                                              int32_t W, float blur_radius, int32_t K, int32_t bin_size,
-                                              int32_t max_faces_per_bin, int32_t perspective_correct,
-                                              int32_t clip_barycentric_coords, int32_t cull_backfaces,
-                                              int64_t* pix_to_face, float* zbuf, float* bary, float* dists,
-                                              void* workspace, size_t workspace_bytes, int64_t pair_capacity,
-                                              void* stream_) {
-  (void)bin_size;
-  (void)max_faces_per_bin;
+static int forward_impl(const float* face_verts, const float* verts, int64_t V, const int64_t* faces,
+                        float* face_verts_out, int64_t F, const int64_t* first, const int64_t* num,
+                        const int64_t* neighbor, int32_t N, int32_t H, int32_t W, float blur_radius, int32_t K,
+                        int32_t perspective_correct, int32_t clip_barycentric_coords, int32_t cull_backfaces,
+                        int64_t* pix_to_face, float* zbuf, float* bary, float* dists, void* workspace,
+                        size_t workspace_bytes, int64_t pair_capacity, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (K > B200R_MAX_K) return fail(B200R_ERR_INVALID_ARGUMENT, "Must have points_per_pixel <= 150");
   if (F < 0 || N < 0 || H < 0 || W < 0 || K < 0) return fail(B200R_ERR_INVALID_ARGUMENT, "negative size");
@@ -889,8 +1010,15 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
   const int64_t ntiles = (int64_t)N * TY * TX;
   if (ntiles > INT_MAX) return fail(B200R_ERR_INVALID_ARGUMENT, "too many tiles");
   BinWorkspace ws = carve_workspace(workspace, F, N, H, W, pair_capacity);
-  if (workspace == nullptr || workspace_bytes < ws.bytes)
+  const size_t nrec = (size_t)(F > 0 ? F : 1);
+  if (workspace == nullptr || workspace_bytes < ws.bytes + FACE_RECORD_BYTES * nrec)
     return fail(B200R_ERR_WORKSPACE, "workspace too small for rasterize_meshes_forward");
+  FaceRecords rec;  // (ws.bytes is a multiple of 16)
+  rec.a = reinterpret_cast<float4*>(static_cast<char*>(workspace) + ws.bytes);
+  rec.b = rec.a + nrec;
+  rec.c = rec.b + nrec;
+  rec.box = rec.c + nrec;
+  rec.rng = reinterpret_cast<int4*>(rec.box + nrec);
 
   const float rx = ndc_range(W, H), ry = ndc_range(H, W);
   const float sqrt_blur = sqrtf(blur_radius);  // IEEE sqrt, like the device sqrt.rn of the reference
@@ -899,8 +1027,17 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
   if (prof) phase_timer().record(0, stream);
   B200R_CUDA_OK(cudaMemsetAsync(ws.tile_count, 0, sizeof(int) * (size_t)ntiles, stream));
   if (F > 0) {
-    mesh_setup_count_kernel<<<(unsigned)((F + SETUP_FACES - 1) / SETUP_FACES), SETUP_FACES, 0, stream>>>(
-        face_verts, F, first, num, N, H, W, TY, TX, rx, ry, sqrt_blur, cull_backfaces, ws.rect, ws.tile_count);
+    const unsigned sgrid = (unsigned)((F + SETUP_FACES - 1) / SETUP_FACES);
+    if (faces != nullptr) {
+      mesh_setup_count_kernel<true><<<sgrid, SETUP_FACES, 0, stream>>>(
+          nullptr, verts, V, faces, face_verts_out, neighbor, F, first, num, N, H, W, TY, TX, rx, ry, sqrt_blur,
+          cull_backfaces, ws.rect, ws.tile_count, rec);
+      face_verts = face_verts_out;
+    } else {
+      mesh_setup_count_kernel<false><<<sgrid, SETUP_FACES, 0, stream>>>(
+          face_verts, nullptr, 0, nullptr, nullptr, neighbor, F, first, num, N, H, W, TY, TX, rx, ry, sqrt_blur,
+          cull_backfaces, ws.rect, ws.tile_count, rec);
+    }
     B200R_LAUNCHED("mesh_setup_count_kernel");
   }
   tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles);
@@ -919,6 +1056,7 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
   FineParams p;
   p.face_verts = face_verts;
   p.neighbor = neighbor;
+  p.rec = rec;
   p.first = first;
   p.num = num;
   p.tile_offset = ws.tile_offset;
@@ -929,25 +1067,30 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
   p.persp = perspective_correct; p.clip = clip_barycentric_coords; p.cull = cull_backfaces;
   p.pix_to_face = pix_to_face; p.zbuf = zbuf; p.bary = bary; p.dists = dists;
   const unsigned grid = (unsigned)ntiles;
-#define B200R_FINE_ONE(KM, NBV)                                                                          \
+  const bool no_blur = !(blur_radius > 0.0f);
+#define B200R_FINE_ONE(KM, NBV, SC)                                                                        \
   do {                                                                                                   \
     static bool configured[64] = {}; /* > 48 KB of dynamic shared memory: opt-in per kernel and device */ \
     int dev_ = 0;                                                                                        \
     B200R_CUDA_OK(cudaGetDevice(&dev_));                                                                 \
     if (dev_ < 0 || dev_ >= 64 || !configured[dev_]) {                                                   \
-      B200R_CUDA_OK(cudaFuncSetAttribute(mesh_fine_kernel<KM, NBV>,                                      \
+      B200R_CUDA_OK(cudaFuncSetAttribute(mesh_fine_kernel<KM, NBV, SC>,                                    \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,                    \
                                          (int)sizeof(FineShared<KM>)));                                  \
       if (dev_ >= 0 && dev_ < 64) configured[dev_] = true;                                               \
     }                                                                                                    \
-    mesh_fine_kernel<KM, NBV><<<grid, TILE_THREADS, sizeof(FineShared<KM>), stream>>>(p);                \
+    mesh_fine_kernel<KM, NBV, SC><<<grid, TILE_THREADS, sizeof(FineShared<KM>), stream>>>(p);            \
   } while (0)
-#define B200R_FINE(KM)            \
-  do {                            \
-    if (neighbor)                 \
-      B200R_FINE_ONE(KM, true);   \
-    else                          \
-      B200R_FINE_ONE(KM, false);  \
+#define B200R_FINE(KM)                   \
+  do {                                   \
+    if (neighbor && no_blur)             \
+      B200R_FINE_ONE(KM, true, true);    \
+    else if (neighbor)                   \
+      B200R_FINE_ONE(KM, true, false);   \
+    else if (no_blur)                    \
+      B200R_FINE_ONE(KM, false, true);   \
+    else                                 \
+      B200R_FINE_ONE(KM, false, false);  \
   } while (0)
   if (K <= 1)
     B200R_FINE(1);
@@ -967,6 +1110,45 @@ extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F
     phase_timer().have_fwd = true;
   }
   return B200R_OK;
+}
+
+extern "C" int b200r_rasterize_meshes_forward(const float* face_verts, int64_t F, const int64_t* first,
+                                              const int64_t* num, const int64_t* neighbor, int32_t N, int32_t H,
+                                              int32_t W, float blur_radius, int32_t K, int32_t bin_size,
+                                              int32_t max_faces_per_bin, int32_t perspective_correct,
+                                              int32_t clip_barycentric_coords, int32_t cull_backfaces,
+                                              int64_t* pix_to_face, float* zbuf, float* bary, float* dists,
+                                              void* workspace, size_t workspace_bytes, int64_t pair_capacity,
+                                              void* stream_) {
+  (void)bin_size;
+  (void)max_faces_per_bin;
+  return forward_impl(face_verts, nullptr, 0, nullptr, nullptr, F, first, num, neighbor, N, H, W, blur_radius, K,
+                      perspective_correct, clip_barycentric_coords, cull_backfaces, pix_to_face, zbuf, bary, dists,
+                      workspace, workspace_bytes, pair_capacity, stream_);
+}
+
+extern "C" int b200r_rasterize_meshes_forward_indexed(const float* verts, int64_t V, const int64_t* faces, int64_t F,
+                                                      const int64_t* first, const int64_t* num,
+                                                      const int64_t* neighbor, int32_t N, int32_t H, int32_t W,
+                                                      float blur_radius, int32_t K, int32_t perspective_correct,
+                                                      int32_t clip_barycentric_coords, int32_t cull_backfaces,
+                                                      int64_t* pix_to_face, float* zbuf, float* bary, float* dists,
+                                                      float* face_verts_out, void* workspace,
+                                                      size_t workspace_bytes, int64_t pair_capacity,
+                                                      void* stream_) {
+  if (V < 0) return fail(B200R_ERR_INVALID_ARGUMENT, "negative size");
+  if (F > 0 && (faces == nullptr || face_verts_out == nullptr || (V > 0 && verts == nullptr)))
+    return fail(B200R_ERR_INVALID_ARGUMENT, "verts, faces and face_verts_out must not be null");
+  if ((int64_t)N * H * W * K == 0 && F > 0) {
+    // no image to produce, but the gathered faces are still an output
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    mesh_gather_kernel<<<(unsigned)((F * 3 + 255) / 256), 256, 0, stream>>>(verts, V, faces, F, face_verts_out);
+    B200R_LAUNCHED("mesh_gather_kernel");
+    return B200R_OK;
+  }
+  return forward_impl(nullptr, verts, V, F > 0 ? faces : nullptr, face_verts_out, F, first, num, neighbor, N, H, W,
+                      blur_radius, K, perspective_correct, clip_barycentric_coords, cull_backfaces, pix_to_face,
+                      zbuf, bary, dists, workspace, workspace_bytes, pair_capacity, stream_);
 }
 
 extern "C" int b200r_rasterize_meshes_backward(const float* face_verts, int64_t F, const int64_t* pix_to_face,
@@ -1001,5 +1183,26 @@ extern "C" int b200r_rasterize_meshes_backward(const float* face_verts, int64_t 
     phase_timer().record(4, stream);
     phase_timer().have_bwd = true;
   }
+  return B200R_OK;
+}
+
+extern "C" int b200r_rasterize_meshes_backward_indexed(const float* face_verts, const int64_t* faces, int64_t F,
+                                                       int64_t V, const int64_t* pix_to_face,
+                                                       const float* grad_zbuf, const float* grad_bary,
+                                                       const float* grad_dists, int32_t N, int32_t H, int32_t W,
+                                                       int32_t K, int32_t perspective_correct,
+                                                       int32_t clip_barycentric_coords, float* grad_verts,
+                                                       float* grad_face_verts_scratch, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (F < 0 || V < 0) return fail(B200R_ERR_INVALID_ARGUMENT, "negative size");
+  if (V > 0) B200R_CUDA_OK(cudaMemsetAsync(grad_verts, 0, sizeof(float) * 3 * (size_t)V, stream));
+  if (F == 0 || V == 0) return B200R_OK;
+  const int rc = b200r_rasterize_meshes_backward(face_verts, F, pix_to_face, grad_zbuf, grad_bary, grad_dists, N, H, W,
+                                                 K, perspective_correct, clip_barycentric_coords,
+                                                 grad_face_verts_scratch, stream_);
+  if (rc != B200R_OK) return rc;
+  mesh_scatter_kernel<<<(unsigned)((F * 3 + 255) / 256), 256, 0, stream>>>(grad_face_verts_scratch, faces, F, V,
+                                                                          grad_verts);
+  B200R_LAUNCHED("mesh_scatter_kernel");
   return B200R_OK;
 }

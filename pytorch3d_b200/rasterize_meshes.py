@@ -54,31 +54,11 @@ def rasterize_meshes(
     """
     verts_packed = meshes.verts_packed()
     faces_packed = meshes.faces_packed()
-    face_verts = verts_packed[faces_packed]
     mesh_to_face_first_idx = meshes.mesh_to_faces_packed_first_idx()
     num_faces_per_mesh = meshes.num_faces_per_mesh()
 
     im_size = parse_image_size(image_size)
     max_image_size = max(*im_size)
-
-    clipped_faces_neighbor_idx = None
-    clipped_faces = None
-    if z_clip_value is not None or cull_to_frustum:
-        # Cull faces outside the view frustum and clip faces that are partially behind the camera to
-        # z >= z_clip_value; this may change the number of faces (rasterize_meshes.py:160-183 of the reference)
-        frustum = ClipFrustum(left=-1, right=1, top=-1, bottom=1, perspective_correct=perspective_correct,
-                              z_clip_value=z_clip_value, cull=cull_to_frustum)
-        clipped_faces = clip_faces(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, frustum=frustum)
-        face_verts = clipped_faces.face_verts
-        mesh_to_face_first_idx = clipped_faces.mesh_to_face_first_idx
-        num_faces_per_mesh = clipped_faces.num_faces_per_mesh
-        # the two halves of a face that was clipped to a quad name each other: only one may enter the top K
-        clipped_faces_neighbor_idx = clipped_faces.clipped_faces_neighbor_idx
-
-    if clipped_faces_neighbor_idx is None:
-        clipped_faces_neighbor_idx = torch.full(
-            size=(face_verts.shape[0],), fill_value=-1, device=face_verts.device, dtype=torch.int64)
-        clipped_faces_neighbor_idx._b200_all_minus_one = True  # selects the kernel variant without that logic
 
     if bin_size is None:
         if max_image_size <= 64:
@@ -94,16 +74,63 @@ def rasterize_meshes(
     if max_faces_per_bin is None:
         max_faces_per_bin = int(max(10000, getattr(meshes, "_F", 0) / 5))
 
+    if z_clip_value is None and not cull_to_frustum:
+        # no clipping: the gather `verts_packed[faces_packed]` (rasterize_meshes.py:144-148 of the reference) and
+        # its backward scatter run inside the native op (b200r_rasterize_meshes_*_indexed)
+        return _RasterizeMeshesIndexed.apply(
+            verts_packed, faces_packed, mesh_to_face_first_idx, num_faces_per_mesh, im_size, blur_radius,
+            faces_per_pixel, perspective_correct, clip_barycentric_coords, cull_backfaces)
+
+    # Cull faces outside the view frustum and clip faces that are partially behind the camera to
+    # z >= z_clip_value; this may change the number of faces (rasterize_meshes.py:160-183 of the reference)
+    face_verts = verts_packed[faces_packed]
+    frustum = ClipFrustum(left=-1, right=1, top=-1, bottom=1, perspective_correct=perspective_correct,
+                          z_clip_value=z_clip_value, cull=cull_to_frustum)
+    clipped_faces = clip_faces(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, frustum=frustum)
+    face_verts = clipped_faces.face_verts
+    mesh_to_face_first_idx = clipped_faces.mesh_to_face_first_idx
+    num_faces_per_mesh = clipped_faces.num_faces_per_mesh
+    # the two halves of a face that was clipped to a quad name each other: only one may enter the top K
+    clipped_faces_neighbor_idx = clipped_faces.clipped_faces_neighbor_idx
+    if clipped_faces_neighbor_idx is None:
+        clipped_faces_neighbor_idx = torch.full(
+            size=(face_verts.shape[0],), fill_value=-1, device=face_verts.device, dtype=torch.int64)
+        clipped_faces_neighbor_idx._b200_all_minus_one = True  # selects the kernel variant without that logic
+
     pix_to_face, zbuf, barycentric_coords, dists = _RasterizeFaceVerts.apply(
         face_verts, mesh_to_face_first_idx, num_faces_per_mesh, clipped_faces_neighbor_idx, im_size, blur_radius,
         faces_per_pixel, bin_size, max_faces_per_bin, perspective_correct, clip_barycentric_coords, cull_backfaces)
 
-    if clipped_faces is not None:
-        # express face indices and barycentrics in terms of the original, unclipped faces
-        # (rasterize_meshes.py:239-249 of the reference)
-        pix_to_face, barycentric_coords = convert_clipped_rasterization_to_original_faces(
-            pix_to_face, barycentric_coords, clipped_faces)
+    # express face indices and barycentrics in terms of the original, unclipped faces
+    # (rasterize_meshes.py:239-249 of the reference)
+    pix_to_face, barycentric_coords = convert_clipped_rasterization_to_original_faces(
+        pix_to_face, barycentric_coords, clipped_faces)
     return pix_to_face, zbuf, barycentric_coords, dists
+
+
+class _RasterizeMeshesIndexed(torch.autograd.Function):
+    """`_RasterizeFaceVerts` fused with the face gather that precedes it: differentiable w.r.t. verts_packed."""
+
+    @staticmethod
+    def forward(ctx, verts_packed, faces_packed, mesh_to_face_first_idx, num_faces_per_mesh, image_size, blur_radius,
+                faces_per_pixel, perspective_correct, clip_barycentric_coords, cull_backfaces):
+        pix_to_face, zbuf, barycentric_coords, dists, face_verts = _C.rasterize_meshes_indexed(
+            verts_packed, faces_packed, mesh_to_face_first_idx, num_faces_per_mesh, image_size, blur_radius,
+            faces_per_pixel, perspective_correct, clip_barycentric_coords, cull_backfaces)
+        ctx.save_for_backward(face_verts, faces_packed, pix_to_face)
+        ctx.mark_non_differentiable(pix_to_face)
+        ctx.num_verts = int(verts_packed.shape[0])
+        ctx.perspective_correct = perspective_correct
+        ctx.clip_barycentric_coords = clip_barycentric_coords
+        return pix_to_face, zbuf, barycentric_coords, dists
+
+    @staticmethod
+    def backward(ctx, grad_pix_to_face, grad_zbuf, grad_barycentric_coords, grad_dists):
+        face_verts, faces_packed, pix_to_face = ctx.saved_tensors
+        grad_verts = _C.rasterize_meshes_backward_indexed(
+            face_verts, faces_packed, ctx.num_verts, pix_to_face, grad_zbuf, grad_barycentric_coords, grad_dists,
+            ctx.perspective_correct, ctx.clip_barycentric_coords)
+        return (grad_verts,) + (None,) * 9
 
 
 class _RasterizeFaceVerts(torch.autograd.Function):

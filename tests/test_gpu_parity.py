@@ -229,6 +229,40 @@ def test_mesh_autograd_wrapper(ops, dev):
     assert not p2f.requires_grad
 
 
+def test_mesh_indexed_entry_points(ops, dev):
+    """The fused (verts, faces) entry points against gather -> op -> scatter done with torch."""
+    from pytorch3d_b200 import synthetic
+    m = synthetic.torus_batch(3, 20, 14, seed=5, device=dev)
+    verts, faces = m.verts_packed(), m.faces_packed()
+    first, num = m.mesh_to_faces_packed_first_idx(), m.num_faces_per_mesh()
+    V = verts.shape[0]
+    for blur, K, persp, clip in [(0.0, 4, 0, 0), (1e-3, 3, 1, 1), (0.0, 12, 0, 0)]:
+        fv = verts[faces]
+        nb = torch.full((fv.shape[0],), -1, dtype=torch.int64, device=dev)
+        want = ops.rasterize_meshes(fv, first, num, nb, (40, 56), blur, K, 0, 0, bool(persp), bool(clip), False)
+        got = ops.rasterize_meshes_indexed(verts, faces, first, num, (40, 56), blur, K, bool(persp), bool(clip), False)
+        for a, b in zip(got[:4], want):
+            assert torch.equal(a, b)
+        assert torch.equal(got[4], fv)
+        gz, gb, gd = (t.to(dev) for t in upstream([want[1].shape, want[2].shape, want[3].shape]))
+        g_fv = ops.rasterize_meshes_backward(fv, want[0], gz, gb, gd, bool(persp), bool(clip))
+        g_want = torch.zeros(V, 3, device=dev).index_add_(0, faces.reshape(-1), g_fv.reshape(-1, 3))
+        g_got = ops.rasterize_meshes_backward_indexed(got[4], faces, V, got[0], gz, gb, gd, bool(persp), bool(clip))
+        assert (g_got - g_want).abs().max() <= 1e-4 * g_want.abs().max()
+    # a face with an out-of-range vertex index is never hit; empty inputs
+    bad = faces.clone()
+    bad[7, 1] = V + 5
+    out = ops.rasterize_meshes_indexed(verts, bad, first, num, (32, 32), 0.0, 2, False, False, False)
+    assert not (out[0] == 7).any() and torch.isnan(out[4][7, 1]).all()
+    e = ops.rasterize_meshes_indexed(verts[:0], faces[:0], first[:0], num[:0], (8, 8), 0.0, 2, False, False, False)
+    assert e[0].shape == (0, 8, 8, 2) and e[4].shape == (0, 3, 3)
+    z = ops.rasterize_meshes_indexed(verts, faces[:0], torch.zeros(1, dtype=torch.int64, device=dev),
+                                     torch.zeros(1, dtype=torch.int64, device=dev), (8, 8), 0.0, 2, False, False, False)
+    assert (z[0] == -1).all()
+    g0 = ops.rasterize_meshes_backward_indexed(z[4], faces[:0], V, z[0], z[1], z[2], z[3], False, False)
+    assert g0.shape == (V, 3) and (g0 == 0).all()
+
+
 # ------------------------------------------------------------------------------------ points
 
 POINT_MATRIX = [(2000, 2, 32, 48, 5), (5000, 1, 64, 64, 10), (3000, 3, 40, 24, 1), (3000, 1, 50, 50, 40),
