@@ -338,6 +338,14 @@ def run_ours(args, rank, local_rank, world):
                  "frac": (fine_bytes + bwd_bytes) * args.steps / (ms * 1e-3) / 1e9 / peak},
     }
 
+    # ---------------- the other single-GPU configs (device-resident; before the CUDA-graph section below)
+    others = None
+    if rank == 0 and world == 1 and not args.skip_others:
+        try:
+            others = other_workloads(dev)
+        except Exception as ex:
+            others = {"error": str(ex)}
+
     # ---------------- end to end through the public API with HOST inputs (pinned) and host results
     # Every step copies its own inputs (verts + faces) from pinned host memory and returns the gradient and the
     # loss to the host.  The loop is software-pipelined two deep, like an input pipeline that prefetches the
@@ -366,8 +374,7 @@ def run_ours(args, rank, local_rank, world):
             sl["f"].copy_(faces_h, non_blocking=True)
             sl["copied"].record(copier)
 
-    def enqueue_compute(sl):
-        compute.wait_event(sl["copied"])
+    def step_body(sl):
         v = sl["v"].detach().requires_grad_(True)
         m = _DeviceMeshes(v, sl["f"], first, num, max_f)
         p2f, zbuf, bary, dists = rasterize_meshes(m, size, blur_radius=blur, faces_per_pixel=K)
@@ -375,8 +382,29 @@ def run_ours(args, rank, local_rank, world):
         loss.backward()
         sl["grad_h"].copy_(v.grad, non_blocking=True)
         sl["loss_h"].copy_(loss.detach(), non_blocking=True)
+
+    def enqueue_compute(sl):
+        compute.wait_event(sl["copied"])
+        if sl.get("graph") is not None:
+            sl["graph"].replay()  # the same public-API calls, captured once per slot in a CUDA graph
+        else:
+            step_body(sl)
         sl["free"].record(compute)
         sl["done"].record(compute)
+
+    def capture_graphs():
+        """The step (public API forward + loss + backward + D2H) captured in one CUDA graph per input slot: the
+        host then issues one launch per step instead of ~60."""
+        for sl in slots:
+            sl["v"].copy_(verts_h)
+            sl["f"].copy_(faces_h)
+        torch.cuda.synchronize(dev)
+        for sl in slots:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step_body(sl)
+            sl["graph"] = g
+        torch.cuda.synchronize(dev)
 
     def run_e2e(n, pipelined):
         out = 0.0
@@ -403,7 +431,8 @@ def run_ours(args, rank, local_rank, world):
 
     n_e2e = max(3, min(args.steps, 50))
     e2e_rates = {}
-    for pipelined in (False, True):
+
+    def time_e2e(pipelined):
         run_e2e(min(args.warmup, 5) or 1, pipelined)
         torch.cuda.synchronize(dev)
         barrier()
@@ -414,18 +443,34 @@ def run_ours(args, rank, local_rank, world):
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e_rates[pipelined] = world * nm * n_e2e / float(dt.item())
+        return world * nm * n_e2e / float(dt.item())
+
+    e2e_rates["serial"] = time_e2e(False)
+    e2e_rates["pipelined"] = time_e2e(True)
+    graph_note = None
+    try:
+        capture_graphs()
+        e2e_rates["pipelined+graph"] = time_e2e(True)
+    except Exception as ex:  # report, do not hide: the eager numbers above stand on their own
+        graph_note = "CUDA graph capture failed: %s" % str(ex)[:200]
+        for sl in slots:
+            sl["graph"] = None
+    for sl in slots:
+        sl["graph"] = None
+    best = max(e2e_rates, key=lambda k: e2e_rates[k] if k != "serial" else 0.0)
     e2e = {
-        "value": e2e_rates[True], "unit": UNIT,
+        "value": e2e_rates[best], "unit": UNIT,
         "h2d_bytes_per_step": int(verts_h.numel() * 4 + faces_h.numel() * 8),
         "d2h_bytes_per_step": int(verts_h.numel() * 4 + 4),
-        "steps": n_e2e,
-        "serial_value": e2e_rates[False],
+        "steps": n_e2e, "mode": best, "modes": e2e_rates,
         "what": "pytorch3d_b200.rasterize_meshes(meshes) + loss.backward(): verts/faces H2D from pinned host "
-                "memory, gradient w.r.t. verts and the loss D2H, every step; fragments stay on the device; "
-                "2-deep pipeline (next step's H2D on a copy stream, results read one step late); serial_value = "
-                "the same without any overlap between steps",
+                "memory, gradient w.r.t. verts and the loss D2H, every step; fragments stay on the device. "
+                "serial = no overlap between steps; pipelined = next step's H2D on a copy stream, results read "
+                "one step late; +graph = the step's launches replayed from a CUDA graph captured from the same "
+                "public-API calls",
     }
+    if graph_note:
+        e2e["note"] = graph_note
 
     # ---------------- the same through the host-buffer C ABI (all fragments to the host)
     e2e_abi = None
@@ -473,13 +518,6 @@ def run_ours(args, rank, local_rank, world):
                   "bytes_gathered_per_rank_per_step": int(bytes_per_rank * world),
                   "what": "same step with every rank all-gathering all four Fragments tensors of all ranks "
                           "(all_gather_into_tensor, NCCL) between forward and backward"}
-
-    others = None
-    if rank == 0 and world == 1 and not args.skip_others:
-        try:
-            others = other_workloads(dev)
-        except Exception as ex:
-            others = {"error": str(ex)}
 
     if rank == 0:
         line = {

@@ -45,16 +45,14 @@ __device__ __forceinline__ void face_box(const Face& f, float sqrt_blur, float& 
   ymax = fadd(fmaxf(fmaxf(f.y0, f.y1), f.y2), sqrt_blur);
 }
 
-// Per-face records (workspace, written once per forward call by the setup pass, read by the fine pass): the
-// constants of a face that every (tile, face) pair would otherwise recompute.  One 16-byte word per array.
-struct FaceRecords {
-  float4* a;    // x0, y0, x1, y1
-  float4* b;    // x2, y2, barycentric denominator, face index (int bits)
-  float4* c;    // z0, z1, z2, clipped-face neighbour index (int bits, -1 = none)
-  float4* box;  // xmin, xmax, ymin, ymax (blur-expanded; empty = never hit)
-  int4* rng;    // xo_lo, xo_hi, yo_lo, yo_hi: the OUTPUT pixels whose centre passes the reference's box test
-};
-constexpr size_t FACE_RECORD_BYTES = 5 * 16;
+// Per-face records (workspace, written once per forward call by the setup pass, gathered by the fine pass): the
+// constants of a face that every (tile, face) pair would otherwise recompute.  Four 16-byte words per face:
+//   [0] x0, y0, x1, y1
+//   [1] x2, y2, barycentric denominator, face index (int bits)
+//   [2] z0, z1, z2, clipped-face neighbour index (int bits, -1 = none)
+//   [3] blur_radius == 0: xo_lo, xo_hi, yo_lo, yo_hi (int): the OUTPUT pixels whose centre passes the reference's
+//       box test;  blur_radius > 0: xmin, xmax, ymin, ymax of the blur-expanded box (empty = never hit)
+constexpr size_t FACE_RECORD_BYTES = 4 * 16;
 
 // Exact pixel range of the box test `p > vmax || p < vmin` (rasterize_meshes.cu:94-97): pix_to_ndc is monotonic
 // in the pixel index, so the passing pixels are contiguous; start from the conservative range and trim the ends.
@@ -82,7 +80,7 @@ __global__ void __launch_bounds__(SETUP_FACES)
                             const int64_t* __restrict__ neighbor, int64_t F, const int64_t* __restrict__ first,
                             const int64_t* __restrict__ num, int N, int H, int W, int TY, int TX, float rx, float ry,
                             float sqrt_blur, int cull_backfaces, uint4* __restrict__ rect,
-                            int* __restrict__ tile_count, const FaceRecords rec) {
+                            int* __restrict__ tile_count, float4* __restrict__ rec) {
   __shared__ __align__(16) float s_fv[SETUP_FACES * 9];
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x;
@@ -132,11 +130,13 @@ __global__ void __launch_bounds__(SETUP_FACES)
     rect[fi] = make_uint4(r.x, r.y, (uint32_t)max(n, 0), 0u);
     // the reference reads the int64 neighbour index into an int (rasterize_meshes.cu:186)
     const int nb = neighbor ? (int)__ldg(neighbor + fi) : -1;
-    rec.a[fi] = make_float4(f.x0, f.y0, f.x1, f.y1);
-    rec.b[fi] = make_float4(f.x2, f.y2, bary_denominator(f), __int_as_float((int)fi));
-    rec.c[fi] = make_float4(f.z0, f.z1, f.z2, __int_as_float(nb));
-    rec.box[fi] = box;
-    rec.rng[fi] = rng;
+    float4* out = rec + fi * 4;
+    out[0] = make_float4(f.x0, f.y0, f.x1, f.y1);
+    out[1] = make_float4(f.x2, f.y2, bary_denominator(f), __int_as_float((int)fi));
+    out[2] = make_float4(f.z0, f.z1, f.z2, __int_as_float(nb));
+    out[3] = sqrt_blur > 0.0f ? box
+                              : make_float4(__int_as_float(rng.x), __int_as_float(rng.y), __int_as_float(rng.z),
+                                            __int_as_float(rng.w));
   }
   warp_count_rect(r, n, TY, TX, tile_count, tid & 31);  // all lanes participate
 }
@@ -318,12 +318,14 @@ __device__ __forceinline__ void out_store(T* ptr, const T v) {
 struct FineParams {
   const float* face_verts;
   const int64_t* neighbor;  // clipped_faces_neighbor_idx or nullptr
-  FaceRecords rec;
+  const float4* rec;
   const int64_t* first;
   const int64_t* num;
   const int* tile_offset;
   const int* pairs;
   int64_t capacity;
+  int* work_counter;  // tiles claimed so far by the persistent fine kernel (zeroed by the scan pass)
+  int ntiles;
   int N, H, W, K, TY, TX;
   float rx, ry, blur_radius, sqrt_blur;
   int persp, clip, cull;
@@ -374,6 +376,37 @@ struct FineShared {
   float4 pay[KMAX * TILE_THREADS];              // queue payload: (signed dist, bary0, bary1, bary2) per slot
   float col[TILE], row[TILE];                   // NDC coordinates of the tile's 16 pixel columns / rows
 };
+
+// Full-sector output stores.  A pixel's K values of one buffer are P 16-byte pieces; the pixels of two adjacent
+// lanes (x, x+1 of the same row) are adjacent in memory, a run of 2P pieces.  Written lane-by-lane, every store
+// instruction would fill only half of each 32-byte sector it touches (the other half comes with a later
+// instruction): twice the L1->L2 write transactions.  Instead the two lanes exchange half of their pieces with
+// one shuffle round per two pieces, so that in instruction j the even lane writes piece 2j and the odd lane
+// piece 2j+1 of the run -- whole sectors.  `mine` = this lane's P pieces; `run` = start of the pair's run;
+// vA / vB = whether the even / odd lane's pixel exists (partial tiles).
+template <int P>
+__device__ __forceinline__ void store_pair_run(float4* run, const float4 (&mine)[P], int odd, bool vA, bool vB) {
+  constexpr int H = P / 2;           // pieces received from the partner
+  constexpr int CE = (P + 1) / 2;    // first instruction whose even-lane piece belongs to the odd lane's pixel
+  float4 recv[H > 0 ? H : 1];
+#pragma unroll
+  for (int r = 0; r < H; ++r) {
+    // the odd lane needs A[2r+1]; the even lane needs B[2 * (CE + r) - P]
+    const float4 send = odd ? mine[2 * (CE + r) - P] : mine[2 * r + 1];
+    recv[r].x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+    recv[r].y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+    recv[r].z = __shfl_xor_sync(0xffffffffu, send.z, 1);
+    recv[r].w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+  }
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    // even lane: run piece 2j (its own while 2j < P); odd lane: run piece 2j+1 (its own once 2j+1 >= P)
+    const float4 ve = 2 * j < P ? mine[2 * j < P ? 2 * j : 0] : recv[j >= CE ? j - CE : 0];
+    const float4 vo = 2 * j + 1 < P ? recv[2 * j + 1 < P ? j : 0] : mine[2 * j + 1 >= P ? 2 * j + 1 - P : 0];
+    const bool target_a = odd ? (2 * j + 1 < P) : (2 * j < P);
+    if (target_a ? vA : vB) out_store(run + 2 * j + odd, odd ? vo : ve);
+  }
+}
 
 // A tile no face touches: all of its outputs are -1.  Full tiles are written as whole 16-pixel row segments
 // (consecutive lanes -> consecutive 16 bytes) without computing anything per pixel.
@@ -461,18 +494,20 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
     __syncthreads();  // previous chunk fully consumed
     if (tid < nc) {
       const int f = overflow ? (int)(mesh_first + base + tid) : p.pairs[seg_begin + base + tid];
-      const float4 ra = __ldg(p.rec.a + f), rb = __ldg(p.rec.b + f), rc = __ldg(p.rec.c + f);
+      const float4* r = p.rec + (int64_t)f * 4;
+      const float4 ra = __ldg(r + 0), rb = __ldg(r + 1), rc = __ldg(r + 2), rd = __ldg(r + 3);
       sh.a[tid] = ra;
       sh.b[tid] = rb;
       sh.c[tid] = rc;
       if (scan) {
-        const int4 g = __ldg(p.rec.rng + f);
-        const int c_lo = max(g.x - tile_x * TILE, 0), c_hi = min(g.y - tile_x * TILE, TILE - 1);
-        const int r_lo = max(g.z - tile_y * TILE, 0), r_hi = min(g.w - tile_y * TILE, TILE - 1);
+        const int gx = __float_as_int(rd.x), gy = __float_as_int(rd.y), gz = __float_as_int(rd.z),
+                  gw = __float_as_int(rd.w);
+        const int c_lo = max(gx - tile_x * TILE, 0), c_hi = min(gy - tile_x * TILE, TILE - 1);
+        const int r_lo = max(gz - tile_y * TILE, 0), r_hi = min(gw - tile_y * TILE, TILE - 1);
         sh.rng[tid] = (c_lo > c_hi || r_lo > r_hi) ? 1u  // empty: c_lo = 1 > c_hi = 0
                                                    : (unsigned)(c_lo | (c_hi << 8) | (r_lo << 16) | (r_hi << 24));
       } else {
-        sh.u.box[tid] = __ldg(p.rec.box + f);
+        sh.u.box[tid] = rd;
       }
     }
     if (scan) {
@@ -498,16 +533,28 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
         const bool pos = fb.z > 0.0f;
         unsigned* mrow = sh.u.mask[fslot >> 5];
         const unsigned bit = 1u << (fslot & 31);
+        // edge_fn(q; a, b) = fma(q.x - a.x, b.y - a.y, -rn((q.y - a.y) * (b.x - a.x))): the differences of the
+        // face's own vertices are per-face constants, the rounded product is a per-row constant
+        const float dx0 = fsub(fb.x, fa.z), dy0 = fsub(fb.y, fa.w);  // v2 - v1
+        const float dx1 = fsub(fa.x, fb.x), dy1 = fsub(fa.y, fb.y);  // v0 - v2
+        const float dx2 = fsub(fa.z, fa.x), dy2 = fsub(fa.w, fa.y);  // v1 - v0
         for (int r = r_lo + dr; r <= r_hi; r += 4) {
           const float qy = sh.row[r];
-          for (int c = c_lo; c <= c_hi; ++c) {
-            const float qx = sh.col[c];
-            const float e0 = edge_fn(qx, qy, fa.z, fa.w, fb.x, fb.y);  // E(p; v1, v2)
-            const float e1 = edge_fn(qx, qy, fb.x, fb.y, fa.x, fa.y);  // E(p; v2, v0)
-            const float e2 = edge_fn(qx, qy, fa.x, fa.y, fa.z, fa.w);  // E(p; v0, v1)
-            const bool ok = pos ? (e0 > 0.0f && e1 > 0.0f && e2 > 0.0f) : (e0 < 0.0f && e1 < 0.0f && e2 < 0.0f);
-            // thread that owns pixel (r, c): warp = footprint (r / 4, c / 8), lane = (r % 4, c % 8)
-            if (ok) atomicOr(&mrow[((r >> 2) * 2 + (c >> 3)) * 32 + (r & 3) * 8 + (c & 7)], bit);
+          const float t0 = fmul(fsub(qy, fa.w), dx0), t1 = fmul(fsub(qy, fb.y), dx1), t2 = fmul(fsub(qy, fa.y), dx2);
+          unsigned* mpix = mrow + (r >> 2) * 64 + (r & 3) * 8;  // thread of pixel (r, c): + (c / 8) * 32 + c % 8
+          for (int c0 = c_lo; c0 <= c_hi; c0 += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // four columns in flight
+              const int c = c0 + u;
+              if (c <= c_hi) {
+                const float qx = sh.col[c];
+                const float e0 = ffma(fsub(qx, fa.z), dy0, -t0);  // E(p; v1, v2)
+                const float e1 = ffma(fsub(qx, fb.x), dy1, -t1);  // E(p; v2, v0)
+                const float e2 = ffma(fsub(qx, fa.x), dy2, -t2);  // E(p; v0, v1)
+                const bool ok = pos ? (e0 > 0.0f && e1 > 0.0f && e2 > 0.0f) : (e0 < 0.0f && e1 < 0.0f && e2 < 0.0f);
+                if (ok) atomicOr(mpix + (c >> 3) * 32 + (c & 7), bit);
+              }
+            }
           }
         }
       }
@@ -573,37 +620,67 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
     }
   }
 
-  if (!valid) return;
   int slot[KMAX];
   q.sort(slot);
   // ---- epilogue: every output is written with 16-byte stores (all K slots, including the -1 padding)
   const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
-  if (K == KMAX && (KMAX % 4) == 0) {
-    longlong2* pf = reinterpret_cast<longlong2*>(p.pix_to_face + o);
+  if constexpr ((KMAX % 4) == 0) {
+   if (K == KMAX) {
+    // lanes 2m / 2m+1 own horizontally adjacent pixels: they write their two pixels' runs together
+    const int odd = lane & 1;
+    const bool vA = __shfl_sync(0xffffffffu, (int)valid, lane & ~1) != 0;
+    const bool vB = __shfl_sync(0xffffffffu, (int)valid, lane | 1) != 0;
+    const int64_t oa = o - (int64_t)odd * KMAX;  // the even lane's pixel
+    {
+      // pix_to_face: int64, but the values are the queue's int32 face ids: exchange those, widen at the store
+      float4 piece[KMAX / 2];
 #pragma unroll
-    for (int k = 0; k < KMAX; k += 2) {
-      const long long i0 = k >= q.size ? -1ll : (long long)q.id[k];
-      const long long i1 = k + 1 >= q.size ? -1ll : (long long)q.id[k + 1];
-      out_store(pf + k / 2, make_longlong2(i0, i1));
-    }
-#pragma unroll
-    for (int k0 = 0; k0 + 3 < KMAX; k0 += 4) {
-      float4 w[4];
-      float zz[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool e = k0 + u >= q.size;
-        w[u] = e ? make_float4(-1.f, -1.f, -1.f, -1.f) : pay[slot[k0 + u] * TILE_THREADS];
-        zz[u] = e ? -1.0f : q.z[k0 + u];
+      for (int k = 0; k < KMAX; k += 2) {
+        const long long i0 = k >= q.size ? -1ll : (long long)q.id[k];
+        const long long i1 = k + 1 >= q.size ? -1ll : (long long)q.id[k + 1];
+        piece[k / 2] = make_float4(__int_as_float((int)(i0 & 0xffffffffll)), __int_as_float((int)(i0 >> 32)),
+                                   __int_as_float((int)(i1 & 0xffffffffll)), __int_as_float((int)(i1 >> 32)));
       }
-      out_store(reinterpret_cast<float4*>(p.zbuf + o) + k0 / 4, make_float4(zz[0], zz[1], zz[2], zz[3]));
-      out_store(reinterpret_cast<float4*>(p.dists + o) + k0 / 4, make_float4(w[0].x, w[1].x, w[2].x, w[3].x));
-      float4* pb = reinterpret_cast<float4*>(p.bary + o * 3) + 3 * (k0 / 4);
-      out_store(pb + 0, make_float4(w[0].y, w[0].z, w[0].w, w[1].y));
-      out_store(pb + 1, make_float4(w[1].z, w[1].w, w[2].y, w[2].z));
-      out_store(pb + 2, make_float4(w[2].w, w[3].y, w[3].z, w[3].w));
+      store_pair_run<KMAX / 2>(reinterpret_cast<float4*>(p.pix_to_face + oa), piece, odd, vA, vB);
     }
-  } else {
+    {
+      float4 piece[KMAX / 4];
+#pragma unroll
+      for (int k0 = 0; k0 < KMAX; k0 += 4)
+        piece[k0 / 4] = make_float4(k0 + 0 >= q.size ? -1.0f : q.z[k0 + 0], k0 + 1 >= q.size ? -1.0f : q.z[k0 + 1],
+                                    k0 + 2 >= q.size ? -1.0f : q.z[k0 + 2], k0 + 3 >= q.size ? -1.0f : q.z[k0 + 3]);
+      store_pair_run<KMAX / 4>(reinterpret_cast<float4*>(p.zbuf + oa), piece, odd, vA, vB);
+    }
+    {
+      float4 piece[KMAX / 4];
+#pragma unroll
+      for (int k0 = 0; k0 < KMAX; k0 += 4) {
+        float d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d[u] = k0 + u >= q.size ? -1.0f : pay[slot[k0 + u] * TILE_THREADS].x;
+        piece[k0 / 4] = make_float4(d[0], d[1], d[2], d[3]);
+      }
+      store_pair_run<KMAX / 4>(reinterpret_cast<float4*>(p.dists + oa), piece, odd, vA, vB);
+    }
+    {
+      float4 piece[3 * KMAX / 4];
+#pragma unroll
+      for (int k0 = 0; k0 < KMAX; k0 += 4) {
+        float4 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          w[u] = k0 + u >= q.size ? make_float4(-1.f, -1.f, -1.f, -1.f) : pay[slot[k0 + u] * TILE_THREADS];
+        piece[3 * (k0 / 4) + 0] = make_float4(w[0].y, w[0].z, w[0].w, w[1].y);
+        piece[3 * (k0 / 4) + 1] = make_float4(w[1].z, w[1].w, w[2].y, w[2].z);
+        piece[3 * (k0 / 4) + 2] = make_float4(w[2].w, w[3].y, w[3].z, w[3].w);
+      }
+      store_pair_run<3 * KMAX / 4>(reinterpret_cast<float4*>(p.bary + oa * 3), piece, odd, vA, vB);
+    }
+    return;
+   }
+  }
+  if (!valid) return;
+  {
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       if (k < K) {
@@ -991,7 +1068,7 @@ using namespace b200r;
 extern "C" size_t b200r_rasterize_meshes_workspace_bytes(int64_t F, int32_t N, int32_t H, int32_t W,
                                                          int64_t pair_capacity) {
   if (F < 0 || N < 0 || H < 0 || W < 0) return 0;
-  return carve_workspace(nullptr, F, N, H, W, pair_capacity).bytes + FACE_RECORD_BYTES * (size_t)(F > 0 ? F : 1);
+  return carve_workspace(nullptr, F, N, H, W, pair_capacity).bytes + FACE_RECORD_BYTES * (size_t)(F > 0 ? F : 1) + 16;
 }
 
 static int forward_impl(const float* face_verts, const float* verts, int64_t V, const int64_t* faces,
@@ -1011,14 +1088,10 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
   if (ntiles > INT_MAX) return fail(B200R_ERR_INVALID_ARGUMENT, "too many tiles");
   BinWorkspace ws = carve_workspace(workspace, F, N, H, W, pair_capacity);
   const size_t nrec = (size_t)(F > 0 ? F : 1);
-  if (workspace == nullptr || workspace_bytes < ws.bytes + FACE_RECORD_BYTES * nrec)
+  if (workspace == nullptr || workspace_bytes < ws.bytes + FACE_RECORD_BYTES * nrec + 16)
     return fail(B200R_ERR_WORKSPACE, "workspace too small for rasterize_meshes_forward");
-  FaceRecords rec;  // (ws.bytes is a multiple of 16)
-  rec.a = reinterpret_cast<float4*>(static_cast<char*>(workspace) + ws.bytes);
-  rec.b = rec.a + nrec;
-  rec.c = rec.b + nrec;
-  rec.box = rec.c + nrec;
-  rec.rng = reinterpret_cast<int4*>(rec.box + nrec);
+  float4* rec = reinterpret_cast<float4*>(static_cast<char*>(workspace) + ws.bytes);  // (ws.bytes % 16 == 0)
+  int* work_counter = reinterpret_cast<int*>(rec + 4 * nrec);
 
   const float rx = ndc_range(W, H), ry = ndc_range(H, W);
   const float sqrt_blur = sqrtf(blur_radius);  // IEEE sqrt, like the device sqrt.rn of the reference
@@ -1040,7 +1113,7 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
     }
     B200R_LAUNCHED("mesh_setup_count_kernel");
   }
-  tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles);
+  tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles, work_counter);
   B200R_LAUNCHED("tile_scan_kernel");
   if (F > 0) {
     tile_fill_kernel<<<(unsigned)((F + 255) / 256), 256, 0, stream>>>(ws.rect, F, TY, TX, ws.tile_count, ws.pairs,
@@ -1057,6 +1130,8 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
   p.face_verts = face_verts;
   p.neighbor = neighbor;
   p.rec = rec;
+  p.work_counter = work_counter;
+  p.ntiles = (int)ntiles;
   p.first = first;
   p.num = num;
   p.tile_offset = ws.tile_offset;
