@@ -79,16 +79,11 @@ __device__ __forceinline__ void warp_count_rect(uint2 r, int n, int TY, int TX, 
 // Exclusive scan of `counts[0..n)` into `offsets[0..n]` by one CTA of 1024 threads, 8192 elements per sweep
 // (eight coalesced loads in flight per thread, then eight block-wide shuffle scans).  `counts` is overwritten
 // with the segment starts as well: it becomes the array of fill cursors.
-// `zero_me` (optional): a work counter of the fine pass that this launch resets.
-static __global__ void __launch_bounds__(1024)
-    tile_scan_kernel(int* __restrict__ counts, int* __restrict__ offsets, int n, int* __restrict__ zero_me) {
+static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict__ counts, int* __restrict__ offsets, int n) {
   __shared__ long long warp_sums[32];
   __shared__ long long carry_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) {
-    carry_s = 0;
-    if (zero_me) *zero_me = 0;
-  }
+  if (tid == 0) carry_s = 0;
   __syncthreads();
   // 64-bit running sums, saturated to INT_MAX on output: a batch whose (tile, element) pairs would overflow
   // int32 simply marks the remaining tiles as "does not fit" (they rasterise from the whole mesh range).

@@ -77,12 +77,4 @@ __device__ __forceinline__ void cta_load_words(float* dst, const float* src, int
   __syncthreads();
 }
 
-// Per-thread asynchronous 16-byte copies global -> shared (cp.async, SASS: LDGSTS): the data never passes through
-// registers, so a gather issued early costs nothing until the matching wait.
-__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src_gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 }  // namespace b200r

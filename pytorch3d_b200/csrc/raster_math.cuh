@@ -94,7 +94,10 @@ __device__ __forceinline__ void bary_clip(float& w0, float& w1, float& w2) {
 __device__ __forceinline__ float point_line_dist(float px, float py, float ax, float ay, float bx, float by) {
   const float bax = fsub(bx, ax), bay = fsub(by, ay);
   const float l2 = dot2(bax, bay, bax, bay);
-  if ((double)l2 <= kEps) {
+  // the reference compares in double: (double)l2 <= 1e-8.  For a float l2 that is the same as l2 <= 1e-8f, because
+  // 1e-8f (9.99999994e-9) is the largest float that is <= 1e-8 -- one FSETP instead of a conversion and a DSETP
+  static_assert((double)1e-8f <= 1e-8, "1e-8f must round below 1e-8");
+  if (l2 <= 1e-8f) {
     const float dx = fsub(px, bx), dy = fsub(py, by);
     return sqnorm2(dx, dy);
   }

@@ -324,8 +324,7 @@ struct FineParams {
   const int* tile_offset;
   const int* pairs;
   int64_t capacity;
-  int* work_counter;  // tiles claimed so far by the persistent fine kernel (zeroed by the scan pass)
-  int ntiles;
+  int n0;  // first image of this launch (grid.z is limited to 65535 images)
   int N, H, W, K, TY, TX;
   float rx, ry, blur_radius, sqrt_blur;
   int persp, clip, cull;
@@ -457,9 +456,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
   FineShared<KMAX>& sh = *reinterpret_cast<FineShared<KMAX>*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31;
   float4* pay = sh.pay + tid;
-  const int t = blockIdx.x;
-  const int n = t / (p.TY * p.TX);
-  const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
+  // grid = (tiles per row, tile rows, images): no integer divisions to find the tile
+  const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = p.n0 + blockIdx.z;
+  const int t = (n * p.TY + tile_y) * p.TX + tile_x;
   // the tile's face list; tiles whose segment did not fit the pair buffer test every face of the mesh
   const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
   const bool overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
@@ -473,12 +472,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
   int xo, yo;
   thread_pixel(tile_x, tile_y, xo, yo);
   const bool valid = xo < p.W && yo < p.H;
-  const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
-  const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
-  {  // coordinate tables of the tile (local column c = xo - 16*tile_x, local row r = yo - 16*tile_y)
-    const int c = xo - tile_x * TILE, r = yo - tile_y * TILE;
-    if (r == 0) sh.col[c] = px;
-    if (c == 0) sh.row[r] = py;
+  const int lc = xo - tile_x * TILE, lr = yo - tile_y * TILE;  // local column / row of my pixel
+  // NDC coordinates of the tile's 16 pixel columns and rows (two IEEE divisions each): computed once per tile
+  // by 32 threads, read by every thread after the barriers of the first chunk
+  if (tid < 2 * TILE) {
+    const int i = tid & (TILE - 1);
+    if (tid < TILE)
+      sh.col[i] = pix_to_ndc(p.W - 1 - (tile_x * TILE + i), p.W, p.rx);
+    else
+      sh.row[i] = pix_to_ndc(p.H - 1 - (tile_y * TILE + i), p.H, p.ry);
   }
 
   TopK<KMAX> q;
@@ -560,6 +562,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
       }
       __syncthreads();
       // every pixel walks its own candidates, in ascending face order
+      const float px = sh.col[lc], py = sh.row[lr];
       for (int w = 0; w < nwords; ++w) {
         unsigned m = sh.u.mask[w][tid];
         while (m != 0u) {
@@ -581,6 +584,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
       }
       continue;  // chunk done
     }
+    const float px = sh.col[lc], py = sh.row[lr];
     for (int sub = 0; sub < nc; sub += ROUND) {
       // ---- pass A: 64-bit mask of the faces of this round whose box contains my pixel
       unsigned m0 = 0, m1 = 0;
@@ -589,9 +593,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
         // that they do not occupy 12 registers during pass B and the epilogue
         float col[8], row[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) col[c] = __shfl_sync(0xffffffffu, px, c);
+        for (int c = 0; c < 8; ++c) col[c] = sh.col[(lc & 8) + c];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) row[r] = __shfl_sync(0xffffffffu, py, 8 * r);
+        for (int r = 0; r < 4; ++r) row[r] = sh.row[(lr & 12) + r];
         if (sub + lane < nc) m0 = box_pixel_mask(sh.u.box[sub + lane], col, row);
         if (sub + 32 + lane < nc) m1 = box_pixel_mask(sh.u.box[sub + 32 + lane], col, row);
       }
@@ -839,6 +843,7 @@ struct BackwardParams {
   const float* grad_bary;
   const float* grad_dists;
   int N, H, W, K, TY, TX;
+  int n0;  // first image of this launch
   float rx, ry;
   int persp, clip;
   float* grad_face_verts;
@@ -988,10 +993,8 @@ __device__ __forceinline__ void warp_scatter(float* __restrict__ grad_face_verts
 // (a pixel with no face costs nothing else); KV == 0: any K, scalar loads.
 template <int KV>
 __global__ void __launch_bounds__(TILE_THREADS) mesh_backward_kernel(const BackwardParams p) {
-  const int t = blockIdx.x;
   const int lane = threadIdx.x & 31;
-  const int n = t / (p.TY * p.TX);
-  const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
+  const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = p.n0 + blockIdx.z;  // grid = (TX, TY, images)
   int xo, yo;
   thread_pixel(tile_x, tile_y, xo, yo);
   const bool in_image = xo < p.W && yo < p.H;
@@ -1068,7 +1071,7 @@ using namespace b200r;
 extern "C" size_t b200r_rasterize_meshes_workspace_bytes(int64_t F, int32_t N, int32_t H, int32_t W,
                                                          int64_t pair_capacity) {
   if (F < 0 || N < 0 || H < 0 || W < 0) return 0;
-  return carve_workspace(nullptr, F, N, H, W, pair_capacity).bytes + FACE_RECORD_BYTES * (size_t)(F > 0 ? F : 1) + 16;
+  return carve_workspace(nullptr, F, N, H, W, pair_capacity).bytes + FACE_RECORD_BYTES * (size_t)(F > 0 ? F : 1);
 }
 
 static int forward_impl(const float* face_verts, const float* verts, int64_t V, const int64_t* faces,
@@ -1088,10 +1091,9 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
   if (ntiles > INT_MAX) return fail(B200R_ERR_INVALID_ARGUMENT, "too many tiles");
   BinWorkspace ws = carve_workspace(workspace, F, N, H, W, pair_capacity);
   const size_t nrec = (size_t)(F > 0 ? F : 1);
-  if (workspace == nullptr || workspace_bytes < ws.bytes + FACE_RECORD_BYTES * nrec + 16)
+  if (workspace == nullptr || workspace_bytes < ws.bytes + FACE_RECORD_BYTES * nrec)
     return fail(B200R_ERR_WORKSPACE, "workspace too small for rasterize_meshes_forward");
   float4* rec = reinterpret_cast<float4*>(static_cast<char*>(workspace) + ws.bytes);  // (ws.bytes % 16 == 0)
-  int* work_counter = reinterpret_cast<int*>(rec + 4 * nrec);
 
   const float rx = ndc_range(W, H), ry = ndc_range(H, W);
   const float sqrt_blur = sqrtf(blur_radius);  // IEEE sqrt, like the device sqrt.rn of the reference
@@ -1113,7 +1115,7 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
     }
     B200R_LAUNCHED("mesh_setup_count_kernel");
   }
-  tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles, work_counter);
+  tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles);
   B200R_LAUNCHED("tile_scan_kernel");
   if (F > 0) {
     tile_fill_kernel<<<(unsigned)((F + 255) / 256), 256, 0, stream>>>(ws.rect, F, TY, TX, ws.tile_count, ws.pairs,
@@ -1130,8 +1132,7 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
   p.face_verts = face_verts;
   p.neighbor = neighbor;
   p.rec = rec;
-  p.work_counter = work_counter;
-  p.ntiles = (int)ntiles;
+  p.n0 = 0;
   p.first = first;
   p.num = num;
   p.tile_offset = ws.tile_offset;
@@ -1154,7 +1155,10 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
                                          (int)sizeof(FineShared<KM>)));                                  \
       if (dev_ >= 0 && dev_ < 64) configured[dev_] = true;                                               \
     }                                                                                                    \
-    mesh_fine_kernel<KM, NBV, SC><<<grid, TILE_THREADS, sizeof(FineShared<KM>), stream>>>(p);            \
+    for (p.n0 = 0; p.n0 < N; p.n0 += 65535) {                                                            \
+      const dim3 grid3((unsigned)TX, (unsigned)TY, (unsigned)min(N - p.n0, 65535));                      \
+      mesh_fine_kernel<KM, NBV, SC><<<grid3, TILE_THREADS, sizeof(FineShared<KM>), stream>>>(p);         \
+    }                                                                                                    \
   } while (0)
 #define B200R_FINE(KM)                   \
   do {                                   \
@@ -1246,13 +1250,15 @@ extern "C" int b200r_rasterize_meshes_backward(const float* face_verts, int64_t 
   p.grad_face_verts = grad_face_verts;
   const bool prof = profiling_enabled();
   if (prof) phase_timer().record(3, stream);
-  const unsigned bgrid = (unsigned)((int64_t)N * TY * TX);
-  if (K == 8)
-    mesh_backward_kernel<8><<<bgrid, TILE_THREADS, 0, stream>>>(p);
-  else if (K == 4)
-    mesh_backward_kernel<4><<<bgrid, TILE_THREADS, 0, stream>>>(p);
-  else
-    mesh_backward_kernel<0><<<bgrid, TILE_THREADS, 0, stream>>>(p);
+  for (p.n0 = 0; p.n0 < N; p.n0 += 65535) {  // grid.z is limited to 65535 images per launch
+    const dim3 bgrid((unsigned)TX, (unsigned)TY, (unsigned)min(N - p.n0, 65535));
+    if (K == 8)
+      mesh_backward_kernel<8><<<bgrid, TILE_THREADS, 0, stream>>>(p);
+    else if (K == 4)
+      mesh_backward_kernel<4><<<bgrid, TILE_THREADS, 0, stream>>>(p);
+    else
+      mesh_backward_kernel<0><<<bgrid, TILE_THREADS, 0, stream>>>(p);
+  }
   B200R_LAUNCHED("mesh_backward_kernel");
   if (prof) {
     phase_timer().record(4, stream);

@@ -464,7 +464,7 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
         points, radius, P, first, num, N, H, W, TY, TX, rx, ry, ws.rect, ws.tile_count);
     B200R_LAUNCHED("points_setup_count_kernel");
   }
-  tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles, nullptr);
+  tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles);
   B200R_LAUNCHED("tile_scan_kernel");
   if (P > 0) {
     tile_fill_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(ws.rect, P, TY, TX, ws.tile_count, ws.pairs,
