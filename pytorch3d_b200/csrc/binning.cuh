@@ -87,45 +87,48 @@ static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict_
   __syncthreads();
   // 64-bit running sums, saturated to INT_MAX on output: a batch whose (tile, element) pairs would overflow
   // int32 simply marks the remaining tiles as "does not fit" (they rasterise from the whole mesh range).
+  // Every thread owns 8 CONSECUTIVE elements: it scans them in registers, the block scans the 1024 thread
+  // totals once (two barriers per sweep of 8192 elements).
   for (int base = 0; base < n; base += 8192) {
+    const int i0 = base + tid * 8;
     int v[8];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int i = base + it * 1024 + tid;
-      v[it] = i < n ? counts[i] : 0;
-    }
+    for (int j = 0; j < 8; ++j) v[j] = i0 + j < n ? counts[i0 + j] : 0;
+    long long total = 0;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      long long inc = v[it];
+    for (int j = 0; j < 8; ++j) total += v[j];
+    long long inc = total;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      long long w = warp_sums[lane];
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const long long t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
+        const long long t = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += t;
       }
-      if (lane == 31) warp_sums[wid] = inc;
-      __syncthreads();
-      if (wid == 0) {
-        long long w = warp_sums[lane];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const long long t = __shfl_up_sync(0xffffffffu, w, d);
-          if (lane >= d) w += t;
-        }
-        warp_sums[lane] = w;
-      }
-      __syncthreads();
-      const long long carry = carry_s;
-      const long long excl = carry + inc - v[it] + (wid > 0 ? warp_sums[wid - 1] : 0);
-      const int i = base + it * 1024 + tid;
-      if (i < n) {
-        const int e32 = (int)min(excl, (long long)INT_MAX);
-        offsets[i] = e32;
-        counts[i] = e32;
-      }
-      __syncthreads();
-      if (tid == 0) carry_s = carry + warp_sums[31];
-      __syncthreads();
+      warp_sums[lane] = w;
     }
+    __syncthreads();
+    const long long carry = carry_s;
+    long long excl = carry + inc - total + (wid > 0 ? warp_sums[wid - 1] : 0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (i0 + j < n) {
+        const int e32 = (int)min(excl, (long long)INT_MAX);
+        offsets[i0 + j] = e32;
+        counts[i0 + j] = e32;
+      }
+      excl += v[j];
+    }
+    __syncthreads();
+    if (tid == 0) carry_s = carry + warp_sums[31];
+    __syncthreads();
   }
   if (tid == 0) offsets[n] = (int)min(carry_s, (long long)INT_MAX);
 }

@@ -10,10 +10,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from pytorch3d_b200 import _C, _lib, synthetic  # noqa: E402
 
+args = sys.argv[1:]
+if args and args[0] == "--lib":  # development: time another build of the library
+    _lib.LIB_PATH = os.path.abspath(args[1])
+    args = args[2:]
 dev = torch.device("cuda:0")
 lib = _lib.load()
 buf = (ctypes.c_float * 3)()
-for name in sys.argv[1:] or ["ns", "c2"]:
+for name in args or ["ns", "c2"]:
     nm, rings, sides, H, W, K, blur = bench.WORKLOADS[name]
     meshes = synthetic.torus_batch(nm, rings, sides, seed=0)
     fv = synthetic.face_verts_of(meshes).to(dev)
