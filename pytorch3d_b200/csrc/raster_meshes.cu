@@ -4,12 +4,13 @@
 //   TriangleBoundingBoxKernel + RasterizeCoarseCudaKernel   (rasterize_coarse.cu:20-51, 76-219)
 //   RasterizeMeshesFineCudaKernel / RasterizeMeshesNaiveCudaKernel (rasterize_meshes.cu:630-736, 245-334)
 //   RasterizeMeshesBackwardCudaKernel                        (rasterize_meshes.cu:433-564)
-// Design: exact tile binning (binning.cuh) -> one CTA per 16x16 pixel tile; the tile's
-// faces are staged once per CTA into shared memory as float4 records with the per-face constants
-// (blur-expanded box, barycentric denominator) precomputed; each warp owns an 8x4 pixel footprint,
-// culls 32 faces at a time against it (one face per lane + ballot) and only then runs the exact
-// per-pixel arithmetic of raster_math.cuh; the K nearest hits live in registers (the reference's queue
-// semantics, fed in ascending face order from sorted tile lists).
+// Design: exact tile binning (binning.cuh); the setup pass also writes a 64-byte record per
+// face (vertices, barycentric denominator, exact pixel rectangle or blur-expanded box).  One CTA per 16x16 pixel
+// tile gathers the records of the tile's faces into shared memory; each warp owns an 8x4 pixel footprint.
+// Without blur the faces are scan-converted into per-pixel candidate bitmasks (division-free inside test), with
+// blur each lane box-tests one face against the footprint and a warp bit-matrix transpose yields per-pixel
+// masks; the exact per-pixel arithmetic of raster_math.cuh runs only on candidates, in ascending face order.
+// The K nearest hits are the reference's queue: keys in registers, payload in shared memory.
 #include <cfloat>
 #include <climits>
 
@@ -55,18 +56,33 @@ __device__ __forceinline__ void face_box(const Face& f, float sqrt_blur, float& 
 constexpr size_t FACE_RECORD_BYTES = 4 * 16;
 
 // Exact pixel range of the box test `p > vmax || p < vmin` (rasterize_meshes.cu:94-97): pix_to_ndc is monotonic
-// in the pixel index, so the passing pixels are contiguous; start from the conservative range and trim the ends.
+// in the pixel index, so the passing pixels are contiguous.  The inverse pixel-centre map in plain float locates
+// each end to within `margin` pixels (see pixel_range); if no pixel centre lies that close to the end, the rounded
+// index is already exact (all but ~0.2 % of the ends), otherwise the end is settled by evaluating pix_to_ndc
+// itself -- two IEEE divisions that the common case never executes.
 __device__ __forceinline__ void exact_pixel_range(float vmin, float vmax, int S, float range, int& lo, int& hi) {
-  pixel_range(vmin, vmax, S, range, lo, hi);
-  while (lo <= hi) {
-    const float v = pix_to_ndc(lo, S, range);
-    if (!(v > vmax || v < vmin)) break;
-    ++lo;
+  const float off = range * 0.5f, scale = (float)S / range, margin = 1e-3f + 1e-6f * (float)S;
+  const float a = (vmin + off) * scale - 0.5f, b = (vmax + off) * scale - 0.5f;
+  // conservative ends (identical to pixel_range) and the ends if the map erred the other way
+  const float a0 = fminf(fmaxf(a - margin, -1.0f), (float)S + 1.0f), a1 = fminf(fmaxf(a + margin, -1.0f), (float)S + 1.0f);
+  const float b0 = fminf(fmaxf(b + margin, -2.0f), (float)S), b1 = fminf(fmaxf(b - margin, -2.0f), (float)S);
+  lo = max(0, (int)ceilf(a0));
+  hi = min(S - 1, (int)floorf(b0));
+  const bool lo_sure = lo == max(0, (int)ceilf(a1)) && a == a;  // (a != a: NaN coordinates take the slow path)
+  const bool hi_sure = hi == min(S - 1, (int)floorf(b1)) && b == b;
+  if (!lo_sure) {
+    while (lo <= hi) {
+      const float v = pix_to_ndc(lo, S, range);
+      if (!(v > vmax || v < vmin)) break;
+      ++lo;
+    }
   }
-  while (hi >= lo) {
-    const float v = pix_to_ndc(hi, S, range);
-    if (!(v > vmax || v < vmin)) break;
-    --hi;
+  if (!hi_sure) {
+    while (hi >= lo) {
+      const float v = pix_to_ndc(hi, S, range);
+      if (!(v > vmax || v < vmin)) break;
+      --hi;
+    }
   }
 }
 
