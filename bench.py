@@ -374,27 +374,38 @@ def run_ours(args, rank, local_rank, world):
             sl["f"].copy_(faces_h, non_blocking=True)
             sl["copied"].record(copier)
 
+    reader = torch.cuda.Stream(device=dev)  # D2H of the results: off the compute stream's critical path
+
     def step_body(sl):
         v = sl["v"].detach().requires_grad_(True)
         m = _DeviceMeshes(v, sl["f"], first, num, max_f)
         p2f, zbuf, bary, dists = rasterize_meshes(m, size, blur_radius=blur, faces_per_pixel=K)
         loss = (zbuf * gz).sum() + (bary * gb).sum() + (dists * gd).sum()
         loss.backward()
-        sl["grad_h"].copy_(v.grad, non_blocking=True)
-        sl["loss_h"].copy_(loss.detach(), non_blocking=True)
+        sl["grad_d"], sl["loss_d"] = v.grad, loss.detach()
 
-    def enqueue_compute(sl):
+    def enqueue_compute(sl, overlap_d2h):
         compute.wait_event(sl["copied"])
+        compute.wait_event(sl["done"])  # (graph mode: the slot's static result tensors have been read back)
         if sl.get("graph") is not None:
             sl["graph"].replay()  # the same public-API calls, captured once per slot in a CUDA graph
         else:
             step_body(sl)
         sl["free"].record(compute)
-        sl["done"].record(compute)
+        out_stream = reader if overlap_d2h else compute
+        with torch.cuda.stream(out_stream):
+            out_stream.wait_event(sl["free"])
+            sl["grad_h"].copy_(sl["grad_d"], non_blocking=True)
+            sl["loss_h"].copy_(sl["loss_d"], non_blocking=True)
+            if overlap_d2h and sl.get("graph") is None:
+                sl["grad_d"].record_stream(reader)
+                sl["loss_d"].record_stream(reader)
+            sl["done"].record(out_stream)
 
     def capture_graphs():
-        """The step (public API forward + loss + backward + D2H) captured in one CUDA graph per input slot: the
-        host then issues one launch per step instead of ~60."""
+        """The step (public API forward + loss + backward) captured in one CUDA graph per input slot: the host then
+        issues one launch per step instead of ~60.  The result tensors of the capture are static; they are copied
+        to the host after every replay."""
         for sl in slots:
             sl["v"].copy_(verts_h)
             sl["f"].copy_(faces_h)
@@ -410,11 +421,12 @@ def run_ours(args, rank, local_rank, world):
         out = 0.0
         for sl in slots:
             sl["free"].record(compute)
+            sl["done"].record(compute)
         if not pipelined:
             for i in range(n):
                 sl = slots[i & 1]
                 enqueue_copy(sl)
-                enqueue_compute(sl)
+                enqueue_compute(sl, False)
                 sl["done"].synchronize()
                 out += float(sl["loss_h"])
             return out
@@ -422,7 +434,7 @@ def run_ours(args, rank, local_rank, world):
         for i in range(n):
             if i + 1 < n:
                 enqueue_copy(slots[(i + 1) & 1])
-            enqueue_compute(slots[i & 1])
+            enqueue_compute(slots[i & 1], True)
             if i > 0:
                 slots[(i - 1) & 1]["done"].synchronize()
                 out += float(slots[(i - 1) & 1]["loss_h"])
@@ -465,7 +477,7 @@ def run_ours(args, rank, local_rank, world):
         "steps": n_e2e, "mode": best, "modes": e2e_rates,
         "what": "pytorch3d_b200.rasterize_meshes(meshes) + loss.backward(): verts/faces H2D from pinned host "
                 "memory, gradient w.r.t. verts and the loss D2H, every step; fragments stay on the device. "
-                "serial = no overlap between steps; pipelined = next step's H2D on a copy stream, results read "
+                "serial = no overlap between steps; pipelined = next step's H2D on a copy stream, results copied back on a third stream and read "
                 "one step late; +graph = the step's launches replayed from a CUDA graph captured from the same "
                 "public-API calls",
     }

@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(TILE_THREADS, B200R_FINE_MIN_CTAS) mesh_fine_k
   for (int base = 0; base < count; base += CHUNK) {
     const int nc = min(CHUNK, count - base);
     const int nwords = (nc + 31) >> 5;
-    __syncthreads();  // previous chunk fully consumed
+    if (base > 0) __syncthreads();  // previous chunk fully consumed
     if (tid < nc) {
       const int f = overflow ? (int)(mesh_first + base + tid) : p.pairs[seg_begin + base + tid];
       const float4* r = p.rec + (int64_t)f * 4;

@@ -56,6 +56,12 @@ MESH_MATRIX = [  # persp, clip, cull, blur, K, H, W, F, N
     (0, 0, 0, 1e-2, 5, 31, 31, 300, 1),
     (0, 0, 0, 1e-2, 7, 16, 16, 300, 1),
     (0, 0, 0, 1e-2, 9, 16, 16, 300, 1),
+    # no blur (scan-conversion path) on images with partial tiles and odd widths: paired stores, empty tiles
+    (0, 0, 0, 0.0, 8, 33, 47, 500, 2),
+    (1, 0, 0, 0.0, 4, 31, 45, 800, 3),
+    (0, 1, 0, 0.0, 2, 50, 19, 400, 1),
+    (0, 0, 0, 0.0, 8, 100, 70, 30, 2),
+    (0, 0, 1, 0.0, 6, 70, 100, 2000, 2),
 ]
 
 
