@@ -345,6 +345,11 @@ def run_ours(args, rank, local_rank, world):
             others = other_workloads(dev)
         except Exception as ex:
             others = {"error": str(ex)}
+        # those workloads leave differently sized blocks in torch's caching allocator; start the end-to-end
+        # section from the same allocator state as a run without them
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
 
     # ---------------- end to end through the public API with HOST inputs (pinned) and host results
     # Every step copies its own inputs (verts + faces) from pinned host memory and returns the gradient and the

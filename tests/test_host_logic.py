@@ -42,6 +42,22 @@ def test_shape_and_limit_errors(built_lib):
         _C.rasterize_meshes(fv, z, z, torch.full((3,), -1), (8, 8), 0.0, 1, 0, 0, False, False, False)
     with pytest.raises(RuntimeError, match="Must have num_closest <= 150"):
         _C.rasterize_points(torch.zeros(4, 3), z, z, (8, 8), torch.zeros(4), 151, 0, 0)
+    # the fused (verts, faces) entry point validates like the ops it replaces
+    verts, faces = torch.zeros(5, 3), torch.zeros(4, 3, dtype=torch.int64)
+    with pytest.raises(RuntimeError, match=r"verts_packed must have dimensions \(num_verts, 3\)"):
+        _C.rasterize_meshes_indexed(torch.zeros(5, 2), faces, z, z, (8, 8), 0.0, 1, False, False, False)
+    with pytest.raises(RuntimeError, match=r"faces_packed must have dimensions \(num_faces, 3\)"):
+        _C.rasterize_meshes_indexed(verts, torch.zeros(4, 4, dtype=torch.int64), z, z, (8, 8), 0.0, 1, False, False, False)
+    with pytest.raises(RuntimeError, match="Must have points_per_pixel <= 150"):
+        _C.rasterize_meshes_indexed(verts, faces, z, z, (8, 8), 0.0, 151, False, False, False)
+    with pytest.raises(RuntimeError, match="expected scalar type Float"):
+        _C.rasterize_meshes_indexed(verts.double(), faces, z, z, (8, 8), 0.0, 1, False, False, False)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        _C.rasterize_meshes_indexed(verts, faces, z, z, (8, 8), 0.0, 1, False, False, False)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        _C.rasterize_meshes_backward_indexed(torch.zeros(4, 3, 3), faces, 5, torch.zeros(1, 8, 8, 1, dtype=torch.int64),
+                                             torch.zeros(1, 8, 8, 1), torch.zeros(1, 8, 8, 1, 3),
+                                             torch.zeros(1, 8, 8, 1), False, False)
 
 
 def test_parse_image_size():
