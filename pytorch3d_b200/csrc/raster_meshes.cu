@@ -466,11 +466,8 @@ __device__ __forceinline__ void write_empty_tile(const FineParams& p, int n, int
   }
 }
 
-#ifndef B200R_FINE_MIN_CTAS
-#define B200R_FINE_MIN_CTAS 4
-#endif
 template <int KMAX, bool NB, bool SCAN>
-__global__ void __launch_bounds__(TILE_THREADS, B200R_FINE_MIN_CTAS) mesh_fine_kernel(const FineParams p) {
+__global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FineParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FineShared<KMAX>& sh = *reinterpret_cast<FineShared<KMAX>*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31;
