@@ -981,24 +981,29 @@ __device__ __forceinline__ void backward_one(const BackwardParams& p, float px, 
   out[8] = gz * k2 + dz2;
 }
 
-// Scatter one warp's contributions.  Neighbouring pixels usually hit the same face, so before touching
-// memory the warp merges lanes that carry the same face with five butterfly stages (partner = lane ^ 1, 2, 4
-// along the footprint row, then ^ 8, 16 across rows): the lower lane of a matching pair takes over the
-// partner's sum.  What is left is one set of 9 atomics per surviving lane instead of per pixel.
+// Scatter one warp's contributions.  Neighbouring pixels usually hit the same face, so before touching memory
+// the warp merges ALL lanes that carry the same face: one set of 9 atomics per distinct face of the warp
+// instead of per pixel (the kernel is sensitive to the number of atomics: merging only within pixel rows costs
+// +10 us on the north-star batch).
 __device__ __forceinline__ void warp_scatter(float* __restrict__ grad_face_verts, int face, float (&g)[9], int lane) {
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int other = __shfl_xor_sync(0xffffffffu, face, d);
-    const bool same = other == face && face >= 0;
-    const bool upper = (lane & d) != 0;
+  // All lanes that hit the same face are found with one MATCH; each lane then adds up its successors in the
+  // group by pointer jumping (after round r a lane holds the sum of 2^r consecutive group members), so the
+  // group's lowest lane ends up with the whole sum after ceil(log2(group size)) rounds -- typically one or
+  // two, faces being a few pixels large -- and is the only one to issue atomics.
+  const unsigned grp = __match_any_sync(0xffffffffu, face);
+  const unsigned above = lane == 31 ? 0u : grp & (0xffffffffu << (lane + 1));
+  int next = (face >= 0 && above != 0u) ? __ffs((int)above) - 1 : -1;
+  while (__any_sync(0xffffffffu, next >= 0)) {
+    const int src = next >= 0 ? next : lane;
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
-      const float v = __shfl_xor_sync(0xffffffffu, g[i], d);
-      g[i] = same ? (upper ? 0.0f : g[i] + v) : g[i];
+      const float v = __shfl_sync(0xffffffffu, g[i], src);
+      if (next >= 0) g[i] += v;
     }
-    if (same && upper) face = -1;  // merged into the partner
+    const int nn = __shfl_sync(0xffffffffu, next, src);
+    next = next >= 0 ? nn : -1;
   }
-  if (face >= 0) {
+  if (face >= 0 && lane == __ffs((int)grp) - 1) {
     float* o = grad_face_verts + (int64_t)face * 9;
 #pragma unroll
     for (int i = 0; i < 9; ++i) atomicAdd(o + i, g[i]);
