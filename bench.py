@@ -350,6 +350,10 @@ def run_ours(args, rank, local_rank, world):
         import gc
         gc.collect()
         torch.cuda.empty_cache()
+        # ... and their CPU-side input generation leaves OpenMP worker threads spinning for a moment; the serial
+        # end-to-end mode is host-latency-bound and would be timed against them
+        torch.cuda.synchronize(dev)
+        time.sleep(1.0)
 
     # ---------------- end to end through the public API with HOST inputs (pinned) and host results
     # Every step copies its own inputs (verts + faces) from pinned host memory and returns the gradient and the

@@ -401,27 +401,54 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_smem_kernel(const Po
   }
 }
 
-// Backward: one thread per (pixel, k) slot, coalesced over the (N,H,W,K) arrays
-// (rasterize_points.cu:366-411): grad_xy = 2 * grad_dist * (p_xy - pix_xy), grad_z = grad_zbuf.
-__global__ void __launch_bounds__(256)
+// Backward (rasterize_points.cu:366-411): grad_xy = 2 * grad_dist * (p_xy - pix_xy), grad_z = grad_zbuf.
+// One thread per pixel on the forward pass's tiles and 8x4 footprints, looping over the K slots.  A point covers
+// many neighbouring pixels, so at every slot the warp first merges ALL lanes that hold the same point
+// (__match_any_sync + pointer jumping, as in the mesh backward) and only one lane per distinct point issues the
+// three atomics.
+__global__ void __launch_bounds__(TILE_THREADS)
     points_backward_kernel(const float* __restrict__ points, const int32_t* __restrict__ idxs,
-                           const float* __restrict__ grad_zbuf, const float* __restrict__ grad_dists, int64_t total,
-                           int H, int W, int K, float rx, float ry, float* __restrict__ grad_points) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int pi = idxs[i];
-    if (pi < 0) continue;
-    const int64_t pix = i / K;
-    const int xo = (int)(pix % W), yo = (int)((pix / W) % H);
-    const float xf = pix_to_ndc(W - 1 - xo, W, rx);
-    const float yf = pix_to_ndc(H - 1 - yo, H, ry);
-    const float gd = grad_dists[i];
-    const float g2 = gd + gd;
-    const float gx = g2 * (__ldg(points + (int64_t)pi * 3 + 0) - xf);
-    const float gy = g2 * (__ldg(points + (int64_t)pi * 3 + 1) - yf);
-    atomicAdd(grad_points + (int64_t)pi * 3 + 0, gx);
-    atomicAdd(grad_points + (int64_t)pi * 3 + 1, gy);
-    atomicAdd(grad_points + (int64_t)pi * 3 + 2, grad_zbuf[i]);
+                           const float* __restrict__ grad_zbuf, const float* __restrict__ grad_dists, int n0, int H,
+                           int W, int K, float rx, float ry, float* __restrict__ grad_points) {
+  const int lane = threadIdx.x & 31;
+  const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = n0 + blockIdx.z;
+  int xo, yo;
+  pthread_pixel(tile_x, tile_y, xo, yo);
+  const bool in_image = xo < W && yo < H;
+  const float xf = pix_to_ndc(W - 1 - xo, W, rx);
+  const float yf = pix_to_ndc(H - 1 - yo, H, ry);
+  const int64_t o = in_image ? (((int64_t)n * H + yo) * W + xo) * K : 0;
+  for (int k = 0; k < K; ++k) {
+    const int pi = in_image ? idxs[o + k] : -1;
+    if (!__any_sync(0xffffffffu, pi >= 0)) continue;
+    float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+    if (pi >= 0) {
+      const float gd = grad_dists[o + k];
+      const float g2 = gd + gd;
+      gx = g2 * (__ldg(points + (int64_t)pi * 3 + 0) - xf);
+      gy = g2 * (__ldg(points + (int64_t)pi * 3 + 1) - yf);
+      gz = grad_zbuf[o + k];
+    }
+    const unsigned grp = __match_any_sync(0xffffffffu, pi);
+    const unsigned above = lane == 31 ? 0u : grp & (0xffffffffu << (lane + 1));
+    int next = (pi >= 0 && above != 0u) ? __ffs((int)above) - 1 : -1;
+    while (__any_sync(0xffffffffu, next >= 0)) {
+      const int src = next >= 0 ? next : lane;
+      const float vx = __shfl_sync(0xffffffffu, gx, src), vy = __shfl_sync(0xffffffffu, gy, src),
+                  vz = __shfl_sync(0xffffffffu, gz, src);
+      const int nn = __shfl_sync(0xffffffffu, next, src);
+      if (next >= 0) {
+        gx += vx;
+        gy += vy;
+        gz += vz;
+      }
+      next = next >= 0 ? nn : -1;
+    }
+    if (pi >= 0 && lane == __ffs((int)grp) - 1) {
+      atomicAdd(grad_points + (int64_t)pi * 3 + 0, gx);
+      atomicAdd(grad_points + (int64_t)pi * 3 + 1, gy);
+      atomicAdd(grad_points + (int64_t)pi * 3 + 2, gz);
+    }
   }
 }
 
@@ -518,12 +545,15 @@ extern "C" int b200r_rasterize_points_backward(const float* points, int64_t P, c
   B200R_CUDA_OK(cudaMemsetAsync(grad_points, 0, sizeof(float) * 3 * (size_t)P, stream));
   const int64_t total = (int64_t)N * H * W * K;
   if (total == 0) return B200R_OK;
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 64) blocks = 148 * 64;
+  const int TY = div_up(H, TILE), TX = div_up(W, TILE);
+  if (TY > 65535) return fail(B200R_ERR_INVALID_ARGUMENT, "image too large");
   const bool prof = profiling_enabled();
   if (prof) phase_timer().record(3, stream);
-  points_backward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(points, idxs, grad_zbuf, grad_dists, total, H, W, K,
+  for (int n0 = 0; n0 < N; n0 += 65535) {  // grid.z is limited to 65535 images per launch
+    const dim3 grid((unsigned)TX, (unsigned)TY, (unsigned)min(N - n0, 65535));
+    points_backward_kernel<<<grid, TILE_THREADS, 0, stream>>>(points, idxs, grad_zbuf, grad_dists, n0, H, W, K,
                                                              ndc_range(W, H), ndc_range(H, W), grad_points);
+  }
   B200R_LAUNCHED("points_backward_kernel");
   if (prof) {
     phase_timer().record(4, stream);
