@@ -108,6 +108,18 @@ def rasterize_meshes(
     return pix_to_face, zbuf, barycentric_coords, dists
 
 
+def _zeros_where_none(pix_to_face, grad_zbuf, grad_bary, grad_dists):
+    """Outputs that did not take part in the loss arrive as None (set_materialize_grads(False))."""
+    shape, dev = tuple(pix_to_face.shape), pix_to_face.device
+    if grad_zbuf is None:
+        grad_zbuf = torch.zeros(shape, dtype=torch.float32, device=dev)
+    if grad_bary is None:
+        grad_bary = torch.zeros(shape + (3,), dtype=torch.float32, device=dev)
+    if grad_dists is None:
+        grad_dists = torch.zeros(shape, dtype=torch.float32, device=dev)
+    return grad_zbuf, grad_bary, grad_dists
+
+
 class _RasterizeMeshesIndexed(torch.autograd.Function):
     """`_RasterizeFaceVerts` fused with the face gather that precedes it: differentiable w.r.t. verts_packed."""
 
@@ -119,6 +131,8 @@ class _RasterizeMeshesIndexed(torch.autograd.Function):
             faces_per_pixel, perspective_correct, clip_barycentric_coords, cull_backfaces)
         ctx.save_for_backward(face_verts, faces_packed, pix_to_face)
         ctx.mark_non_differentiable(pix_to_face)
+        # no zero-filled "gradient" for pix_to_face (134 MB of int64 zeros per step at the north-star size)
+        ctx.set_materialize_grads(False)
         ctx.num_verts = int(verts_packed.shape[0])
         ctx.perspective_correct = perspective_correct
         ctx.clip_barycentric_coords = clip_barycentric_coords
@@ -127,6 +141,8 @@ class _RasterizeMeshesIndexed(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_pix_to_face, grad_zbuf, grad_barycentric_coords, grad_dists):
         face_verts, faces_packed, pix_to_face = ctx.saved_tensors
+        grad_zbuf, grad_barycentric_coords, grad_dists = _zeros_where_none(
+            pix_to_face, grad_zbuf, grad_barycentric_coords, grad_dists)
         grad_verts = _C.rasterize_meshes_backward_indexed(
             face_verts, faces_packed, ctx.num_verts, pix_to_face, grad_zbuf, grad_barycentric_coords, grad_dists,
             ctx.perspective_correct, ctx.clip_barycentric_coords)
@@ -146,6 +162,7 @@ class _RasterizeFaceVerts(torch.autograd.Function):
             clip_barycentric_coords, cull_backfaces)
         ctx.save_for_backward(face_verts, pix_to_face)
         ctx.mark_non_differentiable(pix_to_face)
+        ctx.set_materialize_grads(False)
         ctx.perspective_correct = perspective_correct
         ctx.clip_barycentric_coords = clip_barycentric_coords
         return pix_to_face, zbuf, barycentric_coords, dists
@@ -153,6 +170,8 @@ class _RasterizeFaceVerts(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_pix_to_face, grad_zbuf, grad_barycentric_coords, grad_dists):
         face_verts, pix_to_face = ctx.saved_tensors
+        grad_zbuf, grad_barycentric_coords, grad_dists = _zeros_where_none(
+            pix_to_face, grad_zbuf, grad_barycentric_coords, grad_dists)
         grad_face_verts = _C.rasterize_meshes_backward(
             face_verts, pix_to_face, grad_zbuf, grad_barycentric_coords, grad_dists, ctx.perspective_correct,
             ctx.clip_barycentric_coords)

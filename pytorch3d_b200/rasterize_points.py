@@ -84,10 +84,15 @@ class _RasterizePoints(torch.autograd.Function):
             bin_size, max_points_per_bin)
         ctx.save_for_backward(points, idx)
         ctx.mark_non_differentiable(idx)
+        ctx.set_materialize_grads(False)  # no zero-filled "gradient" for the integer idx output
         return idx, zbuf, dists
 
     @staticmethod
     def backward(ctx, grad_idx, grad_zbuf, grad_dists):
         points, idx = ctx.saved_tensors
+        if grad_zbuf is None:
+            grad_zbuf = torch.zeros(idx.shape, dtype=torch.float32, device=idx.device)
+        if grad_dists is None:
+            grad_dists = torch.zeros(idx.shape, dtype=torch.float32, device=idx.device)
         grad_points = _C.rasterize_points_backward(points, idx, grad_zbuf, grad_dists)
         return (grad_points,) + (None,) * 7

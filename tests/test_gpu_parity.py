@@ -233,6 +233,16 @@ def test_mesh_autograd_wrapper(ops, dev):
     scale = want.abs().max()
     assert (grad_verts.cpu() - want).abs().max() <= 2e-3 * scale
     assert not p2f.requires_grad
+    # a loss that uses only one of the outputs: the other gradients arrive as None
+    m2 = synthetic.torus_batch(2, 16, 16, seed=1, device=dev)
+    m2.requires_grad_(True)
+    _, zbuf2, _, _ = p3b.rasterize_meshes(m2, 48, blur_radius=1e-3, faces_per_pixel=3)
+    (zbuf2 * gz).sum().backward()
+    fv_g = oracle.rasterize_meshes_backward(fv.numpy(), p2f.cpu().numpy(), gz.cpu().numpy(), np.zeros_like(gb.cpu().numpy()),
+                                            np.zeros_like(gd.cpu().numpy()), 0, 0, arith=oracle.ARITH_CUDA)
+    want2 = torch.zeros_like(want)
+    want2.index_put_((m.faces_packed().cpu().reshape(-1),), torch.from_numpy(fv_g).reshape(-1, 3), accumulate=True)
+    assert (m2.verts_packed().grad.cpu() - want2).abs().max() <= 2e-3 * max(float(want2.abs().max()), 1e-6)
 
 
 def test_mesh_indexed_entry_points(ops, dev):
