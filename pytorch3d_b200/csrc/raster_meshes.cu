@@ -1013,7 +1013,7 @@ __device__ __forceinline__ void warp_scatter(float* __restrict__ grad_face_verts
 // KV > 0: K == KV (a multiple of 4) and the pixel's KV face indices are fetched up front with 16-byte loads
 // (a pixel with no face costs nothing else); KV == 0: any K, scalar loads.
 template <int KV>
-__global__ void __launch_bounds__(TILE_THREADS) mesh_backward_kernel(const BackwardParams p) {
+__global__ void __launch_bounds__(TILE_THREADS, 4) mesh_backward_kernel(const BackwardParams p) {
   const int lane = threadIdx.x & 31;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = p.n0 + blockIdx.z;  // grid = (TX, TY, images)
   int xo, yo;
