@@ -300,7 +300,8 @@ struct TopK {
   }
 };
 
-// Shared-memory face records of one staged chunk.
+// Shared-memory face records of one staged chunk of the large-K kernel (mesh_fine_bigk_kernel), which stages from
+// face_verts itself; the K <= 8 kernels copy the setup pass's records instead (FineShared below).
 struct __align__(16) FaceChunk {
   float4 box[CHUNK];  // xmin, xmax, ymin, ymax (blur-expanded; empty box = never hit)
   float4 a[CHUNK];    // x0, y0, x1, y1
