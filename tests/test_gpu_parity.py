@@ -184,6 +184,34 @@ def test_mesh_clipped_neighbors(ops, dev):
         assert_frag_equal(mine, o, "neighbours K=%d" % K)
 
 
+def test_more_images_than_grid_z(ops, dev):
+    """The fine / backward kernels use grid = (tiles x, tiles y, images): batches of more than 65535 images are
+    rendered in slices.  65538 one-triangle meshes / one-point clouds on 16x16 images (one tile each)."""
+    N, g = 65535 + 3, torch.Generator().manual_seed(7)
+    fv = torch.rand(N, 3, 3, generator=g) * 2 - 1
+    fv[..., 2] = 0.5 + torch.rand(N, 3, generator=g)
+    first, num = torch.arange(N), torch.ones(N, dtype=torch.int64)
+    got = run_mesh(ops, dev, fv, first, num, (16, 16), 0.0, 2)
+    want = oracle.rasterize_meshes(fv.numpy(), first.numpy(), num.numpy(), (16, 16), 0.0, 2, **CUDA)
+    assert_frag_equal(got, want, "65538 images")
+    assert (got[0][-1] >= 0).any() or (want[0][-1] < 0).all()
+    gz, gb, gd = (t.to(dev) for t in upstream([want[1].shape, want[2].shape, want[3].shape]))
+    grad = ops.rasterize_meshes_backward(fv.to(dev), got[0], gz, gb, gd, False, False).cpu().numpy()
+    gref = oracle.rasterize_meshes_backward(fv.numpy(), want[0], gz.cpu().numpy(), gb.cpu().numpy(), gd.cpu().numpy(),
+                                            0, 0, arith=oracle.ARITH_CUDA)
+    assert np.abs(grad - gref).max() <= 2e-3 * max(np.abs(gref).max(), 1e-6)
+    pts = torch.rand(N, 3, generator=g) * 1.6 - 0.8
+    pts[:, 2] = 0.5 + torch.rand(N, generator=g)
+    rad = torch.full((N,), 0.3)
+    pgot = ops.rasterize_points(pts.to(dev), first.to(dev), num.to(dev), (16, 16), rad.to(dev), 1, 0, 0)
+    pwant = oracle.rasterize_points(pts.numpy(), first.numpy(), num.numpy(), (16, 16), rad.numpy(), 1, **CUDA)
+    assert_frag_equal(pgot, pwant, "65538 clouds")
+    pgz, pgd = (t.to(dev) for t in upstream([pwant[1].shape, pwant[2].shape]))
+    pgrad = ops.rasterize_points_backward(pts.to(dev), pgot[0], pgz, pgd).cpu().numpy()
+    pref = oracle.rasterize_points_backward(pts.numpy(), pwant[0], pgz.cpu().numpy(), pgd.cpu().numpy())
+    assert np.abs(pgrad - pref).max() <= 1e-4 * max(np.abs(pref).max(), 1e-6)
+
+
 @pytest.mark.parametrize("persp,clip,blur", [(0, 0, 1e-3), (1, 0, 1e-3), (0, 1, 1e-3), (1, 1, 0.0), (1, 1, 1e-3)])
 def test_mesh_backward(ops, dev, ref_cuda, persp, clip, blur):
     from pytorch3d_b200 import synthetic
