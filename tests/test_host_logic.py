@@ -129,3 +129,49 @@ def test_rasterizer_settings_defaults_match_reference():
     assert (ps.image_size, ps.radius, ps.points_per_pixel) == (256, 0.01, 8)
     fr = p3b.Fragments(torch.zeros(1), torch.zeros(1, requires_grad=True), torch.zeros(1), None)
     assert not fr.detach().zbuf.requires_grad
+
+
+def test_wrapper_picks_fused_or_clipping_path(monkeypatch):
+    """rasterize_meshes(meshes) hands (verts, faces) to the fused op unless clipping needs face_verts as a tensor;
+    outputs that take no part in the loss reach the backward op as zeros, not as None.  (Native ops replaced by
+    recording fakes: host logic only.)"""
+    import importlib
+    rm = importlib.import_module("pytorch3d_b200.rasterize_meshes")  # (the package attribute is the function)
+    calls = []
+    m = synthetic.torus_batch(2, 6, 6)
+    m.requires_grad_(True)
+    F, V = m.faces_packed().shape[0], m.verts_packed().shape[0]
+
+    def frags(N, H, W, K):
+        return (torch.zeros(N, H, W, K, dtype=torch.int64), torch.zeros(N, H, W, K), torch.zeros(N, H, W, K, 3),
+                torch.zeros(N, H, W, K))
+
+    def fake_indexed(verts, faces, first, num, size, blur, K, persp, clip, cull):
+        calls.append("indexed")
+        return frags(len(num), size[0], size[1], K) + (verts[faces],)
+
+    def fake_indexed_bwd(face_verts, faces, num_verts, p2f, gz, gb, gd, persp, clip):
+        calls.append(("indexed_bwd", gz is not None and float(gz.abs().sum()), float(gb.abs().sum()),
+                      float(gd.abs().sum())))
+        assert gz.shape == p2f.shape and gb.shape == p2f.shape + (3,) and gd.shape == p2f.shape
+        return torch.ones(num_verts, 3)
+
+    def fake_face_verts(fv, first, num, nb, size, blur, K, bs, mf, persp, clip, cull):
+        calls.append("face_verts")
+        return frags(len(num), size[0], size[1], K)
+
+    monkeypatch.setattr(rm._C, "rasterize_meshes_indexed", fake_indexed)
+    monkeypatch.setattr(rm._C, "rasterize_meshes_backward_indexed", fake_indexed_bwd)
+    monkeypatch.setattr(rm._C, "rasterize_meshes", fake_face_verts)
+    p2f, zbuf, bary, dists = rm.rasterize_meshes(m, 8, faces_per_pixel=2)
+    assert calls == ["indexed"] and not p2f.requires_grad and zbuf.requires_grad
+    (dists * 2.0).sum().backward()  # zbuf and bary unused: their gradients must arrive as zeros
+    assert calls[1][0] == "indexed_bwd" and calls[1][1] == 0.0 and calls[1][2] == 0.0 and calls[1][3] > 0.0
+    assert torch.equal(m.verts_packed().grad, torch.ones(V, 3))
+    calls.clear()
+    rm.rasterize_meshes(m, 8, faces_per_pixel=2, z_clip_value=1e-2)
+    assert calls == ["face_verts"]
+    calls.clear()
+    rm.rasterize_meshes(m, 8, faces_per_pixel=2, cull_to_frustum=True)
+    assert calls == ["face_verts"]
+    assert F > 0
