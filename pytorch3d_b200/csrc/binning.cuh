@@ -267,6 +267,10 @@ __device__ __forceinline__ void sort_segment_warp(int* __restrict__ pairs, int b
 // Tiles are dealt to warps through a multiplicative permutation of the tile index, so that the heavy tiles of
 // a silhouette (neighbours in tile order, and at the same place in every frame of a batch) spread over the SMs.
 __device__ __forceinline__ int sort_tile_of(int slot, int ntiles, int mult) {
+  // (32-bit arithmetic whenever the largest product fits: a 64-bit modulo is ~80 instructions, and every thread
+  //  evaluates this nine times)
+  if ((unsigned long long)(unsigned)ntiles * (unsigned)mult <= 0xffffffffull)
+    return (int)(((unsigned)slot * (unsigned)mult) % (unsigned)ntiles);
   return (int)(((long long)slot * mult) % ntiles);
 }
 
