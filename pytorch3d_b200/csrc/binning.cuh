@@ -7,7 +7,7 @@
 //   pass 1 (setup+count)  atomically counts elements per tile,
 //   pass 2 (scan)         exclusive-scans the counts into segment offsets,
 //   pass 3 (fill)         writes element ids into each tile's compact segment,
-//   pass 4 (sort)         puts every segment in ascending element order.
+//   pass 4 (in the fine kernel) the CTA that owns a tile puts its segment in ascending element order.
 // No M cap, no overflow drop, no -1 fill; elements whose box contains no pixel centre (most
 // sub-pixel triangles) are never binned at all.
 #pragma once
@@ -170,15 +170,13 @@ static __global__ void __launch_bounds__(256)
   }
 }
 
-// Pass 4: sort every tile segment into ascending element order (one CTA per tile).  The fill pass
-// scatters with atomics, so segment order is arbitrary; ascending order makes the fine pass visit a
-// pixel's candidates exactly in the order of the reference's naive kernels (rasterize_meshes.cu:301,
+// Pass 4 (inside the fine kernels): every tile segment is put in ascending element order by the CTA that
+// consumes it.  The fill pass scatters with atomics, so segment order is arbitrary; ascending order makes the fine
+// pass visit a pixel's candidates exactly in the order of the reference's naive kernels (rasterize_meshes.cu:301,
 // rasterize_points.cu:128), which is what pins tie-breaking and makes the output deterministic.
 // "Normalised" bitonic network (every compare-exchange ascending), valid for any segment length:
 // partners beyond the end are treated as +inf and skipped.
-constexpr int SORT_THREADS = 256;
-constexpr int SORT_TILES_PER_CTA = SORT_THREADS / 32;  // one warp per tile on the fast path
-constexpr int SORT_SMEM_ELEMS = 4096;
+constexpr int SORT_THREADS = TILE_THREADS;
 
 // One compare-exchange sweep of the bitonic network over keys[0..n) by the whole CTA.
 template <bool MIRROR>
@@ -195,145 +193,63 @@ __device__ __forceinline__ void sort_sweep(int* keys, int n, int d) {
   }
 }
 
-// Bitonic sort of 32*C keys held C per lane (element index = lane * C + r), entirely in registers: all
-// compare-exchanges are ascending ("normalised" network: each merge starts with a mirror step e ^ (k-1) and
-// continues with half-cleaners e ^ d); partners closer than C are register pairs, the others are reached with
-// one shuffle.  No shared memory, no barriers.
-template <int C>
-__device__ __forceinline__ void warp_bitonic_sort(int (&x)[C], int lane) {
-#pragma unroll
-  for (int k = 2; k <= 32 * C; k <<= 1) {
-    if (k <= C) {  // mirror step inside a lane
-#pragma unroll
-      for (int r = 0; r < C; ++r) {
-        const int pr = r ^ (k - 1);
-        if (r < pr) {
-          const int a = x[r], b = x[pr];
-          x[r] = min(a, b);
-          x[pr] = max(a, b);
-        }
-      }
-    } else {  // mirror step across lanes: partner lane ^ (k/C - 1), registers reversed
-      const int lm = k / C - 1;
-      int y[C];
-#pragma unroll
-      for (int r = 0; r < C; ++r) y[r] = __shfl_xor_sync(0xffffffffu, x[C - 1 - r], lm);
-      const bool lower = (lane & ((lm + 1) >> 1)) == 0;  // the top flipped lane bit decides who is lower
-#pragma unroll
-      for (int r = 0; r < C; ++r) x[r] = lower ? min(x[r], y[r]) : max(x[r], y[r]);
-    }
-#pragma unroll
-    for (int d = k >> 2; d > 0; d >>= 1) {
-      if (d < C) {
-#pragma unroll
-        for (int r = 0; r < C; ++r) {
-          const int pr = r ^ d;
-          if (r < pr) {
-            const int a = x[r], b = x[pr];
-            x[r] = min(a, b);
-            x[pr] = max(a, b);
-          }
-        }
+// The CTA that owns a tile sorts its list itself -- a separate sort launch cost 19 us of the north-star step.
+// Lists of up to 256 faces (one chunk; all but the silhouette tiles) are sorted while they are staged: one key per
+// thread, bitonic network ("normalised": every compare-exchange ascending, each merge = a mirror step i ^ (k-1)
+// followed by half-cleaners i ^ d), partners closer than 32 by shuffle, the others through shared memory
+// (double-buffered: one barrier per step; at most 6 such steps).  Unused threads hold INT_MAX.
+__device__ __forceinline__ int cta_sort256(int key, int n, int* buf) {
+  const int i = threadIdx.x;
+  int phase = 0;
+  for (int k = 2; (k >> 1) < n; k <<= 1) {
+    {
+      const int m = k - 1;
+      int other;
+      if (k <= 32) {
+        other = __shfl_xor_sync(0xffffffffu, key, m);
       } else {
-        const int ld = d / C;
-        const bool lower = (lane & ld) == 0;
-#pragma unroll
-        for (int r = 0; r < C; ++r) {
-          const int v = __shfl_xor_sync(0xffffffffu, x[r], ld);
-          x[r] = lower ? min(x[r], v) : max(x[r], v);
-        }
-      }
-    }
-  }
-}
-
-// One warp sorts one tile segment of up to 32*C keys.
-template <int C>
-__device__ __forceinline__ void sort_segment_warp(int* __restrict__ pairs, int begin, int n, int lane) {
-  int x[C];
-#pragma unroll
-  for (int r = 0; r < C; ++r) {
-    const int e = lane * C + r;
-    x[r] = e < n ? pairs[begin + e] : 0x7fffffff;  // padding sorts to the end
-  }
-  warp_bitonic_sort<C>(x, lane);
-#pragma unroll
-  for (int r = 0; r < C; ++r) {
-    const int e = lane * C + r;
-    if (e < n) pairs[begin + e] = x[r];
-  }
-}
-
-// Tiles are dealt to warps through a multiplicative permutation of the tile index, so that the heavy tiles of
-// a silhouette (neighbours in tile order, and at the same place in every frame of a batch) spread over the SMs.
-__device__ __forceinline__ int sort_tile_of(int slot, int ntiles, int mult) {
-  // (32-bit arithmetic whenever the largest product fits: a 64-bit modulo is ~80 instructions, and every thread
-  //  evaluates this nine times)
-  if ((unsigned long long)(unsigned)ntiles * (unsigned)mult <= 0xffffffffull)
-    return (int)(((unsigned)slot * (unsigned)mult) % (unsigned)ntiles);
-  return (int)(((long long)slot * mult) % ntiles);
-}
-
-constexpr int SORT_WARP_MAX = 1024;  // longest segment a single warp sorts in registers
-
-static __global__ void __launch_bounds__(SORT_THREADS)
-    tile_sort_kernel(const int* __restrict__ offsets, int* __restrict__ pairs, int64_t capacity, int ntiles,
-                     int mult) {
-  __shared__ int s_keys[SORT_SMEM_ELEMS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  {  // segments of up to 1024 keys: one tile per warp
-    const int slot = blockIdx.x * SORT_TILES_PER_CTA + warp;
-    const int t = slot < ntiles ? sort_tile_of(slot, ntiles, mult) : -1;
-    const int begin = t >= 0 ? offsets[t] : 0, end = t >= 0 ? offsets[t + 1] : 0;
-    const int n = end - begin;
-    if (n >= 2 && n <= SORT_WARP_MAX && (int64_t)end <= capacity && end != INT_MAX) {
-      if (n <= 32)
-        sort_segment_warp<1>(pairs, begin, n, lane);
-      else if (n <= 64)
-        sort_segment_warp<2>(pairs, begin, n, lane);
-      else if (n <= 128)
-        sort_segment_warp<4>(pairs, begin, n, lane);
-      else if (n <= 256)
-        sort_segment_warp<8>(pairs, begin, n, lane);
-      else if (n <= 512)
-        sort_segment_warp<16>(pairs, begin, n, lane);
-      else
-        sort_segment_warp<32>(pairs, begin, n, lane);
-    }
-  }
-  // longer segments: bitonic network by the whole CTA in shared (or, beyond 4096 keys, global) memory
-  for (int u = 0; u < SORT_TILES_PER_CTA; ++u) {
-    const int slot = blockIdx.x * SORT_TILES_PER_CTA + u;
-    if (slot >= ntiles) break;
-    const int t = sort_tile_of(slot, ntiles, mult);
-    const int begin = offsets[t], end = offsets[t + 1];
-    const int n = end - begin;
-    if (n <= SORT_WARP_MAX || (int64_t)end > capacity || end == INT_MAX) continue;  // (overflowed: not used)
-    const bool in_smem = n <= SORT_SMEM_ELEMS;
-    int* keys = in_smem ? s_keys : pairs + begin;
-    __syncthreads();
-    if (in_smem)
-      for (int i = threadIdx.x; i < n; i += SORT_THREADS) s_keys[i] = pairs[begin + i];
-    __syncthreads();
-    for (int k = 2; (k >> 1) < n; k <<= 1) {
-      sort_sweep<true>(keys, n, k);
-      __syncthreads();
-      for (int d = k >> 2; d > 0; d >>= 1) {
-        sort_sweep<false>(keys, n, d);
+        buf[phase * TILE_THREADS + i] = key;
         __syncthreads();
+        other = buf[phase * TILE_THREADS + (i ^ m)];
+        phase ^= 1;
       }
+      key = (i & (k >> 1)) == 0 ? min(key, other) : max(key, other);
     }
-    if (in_smem)
-      for (int i = threadIdx.x; i < n; i += SORT_THREADS) pairs[begin + i] = s_keys[i];
+    for (int d = k >> 2; d > 0; d >>= 1) {
+      int other;
+      if (d < 32) {
+        other = __shfl_xor_sync(0xffffffffu, key, d);
+      } else {
+        buf[phase * TILE_THREADS + i] = key;
+        __syncthreads();
+        other = buf[phase * TILE_THREADS + (i ^ d)];
+        phase ^= 1;
+      }
+      key = (i & d) == 0 ? min(key, other) : max(key, other);
+    }
   }
+  return key;
 }
 
-// A multiplier coprime with ntiles for sort_tile_of.
-inline int sort_multiplier(int64_t ntiles) {
-  const int primes[] = {7919, 7907, 7901, 7883, 7879, 104729};
-  for (int p : primes)
-    if (ntiles % p != 0) return p;
-  return 1;
+// Longer lists: the same network swept by the whole CTA over the list in shared memory (when it fits the
+// kernel's dynamic shared memory, which is not in use yet) or in place in global memory.
+__device__ __forceinline__ void cta_sort_segment(int* seg, int n, int* s_keys, int cap) {
+  const bool in_smem = n <= cap;
+  int* keys = in_smem ? s_keys : seg;
+  if (in_smem)
+    for (int i = threadIdx.x; i < n; i += TILE_THREADS) s_keys[i] = seg[i];
+  __syncthreads();
+  for (int k = 2; (k >> 1) < n; k <<= 1) {
+    sort_sweep<true>(keys, n, k);
+    __syncthreads();
+    for (int d = k >> 2; d > 0; d >>= 1) {
+      sort_sweep<false>(keys, n, d);
+      __syncthreads();
+    }
+  }
+  if (in_smem)
+    for (int i = threadIdx.x; i < n; i += TILE_THREADS) seg[i] = s_keys[i];
+  __syncthreads();
 }
 
 // Workspace carving (all int32 / uint2 arrays, 16B-aligned sections).

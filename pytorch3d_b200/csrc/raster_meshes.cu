@@ -23,6 +23,7 @@ namespace b200r {
 
 constexpr int SETUP_FACES = 256;  // faces per CTA in the setup pass (one per thread)
 constexpr int CHUNK = 256;        // faces staged per round in the fine pass
+constexpr int SMEMQ_MAX_K = 32;   // largest K served by the shared-memory queue kernel (mesh_fine_smemq_kernel)
 
 // ------------------------------------------------------------------------------------------------
 // Pass 1: per-face validity + blur-expanded box -> tile rectangle, count per tile.
@@ -164,8 +165,11 @@ struct Hit {
   float z, dist, b0, b1, b2;
 };
 
+// `full` / `max_z`: the pixel's queue already holds K hits, the farthest at depth max_z.  The reference
+// discards a further hit unless pz < q_max_z (rasterize_meshes.cu:226), so such a face is dropped right after
+// its depth is known -- before the three point-segment distances, the expensive part when blur_radius > 0.
 __device__ __forceinline__ bool eval_pixel_face(float px, float py, const Face& f, float den, float blur_radius,
-                                                bool persp, bool clip, Hit& h) {
+                                                bool persp, bool clip, bool full, float max_z, Hit& h) {
   float w0, w1, w2;
   bary_coords(px, py, f, den, w0, w1, w2);
   if (persp) bary_persp(w0, w1, w2, f.z0, f.z1, f.z2);
@@ -173,6 +177,7 @@ __device__ __forceinline__ bool eval_pixel_face(float px, float py, const Face& 
   if (clip) bary_clip(c0, c1, c2);
   const float pz = ffma(f.z2, c2, ffma(f.z0, c0, fmul(f.z1, c1)));
   if (!(pz >= 0.0f)) return false;  // behind the image plane (:163)
+  if (full && !(pz < max_z)) return false;
   const bool inside = w0 > 0.0f && w1 > 0.0f && w2 > 0.0f;
   if (!inside && !(blur_radius > 0.0f)) return false;  // dist >= 0 >= blur_radius always rejects (:175)
   const float dist = point_tri_dist(px, py, f);
@@ -300,8 +305,102 @@ struct TopK {
   }
 };
 
+// Queue policy of the K <= 8 kernel: TopK in registers + payload columns in shared memory.
+template <int KMAX>
+struct RegQueue {
+  TopK<KMAX> q;
+  float4* pay;  // this thread's payload column
+  int K;
+  __device__ __forceinline__ bool full() const { return q.size >= K; }
+  __device__ __forceinline__ float max_z() const { return q.max_z; }
+  __device__ __forceinline__ void offer(const Hit& h, int f) { q.offer(h, f, K, pay); }
+  __device__ __forceinline__ bool offer_neighbor(const Hit& h, int f, int nb) { return q.offer_neighbor(h, f, nb, pay); }
+};
+
+// Queue policy of the 8 < K <= 32 kernel: the same queue with its keys in dynamic shared memory, slot-major with
+// one column per thread (element k of this thread at [k * TILE_THREADS]) -- a dynamic slot index is free there, and
+// a 32-slot queue in registers would cost 64 registers plus 2 * KMAX predicated moves per insertion.  Only
+// (z, face) are kept (plus the signed distance when the clipped-face neighbour rule needs it); the barycentrics
+// of the K winners are recomputed in the epilogue with the same arithmetic, hence the same bits.
+template <bool NB>
+struct SmemQueue {
+  float* qz;
+  int* qi;
+  float* qd;  // NB only
+  int K, size, max_idx;
+  float max_zv;
+  __device__ __forceinline__ void init(unsigned char* base, int K_, int tid) {
+    K = K_;
+    qz = reinterpret_cast<float*>(base) + tid;
+    qi = reinterpret_cast<int*>(base) + K_ * TILE_THREADS + tid;
+    qd = NB ? reinterpret_cast<float*>(base) + 2 * K_ * TILE_THREADS + tid : nullptr;
+    size = 0;
+    max_idx = -1;
+    max_zv = -1000.0f;  // (:292)
+  }
+  __device__ __forceinline__ bool full() const { return size >= K; }
+  __device__ __forceinline__ float max_z() const { return max_zv; }
+  __device__ __forceinline__ void put(int slot, const Hit& h, int f) {
+    qz[slot * TILE_THREADS] = h.z;
+    qi[slot * TILE_THREADS] = f;
+    if (NB) qd[slot * TILE_THREADS] = h.dist;
+  }
+  __device__ __forceinline__ void offer(const Hit& h, int f) {  // (:216-236)
+    if (size < K) {
+      put(size, h, f);
+      if (h.z > max_zv) {
+        max_zv = h.z;
+        max_idx = size;
+      }
+      ++size;
+    } else if (h.z < max_zv) {
+      put(max_idx, h, f);
+      max_zv = h.z;
+      for (int i = 0; i < K; ++i) {
+        const float v = qz[i * TILE_THREADS];
+        if (v > max_zv) {
+          max_zv = v;
+          max_idx = i;
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ bool offer_neighbor(const Hit& h, int f, int nb) {  // (:186-215)
+    int at = -1;
+    for (int i = 0; i < size; ++i)
+      if (qi[i * TILE_THREADS] == nb) {
+        at = i;
+        break;
+      }
+    if (at < 0) return false;
+    if (NB && fabsf(h.dist) < fabsf(qd[at * TILE_THREADS])) {
+      put(at, h, f);
+      if (h.z > max_zv) {
+        max_zv = h.z;
+        max_idx = at;
+      }
+    }
+    return true;
+  }
+  // BubbleSort on (z, idx) (:322): keys are unique -> an insertion sort over the thread's own column
+  __device__ __forceinline__ void sort() {
+    for (int i = 1; i < size; ++i) {
+      const float tz = qz[i * TILE_THREADS];
+      const int ti = qi[i * TILE_THREADS];
+      int j = i - 1;
+      while (j >= 0 && key_less(tz, ti, qz[j * TILE_THREADS], qi[j * TILE_THREADS])) {
+        qz[(j + 1) * TILE_THREADS] = qz[j * TILE_THREADS];
+        qi[(j + 1) * TILE_THREADS] = qi[j * TILE_THREADS];
+        --j;
+      }
+      qz[(j + 1) * TILE_THREADS] = tz;
+      qi[(j + 1) * TILE_THREADS] = ti;
+    }
+  }
+};
+
 // Shared-memory face records of one staged chunk of the large-K kernel (mesh_fine_bigk_kernel), which stages from
-// face_verts itself; the K <= 8 kernels copy the setup pass's records instead (FineShared below).
+// face_verts itself; the K <= 32 kernels copy the setup pass's records instead (FineStage below).
 struct __align__(16) FaceChunk {
   float4 box[CHUNK];  // xmin, xmax, ymin, ymax (blur-expanded; empty box = never hit)
   float4 a[CHUNK];    // x0, y0, x1, y1
@@ -339,12 +438,13 @@ struct FineParams {
   const int64_t* first;
   const int64_t* num;
   const int* tile_offset;
-  const int* pairs;
+  int* pairs;  // tile lists; each CTA puts its own segment in ascending face order before reading it
   int64_t capacity;
   int n0;  // first image of this launch (grid.z is limited to 65535 images)
   int N, H, W, K, TY, TX;
   float rx, ry, blur_radius, sqrt_blur;
   int persp, clip, cull;
+  int smem_ints;  // dynamic shared memory of the launch, in 4-byte words (scratch of the in-kernel list sort)
   int64_t* pix_to_face;
   float* zbuf;
   float* bary;
@@ -378,18 +478,17 @@ __device__ __forceinline__ float warp_max(float v) {
 // lie in a given face's box.
 constexpr int ROUND = 64;
 
-// Dynamic shared memory of the fine kernel (53 KB for KMAX = 8: four CTAs per SM).
-template <int KMAX>
-struct FineShared {
+// Staging area of the fine kernels (21 KB), at the start of their dynamic shared memory; the queue storage follows.
+struct FineStage {
   float4 a[CHUNK];  // x0, y0, x1, y1            } the staged chunk: copies of the per-face records
   float4 b[CHUNK];  // x2, y2, den, face index   }
   float4 c[CHUNK];  // z0, z1, z2, neighbour     }
   union {
     float4 box[CHUNK];                          // blur > 0: blur-expanded boxes (pass A)
     unsigned mask[CHUNK / 32][TILE_THREADS];    // blur = 0: per pixel (thread), one bit per staged face
+    int sort_buf[2 * TILE_THREADS];             // exchange buffers of cta_sort256 (before the chunk is staged)
   } u;
   unsigned rng[CHUNK];                          // blur = 0: tile-local pixel rectangle c_lo | c_hi<<8 | r_lo<<16 | r_hi<<24
-  float4 pay[KMAX * TILE_THREADS];              // queue payload: (signed dist, bary0, bary1, bary2) per slot
   float col[TILE], row[TILE];                   // NDC coordinates of the tile's 16 pixel columns / rows
 };
 
@@ -424,31 +523,58 @@ __device__ __forceinline__ void store_pair_run(float4* run, const float4 (&mine)
   }
 }
 
+// The same for two separate runs of P (even) pieces each: `runA` belongs to the even lane's pixel, `runB` to the
+// odd lane's (a group of 8 slots of a pixel with K > 8: the two pixels' groups are K slots apart).  The lanes
+// swap every other piece, then both write run A (even lane piece 2r, odd lane piece 2r+1: one whole sector per
+// pair and instruction), then run B.
+template <int P>
+__device__ __forceinline__ void store_pair_split(float4* runA, float4* runB, const float4 (&mine)[P], int odd,
+                                                 bool vA, bool vB) {
+  static_assert(P % 2 == 0, "an even number of 16-byte pieces per run");
+  float4 recv[P / 2];  // even lane: B[2r]; odd lane: A[2r+1]
+#pragma unroll
+  for (int r = 0; r < P / 2; ++r) {
+    const float4 send = odd ? mine[2 * r] : mine[2 * r + 1];
+    recv[r].x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+    recv[r].y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+    recv[r].z = __shfl_xor_sync(0xffffffffu, send.z, 1);
+    recv[r].w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+  }
+#pragma unroll
+  for (int r = 0; r < P / 2; ++r)
+    if (vA) out_store(runA + 2 * r + odd, odd ? recv[r] : mine[2 * r]);
+#pragma unroll
+  for (int r = 0; r < P / 2; ++r)
+    if (vB) out_store(runB + 2 * r + odd, odd ? mine[2 * r + 1] : recv[r]);
+}
+
 // A tile no face touches: all of its outputs are -1.  Full tiles are written as whole 16-pixel row segments
-// (consecutive lanes -> consecutive 16 bytes) without computing anything per pixel.
+// (consecutive lanes -> consecutive 16 bytes) without computing anything per pixel.  KMAX > 0: K == KMAX is
+// checked and the loops are unrolled; KMAX == 0: any K that is a multiple of 4.
 template <int KMAX>
 __device__ __forceinline__ void write_empty_tile(const FineParams& p, int n, int tile_x, int tile_y) {
   const int tid = threadIdx.x;
   const int x0 = tile_x * TILE, y0 = tile_y * TILE;
   const int K = p.K;
-  if (K == KMAX && (KMAX % 4) == 0 && x0 + TILE <= p.W && y0 + TILE <= p.H) {
+  if ((KMAX == 0 || K == KMAX) && (K % 4) == 0 && x0 + TILE <= p.W && y0 + TILE <= p.H) {
     const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
-    constexpr int SEG_I = TILE * KMAX / 2;  // longlong2 per row segment of pix_to_face
-    constexpr int SEG_F = TILE * KMAX / 4;  // float4 per row segment of zbuf / dists (x3 for bary)
+    const int KK = KMAX > 0 ? KMAX : K;
+    const int SEG_I = TILE * KK / 2;  // longlong2 per row segment of pix_to_face
+    const int SEG_F = TILE * KK / 4;  // float4 per row segment of zbuf / dists (x3 for bary)
 #pragma unroll
     for (int e = tid; e < TILE * SEG_I; e += TILE_THREADS) {
-      const int64_t o = (((int64_t)n * p.H + y0 + e / SEG_I) * p.W + x0) * KMAX;
+      const int64_t o = (((int64_t)n * p.H + y0 + e / SEG_I) * p.W + x0) * KK;
       out_store(reinterpret_cast<longlong2*>(p.pix_to_face + o) + e % SEG_I, make_longlong2(-1ll, -1ll));
     }
 #pragma unroll
     for (int e = tid; e < TILE * SEG_F; e += TILE_THREADS) {
-      const int64_t o = (((int64_t)n * p.H + y0 + e / SEG_F) * p.W + x0) * KMAX;
+      const int64_t o = (((int64_t)n * p.H + y0 + e / SEG_F) * p.W + x0) * KK;
       out_store(reinterpret_cast<float4*>(p.zbuf + o) + e % SEG_F, m1);
       out_store(reinterpret_cast<float4*>(p.dists + o) + e % SEG_F, m1);
     }
 #pragma unroll
     for (int e = tid; e < TILE * SEG_F * 3; e += TILE_THREADS) {
-      const int64_t o = (((int64_t)n * p.H + y0 + e / (SEG_F * 3)) * p.W + x0) * KMAX;
+      const int64_t o = (((int64_t)n * p.H + y0 + e / (SEG_F * 3)) * p.W + x0) * KK;
       out_store(reinterpret_cast<float4*>(p.bary + o * 3) + e % (SEG_F * 3), m1);
     }
     return;
@@ -467,29 +593,33 @@ __device__ __forceinline__ void write_empty_tile(const FineParams& p, int n, int
   }
 }
 
-template <int KMAX, bool NB, bool SCAN>
-__global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FineParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FineShared<KMAX>& sh = *reinterpret_cast<FineShared<KMAX>*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31;
-  float4* pay = sh.pay + tid;
-  // grid = (tiles per row, tile rows, images): no integer divisions to find the tile
-  const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = p.n0 + blockIdx.z;
-  const int t = (n * p.TY + tile_y) * p.TX + tile_x;
-  // the tile's face list; tiles whose segment did not fit the pair buffer test every face of the mesh
-  const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
-  const bool overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
-  const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
-  if (count == 0) {
-    write_empty_tile<KMAX>(p, n, tile_x, tile_y);
-    return;
-  }
-  const int64_t mesh_first = p.first[n];
+// One candidate face (staged at slot j) against this thread's pixel.
+template <class Q, bool NB>
+__device__ __forceinline__ void consider_face(const FineStage& sh, int j, float px, float py, float blur_radius,
+                                              bool persp, bool clip, Q& q) {
+  const float4 fa = sh.a[j], fb = sh.b[j], fc = sh.c[j];
+  const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
+  const int nb = NB ? __float_as_int(fc.w) : -1;
+  Hit h;
+  // (a face with a clipped-face neighbour may replace that neighbour whatever its depth: no early rejection)
+  if (!eval_pixel_face(px, py, f, fb.z, blur_radius, persp, clip, q.full() && nb == -1, q.max_z(), h)) return;
+  const int fi = __float_as_int(fb.w);
+  if (NB && nb != -1 && q.offer_neighbor(h, fi, nb)) return;
+  q.offer(h, fi);
+}
 
-  int xo, yo;
-  thread_pixel(tile_x, tile_y, xo, yo);
-  const bool valid = xo < p.W && yo < p.H;
-  const int lc = xo - tile_x * TILE, lr = yo - tile_y * TILE;  // local column / row of my pixel
+// The body shared by the fine kernels: sort the tile's list, stage it chunk by chunk, find every pixel's
+// candidates and offer the hits to the pixel's queue `q`.
+template <class Q, bool NB, bool SCAN>
+__device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& sh, Q& q, int tile_x, int tile_y,
+                                               int seg_begin, int count, bool overflow, int64_t mesh_first,
+                                               bool valid, int lc, int lr) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool persp = p.persp != 0, clip = p.clip != 0;
+  const float blur_radius = p.blur_radius;
+  const bool sort_staged = !overflow && count <= CHUNK;  // (an overflowed tile walks the mesh's faces in order)
+  // (the long-list sort may use all of the kernel's shared memory: nothing lives there yet)
+  if (!overflow && count > CHUNK) cta_sort_segment(p.pairs + seg_begin, count, reinterpret_cast<int*>(&sh), p.smem_ints);
   // NDC coordinates of the tile's 16 pixel columns and rows (two IEEE divisions each): computed once per tile
   // by 32 threads, read by every thread after the barriers of the first chunk
   if (tid < 2 * TILE) {
@@ -500,25 +630,23 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
       sh.row[i] = pix_to_ndc(p.H - 1 - (tile_y * TILE + i), p.H, p.ry);
   }
 
-  TopK<KMAX> q;
-  q.init();
-  const bool persp = p.persp != 0, clip = p.clip != 0;
-  const int K = p.K;
-  const float blur_radius = p.blur_radius;
-  constexpr bool scan = SCAN;  // blur_radius = 0 (host dispatch)
-
   for (int base = 0; base < count; base += CHUNK) {
     const int nc = min(CHUNK, count - base);
     const int nwords = (nc + 31) >> 5;
     if (base > 0) __syncthreads();  // previous chunk fully consumed
+    int f = INT_MAX;
+    if (tid < nc) f = overflow ? (int)(mesh_first + base + tid) : p.pairs[seg_begin + base + tid];
+    if (sort_staged) {
+      f = cta_sort256(f, nc, sh.u.sort_buf);
+      if (nc > 32) __syncthreads();  // the exchange buffers alias the masks / boxes written next
+    }
     if (tid < nc) {
-      const int f = overflow ? (int)(mesh_first + base + tid) : p.pairs[seg_begin + base + tid];
       const float4* r = p.rec + (int64_t)f * 4;
       const float4 ra = __ldg(r + 0), rb = __ldg(r + 1), rc = __ldg(r + 2), rd = __ldg(r + 3);
       sh.a[tid] = ra;
       sh.b[tid] = rb;
       sh.c[tid] = rc;
-      if (scan) {
+      if (SCAN) {
         const int gx = __float_as_int(rd.x), gy = __float_as_int(rd.y), gz = __float_as_int(rd.z),
                   gw = __float_as_int(rd.w);
         const int c_lo = max(gx - tile_x * TILE, 0), c_hi = min(gy - tile_x * TILE, TILE - 1);
@@ -529,11 +657,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
         sh.u.box[tid] = rd;
       }
     }
-    if (scan) {
+    if (SCAN) {
       for (int w = 0; w < nwords; ++w) sh.u.mask[w][tid] = 0u;
     }
     __syncthreads();
-    if (scan) {
+    if (SCAN) {
       // ---- scan conversion (no blur band): a hit requires the pixel to be strictly inside the face, i.e. all
       //      three w_i = E_i / den > 0, which implies that every edge function E_i is non-zero and has the sign
       //      of den -- a test that needs no division.  Four lanes take one face and walk the rows of its pixel
@@ -585,18 +713,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
         while (m != 0u) {
           const int j = w * 32 + __ffs((int)m) - 1;
           m &= m - 1u;
-          const float4 fa = sh.a[j], fb = sh.b[j], fc = sh.c[j];
-          const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
-          Hit h;
-          if (eval_pixel_face(px, py, f, fb.z, blur_radius, persp, clip, h)) {
-            const int fi = __float_as_int(fb.w);
-            bool consumed = false;
-            if (NB) {
-              const int nb = __float_as_int(fc.w);
-              if (nb != -1) consumed = q.offer_neighbor(h, fi, nb, pay);
-            }
-            if (!consumed) q.offer(h, fi, K, pay);
-          }
+          consider_face<Q, NB>(sh, j, px, py, blur_radius, persp, clip, q);
         }
       }
       continue;  // chunk done
@@ -624,22 +741,57 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
         if (mine != 0ull) {
           const int j = sub + __ffsll((long long)mine) - 1;
           mine &= mine - 1ull;
-          const float4 fa = sh.a[j], fb = sh.b[j], fc = sh.c[j];
-          const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
-          Hit h;
-          if (eval_pixel_face(px, py, f, fb.z, blur_radius, persp, clip, h)) {
-            const int fi = __float_as_int(fb.w);
-            bool consumed = false;
-            if (NB) {
-              const int nb = __float_as_int(fc.w);
-              if (nb != -1) consumed = q.offer_neighbor(h, fi, nb, pay);
-            }
-            if (!consumed) q.offer(h, fi, K, pay);
-          }
+          consider_face<Q, NB>(sh, j, px, py, blur_radius, persp, clip, q);
         }
       }
     }
   }
+}
+
+// Which tile, which faces: grid = (tiles per row, tile rows, images) -- no integer divisions.
+struct TileWork {
+  int tile_x, tile_y, n, seg_begin, count;
+  bool overflow;
+};
+__device__ __forceinline__ TileWork tile_work(const FineParams& p) {
+  TileWork t;
+  t.tile_x = blockIdx.x;
+  t.tile_y = blockIdx.y;
+  t.n = p.n0 + blockIdx.z;
+  const int i = (t.n * p.TY + t.tile_y) * p.TX + t.tile_x;
+  // the tile's face list; tiles whose segment did not fit the pair buffer test every face of the mesh
+  t.seg_begin = p.tile_offset[i];
+  const int seg_end = p.tile_offset[i + 1];
+  t.overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
+  t.count = t.overflow ? (int)p.num[t.n] : seg_end - t.seg_begin;
+  return t;
+}
+
+template <int KMAX, bool NB, bool SCAN>
+__global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FineParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FineStage& sh = *reinterpret_cast<FineStage*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const TileWork t = tile_work(p);
+  const int tile_x = t.tile_x, tile_y = t.tile_y, n = t.n;
+  if (t.count == 0) {
+    write_empty_tile<KMAX>(p, n, tile_x, tile_y);
+    return;
+  }
+  int xo, yo;
+  thread_pixel(tile_x, tile_y, xo, yo);
+  const bool valid = xo < p.W && yo < p.H;
+  const int lc = xo - tile_x * TILE, lr = yo - tile_y * TILE;  // local column / row of my pixel
+
+  RegQueue<KMAX> rq;
+  rq.q.init();
+  rq.pay = reinterpret_cast<float4*>(smem_raw + sizeof(FineStage)) + tid;
+  rq.K = p.K;
+  fine_tile_body<RegQueue<KMAX>, NB, SCAN>(p, sh, rq, tile_x, tile_y, t.seg_begin, t.count, t.overflow, p.first[n],
+                                           valid, lc, lr);
+  TopK<KMAX>& q = rq.q;
+  float4* pay = rq.pay;
+  const int K = p.K;
 
   int slot[KMAX];
   q.sort(slot);
@@ -719,7 +871,109 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
 }
 
 // ------------------------------------------------------------------------------------------------
-// Large-K path (8 < K <= 150): the same queue in thread-local arrays holding only (z, face, dist); the
+// 8 < K <= 32: the same tile body with the queue keys in shared memory (SmemQueue); the winners' barycentrics
+// and distances are recomputed from the face records in the epilogue (identical arithmetic, identical bits).
+// Serves the reference's range of one kernel (rasterize_meshes.cu:630-736) without its 1.8 KB of thread-local
+// queue per pixel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void recompute_hit(const FineParams& p, int fi, float px, float py, Hit& h) {
+  const float4* r = p.rec + (int64_t)fi * 4;
+  const float4 fa = __ldg(r + 0), fb = __ldg(r + 1), fc = __ldg(r + 2);
+  const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
+  eval_pixel_face(px, py, f, fb.z, p.blur_radius, p.persp != 0, p.clip != 0, false, 0.0f, h);
+}
+
+template <bool NB, bool SCAN>
+__global__ void __launch_bounds__(TILE_THREADS, 2) mesh_fine_smemq_kernel(const FineParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FineStage& sh = *reinterpret_cast<FineStage*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const TileWork t = tile_work(p);
+  const int tile_x = t.tile_x, tile_y = t.tile_y, n = t.n;
+  if (t.count == 0) {
+    write_empty_tile<0>(p, n, tile_x, tile_y);
+    return;
+  }
+  int xo, yo;
+  thread_pixel(tile_x, tile_y, xo, yo);
+  const bool valid = xo < p.W && yo < p.H;
+  const int lc = xo - tile_x * TILE, lr = yo - tile_y * TILE;
+  const int K = p.K;
+
+  SmemQueue<NB> q;
+  q.init(smem_raw + sizeof(FineStage), K, tid);
+  fine_tile_body<SmemQueue<NB>, NB, SCAN>(p, sh, q, tile_x, tile_y, t.seg_begin, t.count, t.overflow, p.first[n],
+                                          valid, lc, lr);
+  q.sort();
+  const float px = sh.col[lc], py = sh.row[lr];
+  const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
+  if ((K & 7) == 0) {
+    // groups of 8 slots: 64 B of pix_to_face, 32 B of zbuf / dists, 96 B of barycentrics per pixel -- lanes
+    // 2m / 2m+1 (adjacent pixels) write each group together, whole sectors per instruction
+    const int odd = lane & 1;
+    const bool vA = __shfl_sync(0xffffffffu, (int)valid, lane & ~1) != 0;
+    const bool vB = __shfl_sync(0xffffffffu, (int)valid, lane | 1) != 0;
+    const int64_t oa = o - (int64_t)odd * K, ob = oa + K;  // the even / odd lane's pixel
+    for (int g = 0; g < K; g += 8) {
+      float4 pi[4], pzv[2], pd[2], pb[6];
+      float z[8], d[8], b[24];
+      int id[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        Hit h = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
+        id[u] = -1;
+        if (g + u < q.size) {
+          id[u] = q.qi[(g + u) * TILE_THREADS];
+          recompute_hit(p, id[u], px, py, h);
+        }
+        z[u] = h.z;
+        d[u] = h.dist;
+        b[3 * u + 0] = h.b0;
+        b[3 * u + 1] = h.b1;
+        b[3 * u + 2] = h.b2;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)  // int64 = (low word, sign word)
+        pi[u] = make_float4(__int_as_float(id[2 * u]), __int_as_float(id[2 * u] >> 31),
+                            __int_as_float(id[2 * u + 1]), __int_as_float(id[2 * u + 1] >> 31));
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        pzv[u] = make_float4(z[4 * u], z[4 * u + 1], z[4 * u + 2], z[4 * u + 3]);
+        pd[u] = make_float4(d[4 * u], d[4 * u + 1], d[4 * u + 2], d[4 * u + 3]);
+      }
+#pragma unroll
+      for (int u = 0; u < 6; ++u) pb[u] = make_float4(b[4 * u], b[4 * u + 1], b[4 * u + 2], b[4 * u + 3]);
+      store_pair_split<4>(reinterpret_cast<float4*>(p.pix_to_face + oa + g),
+                          reinterpret_cast<float4*>(p.pix_to_face + ob + g), pi, odd, vA, vB);
+      store_pair_split<2>(reinterpret_cast<float4*>(p.zbuf + oa + g), reinterpret_cast<float4*>(p.zbuf + ob + g), pzv,
+                          odd, vA, vB);
+      store_pair_split<2>(reinterpret_cast<float4*>(p.dists + oa + g), reinterpret_cast<float4*>(p.dists + ob + g),
+                          pd, odd, vA, vB);
+      store_pair_split<6>(reinterpret_cast<float4*>(p.bary + (oa + g) * 3),
+                          reinterpret_cast<float4*>(p.bary + (ob + g) * 3), pb, odd, vA, vB);
+    }
+    return;
+  }
+  if (!valid) return;
+  for (int k = 0; k < K; ++k) {
+    Hit h = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
+    long long id = -1;
+    if (k < q.size) {
+      const int fi = q.qi[k * TILE_THREADS];
+      recompute_hit(p, fi, px, py, h);
+      id = fi;
+    }
+    p.pix_to_face[o + k] = id;
+    p.zbuf[o + k] = h.z;
+    p.dists[o + k] = h.dist;
+    p.bary[(o + k) * 3 + 0] = h.b0;
+    p.bary[(o + k) * 3 + 1] = h.b1;
+    p.bary[(o + k) * 3 + 2] = h.b2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Large-K path (32 < K <= 150): the same queue in thread-local arrays holding only (z, face, dist); the
 // barycentrics of the final winners are recomputed (same arithmetic, so identical values).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const FineParams p) {
@@ -741,6 +995,10 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const Fine
   const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
   const bool persp = p.persp != 0, clip = p.clip != 0, cull = p.cull != 0;
   const int K = p.K;
+
+  // ascending face order (see cta_sort256); the staging area doubles as the sort's scratch
+  if (!overflow && count > 1)
+    cta_sort_segment(p.pairs + seg_begin, count, reinterpret_cast<int*>(&s), (int)(sizeof(FaceChunk) / sizeof(int)));
 
   float qz[B200R_MAX_K], qd[B200R_MAX_K];
   int qi[B200R_MAX_K];
@@ -770,9 +1028,9 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const Fine
         const float4 fa = s.a[j], fb = s.b[j], fc = s.c[j];
         const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
         Hit h;
-        if (!eval_pixel_face(px, py, f, fb.z, p.blur_radius, persp, clip, h)) continue;
-        const int fi = __float_as_int(fb.w);
         const int nb = __float_as_int(fc.w);
+        if (!eval_pixel_face(px, py, f, fb.z, p.blur_radius, persp, clip, qn >= K && nb == -1, q_max_z, h)) continue;
+        const int fi = __float_as_int(fb.w);
         int at = -1;
         if (nb != -1)
           for (int i = 0; i < qn; ++i)
@@ -835,7 +1093,7 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const Fine
       const float* v = p.face_verts + (int64_t)qi[k] * 9;
       const Face f = {__ldg(v + 0), __ldg(v + 1), __ldg(v + 2), __ldg(v + 3), __ldg(v + 4),
                       __ldg(v + 5), __ldg(v + 6), __ldg(v + 7), __ldg(v + 8)};
-      eval_pixel_face(px, py, f, bary_denominator(f), p.blur_radius, persp, clip, h);
+      eval_pixel_face(px, py, f, bary_denominator(f), p.blur_radius, persp, clip, false, 0.0f, h);
       id = qi[k];
     }
     p.pix_to_face[o + k] = id;
@@ -1011,9 +1269,9 @@ __device__ __forceinline__ void warp_scatter(float* __restrict__ grad_face_verts
   }
 }
 
-// KV > 0: K == KV (a multiple of 4) and the pixel's KV face indices are fetched up front with 16-byte loads
-// (a pixel with no face costs nothing else); KV == 0: any K, scalar loads.
-template <int KV>
+// GV > 0: K is a multiple of GV (8 or 4) and a pixel's face indices are fetched GV at a time with 16-byte loads
+// (a group without faces costs nothing else); GV == 0: any K, scalar loads.
+template <int GV>
 __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_backward_kernel(const BackwardParams p) {
   const int lane = threadIdx.x & 31;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = p.n0 + blockIdx.z;  // grid = (TX, TY, images)
@@ -1025,34 +1283,35 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_backward_kernel(const Ba
   const int K = p.K;
   const int64_t o = in_image ? (((int64_t)n * p.H + yo) * p.W + xo) * K : 0;
   const bool persp = p.persp != 0, clip = p.clip != 0;
+  constexpr int G = GV > 0 ? GV : 1;
 
-  int fk[KV > 0 ? KV : 1];
-  if (KV > 0) {
+  for (int k0 = 0; k0 < K; k0 += G) {
+    int fk[G];
+    if (GV > 0) {
 #pragma unroll
-    for (int k = 0; k < KV; k += 2) {
-      longlong2 v = make_longlong2(-1, -1);
-      if (in_image) v = __ldg(reinterpret_cast<const longlong2*>(p.pix_to_face + o + k));
-      fk[k] = (int)v.x;  // the reference reads the int64 index into an int as well (:471)
-      fk[k + 1] = (int)v.y;
+      for (int k = 0; k < G; k += 2) {
+        longlong2 v = make_longlong2(-1, -1);
+        if (in_image) v = __ldg(reinterpret_cast<const longlong2*>(p.pix_to_face + o + k0 + k));
+        fk[k] = (int)v.x;  // the reference reads the int64 index into an int as well (:471)
+        fk[k + 1] = (int)v.y;
+      }
+    } else {
+      fk[0] = in_image ? (int)p.pix_to_face[o + k0] : -1;
     }
-  }
-  for (int k = 0; k < K; ++k) {
-    int face = -1;
-    if (KV > 0) {
-      face = fk[0];
+#pragma unroll 1
+    for (int j = 0; j < G; ++j) {
+      const int face = fk[0];
 #pragma unroll
-      for (int j = 0; j + 1 < KV; ++j) fk[j] = fk[j + 1];  // rotate: one copy of the gradient code
-    } else if (in_image) {
-      face = (int)p.pix_to_face[o + k];
+      for (int u = 0; u + 1 < G; ++u) fk[u] = fk[u + 1];  // rotate: one copy of the gradient code
+      if (!__any_sync(0xffffffffu, face >= 0)) continue;  // padded slots (:472-474)
+      float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (face >= 0) {
+        const int64_t i = o + k0 + j;
+        backward_one(p, px, py, face, __ldg(p.grad_zbuf + i), __ldg(p.grad_dists + i), __ldg(p.grad_bary + i * 3),
+                     __ldg(p.grad_bary + i * 3 + 1), __ldg(p.grad_bary + i * 3 + 2), persp, clip, g);
+      }
+      warp_scatter(p.grad_face_verts, face, g, lane);
     }
-    if (!__any_sync(0xffffffffu, face >= 0)) continue;  // padded slots (:472-474)
-    float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (face >= 0) {
-      const int64_t i = o + k;
-      backward_one(p, px, py, face, __ldg(p.grad_zbuf + i), __ldg(p.grad_dists + i), __ldg(p.grad_bary + i * 3),
-                   __ldg(p.grad_bary + i * 3 + 1), __ldg(p.grad_bary + i * 3 + 2), persp, clip, g);
-    }
-    warp_scatter(p.grad_face_verts, face, g, lane);
   }
 }
 
@@ -1144,11 +1403,7 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
                                                                     ws.capacity);
     B200R_LAUNCHED("tile_fill_kernel");
   }
-  if (ntiles > 0) {
-    tile_sort_kernel<<<(unsigned)((ntiles + SORT_TILES_PER_CTA - 1) / SORT_TILES_PER_CTA), SORT_THREADS, 0, stream>>>(
-        ws.tile_offset, ws.pairs, ws.capacity, (int)ntiles, sort_multiplier(ntiles));
-    B200R_LAUNCHED("tile_sort_kernel");
-  }
+  // (no sort launch: every fine CTA puts its own tile list in ascending face order, see cta_sort256)
   if (prof) phase_timer().record(1, stream);
   FineParams p;
   p.face_verts = face_verts;
@@ -1163,35 +1418,37 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
   p.N = N; p.H = H; p.W = W; p.K = K; p.TY = TY; p.TX = TX;
   p.rx = rx; p.ry = ry; p.blur_radius = blur_radius; p.sqrt_blur = sqrt_blur;
   p.persp = perspective_correct; p.clip = clip_barycentric_coords; p.cull = cull_backfaces;
+  p.smem_ints = 0;
   p.pix_to_face = pix_to_face; p.zbuf = zbuf; p.bary = bary; p.dists = dists;
   const unsigned grid = (unsigned)ntiles;
   const bool no_blur = !(blur_radius > 0.0f);
-#define B200R_FINE_ONE(KM, NBV, SC)                                                                        \
+  int dev_ = 0;
+  B200R_CUDA_OK(cudaGetDevice(&dev_));
+  // > 48 KB of dynamic shared memory: opt-in once per kernel and device
+#define B200R_FINE_LAUNCH(KERNEL, SMEM_MAX, SMEM)                                                         \
   do {                                                                                                   \
-    static bool configured[64] = {}; /* > 48 KB of dynamic shared memory: opt-in per kernel and device */ \
-    int dev_ = 0;                                                                                        \
-    B200R_CUDA_OK(cudaGetDevice(&dev_));                                                                 \
+    static bool configured[64] = {};                                                                     \
     if (dev_ < 0 || dev_ >= 64 || !configured[dev_]) {                                                   \
-      B200R_CUDA_OK(cudaFuncSetAttribute(mesh_fine_kernel<KM, NBV, SC>,                                    \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,                    \
-                                         (int)sizeof(FineShared<KM>)));                                  \
+      B200R_CUDA_OK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_MAX))); \
       if (dev_ >= 0 && dev_ < 64) configured[dev_] = true;                                               \
     }                                                                                                    \
+    p.smem_ints = (int)((SMEM) / sizeof(int));                                                           \
     for (p.n0 = 0; p.n0 < N; p.n0 += 65535) {                                                            \
       const dim3 grid3((unsigned)TX, (unsigned)TY, (unsigned)min(N - p.n0, 65535));                      \
-      mesh_fine_kernel<KM, NBV, SC><<<grid3, TILE_THREADS, sizeof(FineShared<KM>), stream>>>(p);         \
+      KERNEL<<<grid3, TILE_THREADS, (SMEM), stream>>>(p);                                                \
     }                                                                                                    \
   } while (0)
-#define B200R_FINE(KM)                   \
-  do {                                   \
-    if (neighbor && no_blur)             \
-      B200R_FINE_ONE(KM, true, true);    \
-    else if (neighbor)                   \
-      B200R_FINE_ONE(KM, true, false);   \
-    else if (no_blur)                    \
-      B200R_FINE_ONE(KM, false, true);   \
-    else                                 \
-      B200R_FINE_ONE(KM, false, false);  \
+#define B200R_FINE(KM)                                                                                    \
+  do {                                                                                                   \
+    constexpr size_t smem_ = sizeof(FineStage) + sizeof(float4) * KM * TILE_THREADS;                     \
+    if (neighbor && no_blur)                                                                             \
+      B200R_FINE_LAUNCH((mesh_fine_kernel<KM, true, true>), smem_, smem_);                               \
+    else if (neighbor)                                                                                   \
+      B200R_FINE_LAUNCH((mesh_fine_kernel<KM, true, false>), smem_, smem_);                              \
+    else if (no_blur)                                                                                    \
+      B200R_FINE_LAUNCH((mesh_fine_kernel<KM, false, true>), smem_, smem_);                              \
+    else                                                                                                 \
+      B200R_FINE_LAUNCH((mesh_fine_kernel<KM, false, false>), smem_, smem_);                             \
   } while (0)
   if (K <= 1)
     B200R_FINE(1);
@@ -1201,10 +1458,24 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
     B200R_FINE(4);
   else if (K <= 8)
     B200R_FINE(8);
-  else
+  else if (K <= SMEMQ_MAX_K) {
+    // queue keys in shared memory: (z, face) per slot, plus the signed distance for the neighbour rule
+    const size_t smem_max_nb = sizeof(FineStage) + (size_t)SMEMQ_MAX_K * TILE_THREADS * 12;
+    const size_t smem_max = sizeof(FineStage) + (size_t)SMEMQ_MAX_K * TILE_THREADS * 8;
+    const size_t smem_nb = sizeof(FineStage) + (size_t)K * TILE_THREADS * 12;
+    const size_t smem = sizeof(FineStage) + (size_t)K * TILE_THREADS * 8;
+    if (neighbor && no_blur)
+      B200R_FINE_LAUNCH((mesh_fine_smemq_kernel<true, true>), smem_max_nb, smem_nb);
+    else if (neighbor)
+      B200R_FINE_LAUNCH((mesh_fine_smemq_kernel<true, false>), smem_max_nb, smem_nb);
+    else if (no_blur)
+      B200R_FINE_LAUNCH((mesh_fine_smemq_kernel<false, true>), smem_max, smem);
+    else
+      B200R_FINE_LAUNCH((mesh_fine_smemq_kernel<false, false>), smem_max, smem);
+  } else
     mesh_fine_bigk_kernel<<<grid, TILE_THREADS, 0, stream>>>(p);
 #undef B200R_FINE
-#undef B200R_FINE_ONE
+#undef B200R_FINE_LAUNCH
   B200R_LAUNCHED("mesh_fine_kernel");
   if (prof) {
     phase_timer().record(2, stream);
@@ -1274,9 +1545,9 @@ extern "C" int b200r_rasterize_meshes_backward(const float* face_verts, int64_t 
   if (prof) phase_timer().record(3, stream);
   for (p.n0 = 0; p.n0 < N; p.n0 += 65535) {  // grid.z is limited to 65535 images per launch
     const dim3 bgrid((unsigned)TX, (unsigned)TY, (unsigned)min(N - p.n0, 65535));
-    if (K == 8)
+    if ((K & 7) == 0)
       mesh_backward_kernel<8><<<bgrid, TILE_THREADS, 0, stream>>>(p);
-    else if (K == 4)
+    else if ((K & 3) == 0)
       mesh_backward_kernel<4><<<bgrid, TILE_THREADS, 0, stream>>>(p);
     else
       mesh_backward_kernel<0><<<bgrid, TILE_THREADS, 0, stream>>>(p);

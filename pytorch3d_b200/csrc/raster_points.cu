@@ -17,15 +17,21 @@
 namespace b200r {
 
 constexpr int SETUP_POINTS = 256;
-constexpr int PCHUNK = 512;  // points staged per round (2 per thread)
+constexpr int PCHUNK = 256;                  // points staged per round (one per thread)
+constexpr int QSTRIDE = TILE_THREADS + 1;    // row stride of the per-thread columns in shared memory: slot k of
+                                             // thread t lives in bank (k + t) % 32, so neither a warp reading one
+                                             // slot nor the row-major write-out of a pixel's K slots conflicts
+constexpr int SMEMQ_MAX_K = 32;              // largest K served by the shared-memory queue kernel
+constexpr size_t POINT_RECORD_BYTES = 16;    // (x, y, z, radius) per point, written by the setup pass
 
-// Pass 1: per-point box (x +- r, y +- r), skip z < 0 (rasterize_coarse.cu:53-74), count per tile.
+// Pass 1: per-point box (x +- r, y +- r), skip z < 0 (rasterize_coarse.cu:53-74), count per tile, and the
+// 16-byte (x, y, z, r) record the fine pass stages with one vector load.
 // The CTA's 256 points (3072 contiguous bytes of the packed (P,3) array) arrive by one TMA bulk copy.
 __global__ void __launch_bounds__(SETUP_POINTS)
     points_setup_count_kernel(const float* __restrict__ points, const float* __restrict__ radius, int64_t P,
                               const int64_t* __restrict__ first, const int64_t* __restrict__ num, int N, int H,
                               int W, int TY, int TX, float rx, float ry, uint4* __restrict__ rect,
-                              int* __restrict__ tile_count) {
+                              int* __restrict__ tile_count, float4* __restrict__ prec) {
   __shared__ __align__(16) float s_pts[SETUP_POINTS * 3];
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x;
@@ -46,119 +52,49 @@ __global__ void __launch_bounds__(SETUP_POINTS)
     n = find_owner(first, num, N, pi);
     if (n >= 0 && !(z < 0.0f)) rc = bbox_to_tile_rect(fsub(x, r), fadd(x, r), fsub(y, r), fadd(y, r), H, W, rx, ry);
     rect[pi] = make_uint4(rc.x, rc.y, (uint32_t)max(n, 0), 0u);
+    prec[pi] = make_float4(x, y, z, r);
   }
   warp_count_rect(rc, n, TY, TX, tile_count, tid & 31);  // all lanes participate
 }
 
-// The K nearest points of one pixel: the reference's queue (rasterize_points.cu:61-79) restated for
-// registers -- an UNSORTED array of K slots plus the tracked maximum z; a hit fills the next free slot or,
-// when full and pz < q_max_z, overwrites the tracked maximum, which is then searched again.  Points arrive
-// in ascending index order (sorted tile lists), so tie behaviour equals the reference's naive kernel.
-template <int KMAX>
-struct PTopK {
-  float z[KMAX];
-  int id[KMAX];
-  float d[KMAX];
-  int size;
-  float max_z;
-  int max_idx;
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int i = 0; i < KMAX; ++i) {
-      z[i] = -1.0f;
-      id[i] = -1;
-      d[i] = -1.0f;
-    }
-    size = 0;
-    max_z = -1000.0f;
-    max_idx = -1;
-  }
-  __device__ __forceinline__ void put(int slot, float pz, int p, float d2) {
-#pragma unroll
-    for (int i = 0; i < KMAX; ++i) {
-      const bool w = i == slot;
-      z[i] = w ? pz : z[i];
-      id[i] = w ? p : id[i];
-      d[i] = w ? d2 : d[i];
-    }
-  }
-  __device__ __forceinline__ void offer(float pz, int p, float d2, int K) {
-    if (size < K) {
-      put(size, pz, p, d2);
-      if (pz > max_z) {
-        max_z = pz;
-        max_idx = size;
-      }
-      ++size;
-    } else if (pz < max_z) {
-      put(max_idx, pz, p, d2);
-      max_z = pz;
-#pragma unroll
-      for (int i = 0; i < KMAX; ++i) {
-        if (i < K && z[i] > max_z) {
-          max_z = z[i];
-          max_idx = i;
-        }
-      }
-    }
-  }
-  // BubbleSort on z only (rasterize_points.cu:26-28): a STABLE sort, so z-ties keep slot order.  An
-  // odd-even transposition network with a strict compare is stable too and gives the same permutation.
-  __device__ __forceinline__ void sort() {
-#pragma unroll
-    for (int i = 0; i < KMAX; ++i)
-      if (i >= size) z[i] = FLT_MAX;
-#pragma unroll
-    for (int r = 0; r < KMAX; ++r) {
-#pragma unroll
-      for (int i = r & 1; i + 1 < KMAX; i += 2) {
-        if (z[i + 1] < z[i]) {
-          float t;
-          int ti;
-          t = z[i]; z[i] = z[i + 1]; z[i + 1] = t;
-          ti = id[i]; id[i] = id[i + 1]; id[i + 1] = ti;
-          t = d[i]; d[i] = d[i + 1]; d[i + 1] = t;
-        }
-      }
-    }
-  }
-};
-
-struct __align__(16) PointChunk {
-  float4 box[PCHUNK];  // xmin, xmax, ymin, ymax (empty = never hit)
+// One staged chunk of points.
+struct __align__(16) PointStage {
+  union {
+    float4 box[PCHUNK];           // xmin, xmax, ymin, ymax (empty = never hit)
+    int sort_buf[2 * TILE_THREADS];  // exchange buffers of cta_sort256 (before the chunk is staged)
+  } u;
   float4 rec[PCHUNK];  // x, y, z, r^2
   int id[PCHUNK];
 };
 
 struct PointFineParams {
-  const float* points;
-  const float* radius;
+  const float4* prec;  // (x, y, z, r) per point
   const int64_t* first;
   const int64_t* num;
   const int* tile_offset;
-  const int* pairs;
+  int* pairs;  // tile lists; each CTA puts its own segment in ascending point order before reading it
   int64_t capacity;
+  int n0;  // first image of this launch (grid.z is limited to 65535 images)
   int N, H, W, K, TY, TX;
   float rx, ry;
+  int smem_ints;  // dynamic shared memory of the launch in 4-byte words (scratch of the in-kernel list sort)
+  int vec_ok;     // (W * K) % 4 == 0 and 16-byte aligned outputs: row segments can be written as 16-byte pieces
   int32_t* idx;
   float* zbuf;
   float* dists;
 };
 
-__device__ __forceinline__ void stage_point(PointChunk& s, int slot, const float* __restrict__ points,
-                                            const float* __restrict__ radius, int pi) {
-  const float x = __ldg(points + (int64_t)pi * 3 + 0), y = __ldg(points + (int64_t)pi * 3 + 1),
-              z = __ldg(points + (int64_t)pi * 3 + 2);
-  const float r = __ldg(radius + pi);
+__device__ __forceinline__ void stage_point(PointStage& s, int slot, const float4* __restrict__ prec, int pi) {
+  const float4 r = __ldg(prec + pi);
   float xmin = FLT_MAX, xmax = -FLT_MAX, ymin = FLT_MAX, ymax = -FLT_MAX;
-  if (!(z < 0.0f)) {  // points behind the camera are not rendered (rasterize_points.cu:55-56)
-    xmin = fsub(x, r);
-    xmax = fadd(x, r);
-    ymin = fsub(y, r);
-    ymax = fadd(y, r);
+  if (!(r.z < 0.0f)) {  // points behind the camera are not rendered (rasterize_points.cu:55-56)
+    xmin = fsub(r.x, r.w);
+    xmax = fadd(r.x, r.w);
+    ymin = fsub(r.y, r.w);
+    ymax = fadd(r.y, r.w);
   }
-  s.box[slot] = make_float4(xmin, xmax, ymin, ymax);
-  s.rec[slot] = make_float4(x, y, z, fmul(r, r));
+  s.u.box[slot] = make_float4(xmin, xmax, ymin, ymax);
+  s.rec[slot] = make_float4(r.x, r.y, r.z, fmul(r.w, r.w));
   s.id[slot] = pi;
 }
 
@@ -168,53 +104,48 @@ __device__ __forceinline__ void pthread_pixel(int tile_x, int tile_y, int& xo, i
   yo = tile_y * TILE + (w >> 1) * 4 + (lane >> 3);
 }
 
-// KMAX > 0: register top-K; KMAX == 0: thread-local arrays for K up to 150.
-template <int KMAX>
-__global__ void __launch_bounds__(TILE_THREADS) points_fine_kernel(const PointFineParams p) {
-  __shared__ PointChunk s;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int t = blockIdx.x;
-  const int n = t / (p.TY * p.TX);
-  const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
-  int xo, yo;
-  pthread_pixel(tile_x, tile_y, xo, yo);
-  const bool valid = xo < p.W && yo < p.H;
-  const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
-  const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
-  float col[8], row[4];  // the footprint's 8 column and 4 row coordinates (lane = row * 8 + column)
-#pragma unroll
-  for (int c = 0; c < 8; ++c) col[c] = __shfl_sync(0xffffffffu, px, c);
-#pragma unroll
-  for (int r = 0; r < 4; ++r) row[r] = __shfl_sync(0xffffffffu, py, 8 * r);
+// Thread that owns local pixel (row r, column c) of the tile (inverse of pthread_pixel).
+__device__ __forceinline__ int thread_of_pixel(int r, int c) {
+  return ((r >> 2) * 2 + (c >> 3)) * 32 + (r & 3) * 8 + (c & 7);
+}
 
-  const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
+// The tile body shared by the point kernels: sort the tile's list, stage it chunk by chunk, box-test (pass A: one
+// lane per point against the warp's footprint + bit-matrix transpose, see raster_meshes.cu) and offer every hit
+// to `offer(z, point, dist2)` in ascending point order.
+template <class Offer>
+__device__ __forceinline__ void points_tile_body(const PointFineParams& p, PointStage& s, int* smem_ints_base,
+                                                 int tile, int n, bool valid, float px, float py, Offer offer) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int seg_begin = p.tile_offset[tile], seg_end = p.tile_offset[tile + 1];
   const bool overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
   const int64_t cloud_first = p.first[n];
   const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
-  const int K = p.K;
-
-  constexpr int QN = KMAX > 0 ? KMAX : 1;
-  PTopK<QN> q;
-  float lz[KMAX > 0 ? 1 : B200R_MAX_K];
-  int li[KMAX > 0 ? 1 : B200R_MAX_K];
-  float ld[KMAX > 0 ? 1 : B200R_MAX_K];
-  int ln = 0, l_max_idx = -1;
-  float l_max_z = -1000.0f;
-  if (KMAX > 0) q.init();
+  const bool sort_staged = !overflow && count <= PCHUNK;
+  if (!overflow && count > PCHUNK) cta_sort_segment(p.pairs + seg_begin, count, smem_ints_base, p.smem_ints);
 
   for (int base = 0; base < count; base += PCHUNK) {
     const int nc = min(PCHUNK, count - base);
-    __syncthreads();
-    for (int j = tid; j < nc; j += TILE_THREADS) {
-      const int pi = overflow ? (int)(cloud_first + base + j) : p.pairs[seg_begin + base + j];
-      stage_point(s, j, p.points, p.radius, pi);
+    if (base > 0) __syncthreads();  // previous chunk fully consumed
+    int pi = INT_MAX;
+    if (tid < nc) pi = overflow ? (int)(cloud_first + base + tid) : p.pairs[seg_begin + base + tid];
+    if (sort_staged) {
+      pi = cta_sort256(pi, nc, s.u.sort_buf);
+      if (nc > 32) __syncthreads();  // the exchange buffers alias the boxes written next
     }
+    if (tid < nc) stage_point(s, tid, p.prec, pi);
     __syncthreads();
     for (int sub = 0; sub < nc; sub += 64) {
-      // pass A: 64-bit mask of the points of this round whose box contains my pixel (see raster_meshes.cu)
+      // pass A: 64-bit mask of the points of this round whose box contains my pixel
       unsigned m0 = 0, m1 = 0;
-      if (sub + lane < nc) m0 = box_pixel_mask(s.box[sub + lane], col, row);
-      if (sub + 32 + lane < nc) m1 = box_pixel_mask(s.box[sub + 32 + lane], col, row);
+      {
+        float col[8], row[4];  // the footprint's 8 column and 4 row coordinates (lane = row * 8 + column)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) col[c] = __shfl_sync(0xffffffffu, px, c);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) row[r] = __shfl_sync(0xffffffffu, py, 8 * r);
+        if (sub + lane < nc) m0 = box_pixel_mask(s.u.box[sub + lane], col, row);
+        if (sub + 32 + lane < nc) m1 = box_pixel_mask(s.u.box[sub + 32 + lane], col, row);
+      }
       m0 = warp_transpose_bits(m0, lane);
       if (sub + 32 < nc) m1 = warp_transpose_bits(m1, lane);
       unsigned long long mine = valid ? (((unsigned long long)m1 << 32) | m0) : 0ull;
@@ -228,176 +159,181 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_kernel(const PointFi
         const float dx = fsub(px, r.x), dy = fsub(py, r.y);
         const float d2 = sqnorm2(dx, dy);
         if (r.z < 0.0f || !(d2 < r.w)) continue;
-        const int pi = s.id[j];
-        if (KMAX > 0) {
-          q.offer(r.z, pi, d2, K);
-        } else if (ln < K) {
-          lz[ln] = r.z;
-          li[ln] = pi;
-          ld[ln] = d2;
-          if (r.z > l_max_z) {
-            l_max_z = r.z;
-            l_max_idx = ln;
-          }
-          ++ln;
-        } else if (r.z < l_max_z) {
-          lz[l_max_idx] = r.z;
-          li[l_max_idx] = pi;
-          ld[l_max_idx] = d2;
-          l_max_z = r.z;
-          for (int i = 0; i < K; ++i)
-            if (lz[i] > l_max_z) {
-              l_max_z = lz[i];
-              l_max_idx = i;
-            }
-        }
+        offer(r.z, s.id[j], d2);
       }
-    }
-  }
-  if (!valid) return;
-  const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
-  if (KMAX > 0) {
-    q.sort();
-#pragma unroll
-    for (int k = 0; k < QN; ++k) {
-      if (k < K) {
-        const bool e = k >= q.size;
-        p.idx[o + k] = e ? -1 : q.id[k];
-        p.zbuf[o + k] = e ? -1.0f : q.z[k];
-        p.dists[o + k] = q.d[k];
-      }
-    }
-  } else {
-    for (int i = 1; i < ln; ++i) {  // stable insertion sort on z only
-      const float tz = lz[i], td = ld[i];
-      const int ti = li[i];
-      int j = i - 1;
-      while (j >= 0 && tz < lz[j]) {
-        lz[j + 1] = lz[j];
-        li[j + 1] = li[j];
-        ld[j + 1] = ld[j];
-        --j;
-      }
-      lz[j + 1] = tz;
-      li[j + 1] = ti;
-      ld[j + 1] = td;
-    }
-    for (int k = 0; k < K; ++k) {
-      p.idx[o + k] = k < ln ? li[k] : -1;
-      p.zbuf[o + k] = k < ln ? lz[k] : -1.0f;
-      p.dists[o + k] = k < ln ? ld[k] : -1.0f;
     }
   }
 }
 
-// Medium K (5..32): the queue lives in dynamic shared memory as three [K][256] arrays (slot-major, one column
-// per thread), where the dynamic slot index of the reference's queue costs nothing: appending a hit is three
-// stores instead of 3*KMAX predicated register moves, the kernel needs ~50 registers instead of 117 (K = 10),
-// and the final stable sort on z is an insertion sort over the thread's own column.
+// K <= 32: the reference's queue (rasterize_points.cu:61-79) -- an UNSORTED array of K slots plus the tracked
+// maximum z; a hit fills the next free slot or, when full and pz < q_max_z, overwrites the tracked maximum,
+// which is then searched again -- with its three arrays in dynamic shared memory as per-thread columns, where
+// the dynamic slot index costs nothing.  Points arrive in ascending index order (sorted tile lists), so tie
+// behaviour equals the reference's naive kernel.  The epilogue sorts each column (stable, on z only) and the CTA
+// writes the tile's outputs row segment by row segment: 16 pixels x K values are contiguous in memory, so every
+// store instruction fills whole 32-byte sectors (per-pixel stores at a 4*K-byte stride filled one eighth).
 __global__ void __launch_bounds__(TILE_THREADS) points_fine_smem_kernel(const PointFineParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PointChunk& s = *reinterpret_cast<PointChunk*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31;
+  PointStage& s = *reinterpret_cast<PointStage*>(smem_raw);
+  const int tid = threadIdx.x;
   const int K = p.K;
-  float* qz = reinterpret_cast<float*>(smem_raw + sizeof(PointChunk)) + tid;  // qz[k * 256]
-  int* qi = reinterpret_cast<int*>(qz - tid + K * TILE_THREADS) + tid;
-  float* qd = reinterpret_cast<float*>(qi - tid + K * TILE_THREADS) + tid;
-  const int t = blockIdx.x;
-  const int n = t / (p.TY * p.TX);
-  const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
+  float* qz0 = reinterpret_cast<float*>(smem_raw + sizeof(PointStage));
+  int* qi0 = reinterpret_cast<int*>(qz0 + K * QSTRIDE);
+  float* qd0 = reinterpret_cast<float*>(qi0 + K * QSTRIDE);
+  float* qz = qz0 + tid;  // qz[k * QSTRIDE]
+  int* qi = qi0 + tid;
+  float* qd = qd0 + tid;
+  const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = p.n0 + blockIdx.z;
+  const int tile = (n * p.TY + tile_y) * p.TX + tile_x;
   int xo, yo;
   pthread_pixel(tile_x, tile_y, xo, yo);
   const bool valid = xo < p.W && yo < p.H;
   const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
   const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
 
-  const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
-  const bool overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
-  const int64_t cloud_first = p.first[n];
-  const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
-
   int size = 0, max_idx = -1;
   float max_z = -1000.0f;
-
-  for (int base = 0; base < count; base += PCHUNK) {
-    const int nc = min(PCHUNK, count - base);
-    __syncthreads();
-    for (int j = tid; j < nc; j += TILE_THREADS) {
-      const int pi = overflow ? (int)(cloud_first + base + j) : p.pairs[seg_begin + base + j];
-      stage_point(s, j, p.points, p.radius, pi);
-    }
-    __syncthreads();
-    for (int sub = 0; sub < nc; sub += 64) {
-      unsigned m0 = 0, m1 = 0;
-      {
-        float col[8], row[4];  // the footprint's 8 column and 4 row coordinates (lane = row * 8 + column)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) col[c] = __shfl_sync(0xffffffffu, px, c);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) row[r] = __shfl_sync(0xffffffffu, py, 8 * r);
-        if (sub + lane < nc) m0 = box_pixel_mask(s.box[sub + lane], col, row);
-        if (sub + 32 + lane < nc) m1 = box_pixel_mask(s.box[sub + 32 + lane], col, row);
-      }
-      m0 = warp_transpose_bits(m0, lane);
-      if (sub + 32 < nc) m1 = warp_transpose_bits(m1, lane);
-      unsigned long long mine = valid ? (((unsigned long long)m1 << 32) | m0) : 0ull;
-      while (__any_sync(0xffffffffu, mine != 0ull)) {
-        if (mine == 0ull) continue;
-        const int j = sub + __ffsll((long long)mine) - 1;
-        mine &= mine - 1ull;
-        const float4 r = s.rec[j];
-        // CheckPixelInsidePoint (rasterize_points.cu:49-60): dist2 = fma(dy, dy, rn(dx*dx)) < rn(r*r)
-        const float dx = fsub(px, r.x), dy = fsub(py, r.y);
-        const float d2 = sqnorm2(dx, dy);
-        if (r.z < 0.0f || !(d2 < r.w)) continue;
-        const int pi = s.id[j];
-        if (size < K) {  // (:61-67)
-          qz[size * TILE_THREADS] = r.z;
-          qi[size * TILE_THREADS] = pi;
-          qd[size * TILE_THREADS] = d2;
-          if (r.z > max_z) {
-            max_z = r.z;
-            max_idx = size;
-          }
-          ++size;
-        } else if (r.z < max_z) {  // (:68-78)
-          qz[max_idx * TILE_THREADS] = r.z;
-          qi[max_idx * TILE_THREADS] = pi;
-          qd[max_idx * TILE_THREADS] = d2;
-          max_z = r.z;
-          for (int i = 0; i < K; ++i) {
-            const float v = qz[i * TILE_THREADS];
-            if (v > max_z) {
-              max_z = v;
-              max_idx = i;
-            }
-          }
-        }
-      }
-    }
-  }
-  if (!valid) return;
+  points_tile_body(p, s, reinterpret_cast<int*>(smem_raw), tile, n, valid, px, py,
+                   [&](float pz, int pi, float d2) {
+                     if (size < K) {  // (:61-67)
+                       qz[size * QSTRIDE] = pz;
+                       qi[size * QSTRIDE] = pi;
+                       qd[size * QSTRIDE] = d2;
+                       if (pz > max_z) {
+                         max_z = pz;
+                         max_idx = size;
+                       }
+                       ++size;
+                     } else if (pz < max_z) {  // (:68-78)
+                       qz[max_idx * QSTRIDE] = pz;
+                       qi[max_idx * QSTRIDE] = pi;
+                       qd[max_idx * QSTRIDE] = d2;
+                       max_z = pz;
+                       for (int i = 0; i < K; ++i) {
+                         const float v = qz[i * QSTRIDE];
+                         if (v > max_z) {
+                           max_z = v;
+                           max_idx = i;
+                         }
+                       }
+                     }
+                   });
   // BubbleSort on z only (rasterize_points.cu:26-28): stable -> insertion sort over the thread's own column
   for (int i = 1; i < size; ++i) {
-    const float tz = qz[i * TILE_THREADS], td = qd[i * TILE_THREADS];
-    const int ti = qi[i * TILE_THREADS];
+    const float tz = qz[i * QSTRIDE], td = qd[i * QSTRIDE];
+    const int ti = qi[i * QSTRIDE];
     int j = i - 1;
-    while (j >= 0 && tz < qz[j * TILE_THREADS]) {
-      qz[(j + 1) * TILE_THREADS] = qz[j * TILE_THREADS];
-      qi[(j + 1) * TILE_THREADS] = qi[j * TILE_THREADS];
-      qd[(j + 1) * TILE_THREADS] = qd[j * TILE_THREADS];
+    while (j >= 0 && tz < qz[j * QSTRIDE]) {
+      qz[(j + 1) * QSTRIDE] = qz[j * QSTRIDE];
+      qi[(j + 1) * QSTRIDE] = qi[j * QSTRIDE];
+      qd[(j + 1) * QSTRIDE] = qd[j * QSTRIDE];
       --j;
     }
-    qz[(j + 1) * TILE_THREADS] = tz;
-    qi[(j + 1) * TILE_THREADS] = ti;
-    qd[(j + 1) * TILE_THREADS] = td;
+    qz[(j + 1) * QSTRIDE] = tz;
+    qi[(j + 1) * QSTRIDE] = ti;
+    qd[(j + 1) * QSTRIDE] = td;
+  }
+  if (!p.vec_ok) {
+    if (!valid) return;
+    const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
+    for (int k = 0; k < K; ++k) {
+      const bool e = k >= size;
+      p.idx[o + k] = e ? -1 : qi[k * QSTRIDE];
+      p.zbuf[o + k] = e ? -1.0f : qz[k * QSTRIDE];
+      p.dists[o + k] = e ? -1.0f : qd[k * QSTRIDE];
+    }
+    return;
+  }
+  for (int k = size; k < K; ++k) {  // the -1 padding of the unused slots
+    qz[k * QSTRIDE] = -1.0f;
+    qi[k * QSTRIDE] = -1;
+    qd[k * QSTRIDE] = -1.0f;
+  }
+  __syncthreads();
+  // row-major write-out: row r of the tile is npx * K consecutive values of each output
+  const int x0 = tile_x * TILE, y0 = tile_y * TILE;
+  const int npx = min(TILE, p.W - x0), nrow = min(TILE, p.H - y0);
+  const int seg4 = (npx * K) >> 2;  // 16-byte pieces per row segment (npx * K is a multiple of 4 when vec_ok)
+  for (int e = tid; e < nrow * seg4; e += TILE_THREADS) {
+    const int r = e / seg4, v = e - r * seg4;
+    int c = (4 * v) / K, k = 4 * v - c * K;
+    float z[4], d[4];
+    int id[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int at = k * QSTRIDE + thread_of_pixel(r, c);
+      z[j] = qz0[at];
+      id[j] = qi0[at];
+      d[j] = qd0[at];
+      if (++k == K) {
+        k = 0;
+        ++c;
+      }
+    }
+    const int64_t o4 = (((((int64_t)n * p.H + y0 + r) * p.W + x0) * K) >> 2) + v;
+    __stcs(reinterpret_cast<int4*>(p.idx) + o4, make_int4(id[0], id[1], id[2], id[3]));
+    __stcs(reinterpret_cast<float4*>(p.zbuf) + o4, make_float4(z[0], z[1], z[2], z[3]));
+    __stcs(reinterpret_cast<float4*>(p.dists) + o4, make_float4(d[0], d[1], d[2], d[3]));
+  }
+}
+
+// 32 < K <= 150: the same queue in thread-local arrays.
+__global__ void __launch_bounds__(TILE_THREADS) points_fine_bigk_kernel(const PointFineParams p) {
+  __shared__ PointStage s;
+  const int K = p.K;
+  const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = p.n0 + blockIdx.z;
+  const int tile = (n * p.TY + tile_y) * p.TX + tile_x;
+  int xo, yo;
+  pthread_pixel(tile_x, tile_y, xo, yo);
+  const bool valid = xo < p.W && yo < p.H;
+  const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
+  const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
+  float lz[B200R_MAX_K], ld[B200R_MAX_K];
+  int li[B200R_MAX_K];
+  int ln = 0, l_max_idx = -1;
+  float l_max_z = -1000.0f;
+  points_tile_body(p, s, reinterpret_cast<int*>(&s), tile, n, valid, px, py, [&](float pz, int pi, float d2) {
+    if (ln < K) {
+      lz[ln] = pz;
+      li[ln] = pi;
+      ld[ln] = d2;
+      if (pz > l_max_z) {
+        l_max_z = pz;
+        l_max_idx = ln;
+      }
+      ++ln;
+    } else if (pz < l_max_z) {
+      lz[l_max_idx] = pz;
+      li[l_max_idx] = pi;
+      ld[l_max_idx] = d2;
+      l_max_z = pz;
+      for (int i = 0; i < K; ++i)
+        if (lz[i] > l_max_z) {
+          l_max_z = lz[i];
+          l_max_idx = i;
+        }
+    }
+  });
+  if (!valid) return;
+  for (int i = 1; i < ln; ++i) {  // stable insertion sort on z only
+    const float tz = lz[i], td = ld[i];
+    const int ti = li[i];
+    int j = i - 1;
+    while (j >= 0 && tz < lz[j]) {
+      lz[j + 1] = lz[j];
+      li[j + 1] = li[j];
+      ld[j + 1] = ld[j];
+      --j;
+    }
+    lz[j + 1] = tz;
+    li[j + 1] = ti;
+    ld[j + 1] = td;
   }
   const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
   for (int k = 0; k < K; ++k) {
-    const bool e = k >= size;
-    p.idx[o + k] = e ? -1 : qi[k * TILE_THREADS];
-    p.zbuf[o + k] = e ? -1.0f : qz[k * TILE_THREADS];
-    p.dists[o + k] = e ? -1.0f : qd[k * TILE_THREADS];
+    p.idx[o + k] = k < ln ? li[k] : -1;
+    p.zbuf[o + k] = k < ln ? lz[k] : -1.0f;
+    p.dists[o + k] = k < ln ? ld[k] : -1.0f;
   }
 }
 
@@ -405,12 +341,16 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_smem_kernel(const Po
 // One thread per pixel on the forward pass's tiles and 8x4 footprints, looping over the K slots.  A point covers
 // many neighbouring pixels, so at every slot the warp first merges ALL lanes that hold the same point
 // (__match_any_sync + pointer jumping, as in the mesh backward) and only one lane per distinct point issues the
-// three atomics.
+// three atomics.  STAGED: the tile's indices and upstream gradients are first read row segment by row segment
+// (16 pixels x K values are contiguous: coalesced 16-byte loads) into per-thread columns in shared memory;
+// otherwise (K > 32, or rows that are not 16-byte multiples) every thread reads its own K values directly.
+template <bool STAGED>
 __global__ void __launch_bounds__(TILE_THREADS)
     points_backward_kernel(const float* __restrict__ points, const int32_t* __restrict__ idxs,
                            const float* __restrict__ grad_zbuf, const float* __restrict__ grad_dists, int n0, int H,
                            int W, int K, float rx, float ry, float* __restrict__ grad_points) {
-  const int lane = threadIdx.x & 31;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = n0 + blockIdx.z;
   int xo, yo;
   pthread_pixel(tile_x, tile_y, xo, yo);
@@ -418,16 +358,47 @@ __global__ void __launch_bounds__(TILE_THREADS)
   const float xf = pix_to_ndc(W - 1 - xo, W, rx);
   const float yf = pix_to_ndc(H - 1 - yo, H, ry);
   const int64_t o = in_image ? (((int64_t)n * H + yo) * W + xo) * K : 0;
+  int* si0 = reinterpret_cast<int*>(smem_raw);
+  float* sz0 = reinterpret_cast<float*>(si0 + K * QSTRIDE);
+  float* sd0 = sz0 + K * QSTRIDE;
+  if (STAGED) {
+    const int x0 = tile_x * TILE, y0 = tile_y * TILE;
+    const int npx = min(TILE, W - x0), nrow = min(TILE, H - y0);
+    const int seg4 = (npx * K) >> 2;
+    for (int e = tid; e < nrow * seg4; e += TILE_THREADS) {
+      const int r = e / seg4, v = e - r * seg4;
+      const int64_t o4 = (((((int64_t)n * H + y0 + r) * W + x0) * K) >> 2) + v;
+      const int4 vi = __ldcs(reinterpret_cast<const int4*>(idxs) + o4);
+      const float4 vz = __ldcs(reinterpret_cast<const float4*>(grad_zbuf) + o4);
+      const float4 vd = __ldcs(reinterpret_cast<const float4*>(grad_dists) + o4);
+      const int ii[4] = {vi.x, vi.y, vi.z, vi.w};
+      const float zz[4] = {vz.x, vz.y, vz.z, vz.w}, dd[4] = {vd.x, vd.y, vd.z, vd.w};
+      int c = (4 * v) / K, k = 4 * v - c * K;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int at = k * QSTRIDE + thread_of_pixel(r, c);
+        si0[at] = ii[j];
+        sz0[at] = zz[j];
+        sd0[at] = dd[j];
+        if (++k == K) {
+          k = 0;
+          ++c;
+        }
+      }
+    }
+    __syncthreads();
+  }
   for (int k = 0; k < K; ++k) {
-    const int pi = in_image ? idxs[o + k] : -1;
+    int pi = -1;
+    if (in_image) pi = STAGED ? si0[k * QSTRIDE + tid] : idxs[o + k];
     if (!__any_sync(0xffffffffu, pi >= 0)) continue;
     float gx = 0.0f, gy = 0.0f, gz = 0.0f;
     if (pi >= 0) {
-      const float gd = grad_dists[o + k];
+      const float gd = STAGED ? sd0[k * QSTRIDE + tid] : grad_dists[o + k];
       const float g2 = gd + gd;
       gx = g2 * (__ldg(points + (int64_t)pi * 3 + 0) - xf);
       gy = g2 * (__ldg(points + (int64_t)pi * 3 + 1) - yf);
-      gz = grad_zbuf[o + k];
+      gz = STAGED ? sz0[k * QSTRIDE + tid] : grad_zbuf[o + k];
     }
     const unsigned grp = __match_any_sync(0xffffffffu, pi);
     const unsigned above = lane == 31 ? 0u : grp & (0xffffffffu << (lane + 1));
@@ -459,8 +430,10 @@ using namespace b200r;
 extern "C" size_t b200r_rasterize_points_workspace_bytes(int64_t P, int32_t N, int32_t H, int32_t W,
                                                          int64_t pair_capacity) {
   if (P < 0 || N < 0 || H < 0 || W < 0) return 0;
-  return carve_workspace(nullptr, P, N, H, W, pair_capacity).bytes;
+  return carve_workspace(nullptr, P, N, H, W, pair_capacity).bytes + POINT_RECORD_BYTES * (size_t)(P > 0 ? P : 1);
 }
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, const int64_t* first,
                                               const int64_t* num, const float* radius, int32_t N, int32_t H,
@@ -479,8 +452,10 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
   const int64_t ntiles = (int64_t)N * TY * TX;
   if (ntiles > INT_MAX) return fail(B200R_ERR_INVALID_ARGUMENT, "too many tiles");
   BinWorkspace ws = carve_workspace(workspace, P, N, H, W, pair_capacity);
-  if (workspace == nullptr || workspace_bytes < ws.bytes)
+  const size_t nrec = (size_t)(P > 0 ? P : 1);
+  if (workspace == nullptr || workspace_bytes < ws.bytes + POINT_RECORD_BYTES * nrec)
     return fail(B200R_ERR_WORKSPACE, "workspace too small for rasterize_points_forward");
+  float4* prec = reinterpret_cast<float4*>(static_cast<char*>(workspace) + ws.bytes);  // (ws.bytes % 16 == 0)
   const float rx = ndc_range(W, H), ry = ndc_range(H, W);
 
   const bool prof = profiling_enabled();
@@ -488,7 +463,7 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
   B200R_CUDA_OK(cudaMemsetAsync(ws.tile_count, 0, sizeof(int) * (size_t)ntiles, stream));
   if (P > 0) {
     points_setup_count_kernel<<<(unsigned)((P + SETUP_POINTS - 1) / SETUP_POINTS), SETUP_POINTS, 0, stream>>>(
-        points, radius, P, first, num, N, H, W, TY, TX, rx, ry, ws.rect, ws.tile_count);
+        points, radius, P, first, num, N, H, W, TY, TX, rx, ry, ws.rect, ws.tile_count, prec);
     B200R_LAUNCHED("points_setup_count_kernel");
   }
   tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles);
@@ -498,36 +473,36 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
                                                                     ws.capacity);
     B200R_LAUNCHED("tile_fill_kernel");
   }
-  tile_sort_kernel<<<(unsigned)((ntiles + SORT_TILES_PER_CTA - 1) / SORT_TILES_PER_CTA), SORT_THREADS, 0, stream>>>(
-        ws.tile_offset, ws.pairs, ws.capacity, (int)ntiles, sort_multiplier(ntiles));
-  B200R_LAUNCHED("tile_sort_kernel");
+  // (no sort launch: every fine CTA puts its own tile list in ascending point order, see cta_sort256)
   if (prof) phase_timer().record(1, stream);
   PointFineParams p;
-  p.points = points; p.radius = radius; p.first = first; p.num = num;
+  p.prec = prec; p.first = first; p.num = num;
   p.tile_offset = ws.tile_offset; p.pairs = ws.pairs; p.capacity = ws.capacity;
   p.N = N; p.H = H; p.W = W; p.K = K; p.TY = TY; p.TX = TX; p.rx = rx; p.ry = ry;
   p.idx = idx; p.zbuf = zbuf; p.dists = dists;
-  const unsigned grid = (unsigned)ntiles;
-  if (K <= 1)
-    points_fine_kernel<1><<<grid, TILE_THREADS, 0, stream>>>(p);
-  else if (K <= 2)
-    points_fine_kernel<2><<<grid, TILE_THREADS, 0, stream>>>(p);
-  else if (K <= 4)
-    points_fine_kernel<4><<<grid, TILE_THREADS, 0, stream>>>(p);
-  else if (K <= 32) {
-    const size_t smem = sizeof(PointChunk) + (size_t)K * TILE_THREADS * 12;
+  p.vec_ok = (((int64_t)W * K) % 4 == 0 && aligned16(idx) && aligned16(zbuf) && aligned16(dists)) ? 1 : 0;
+  size_t smem = 0;
+  if (K <= SMEMQ_MAX_K) {
+    smem = sizeof(PointStage) + (size_t)K * QSTRIDE * 12;
     static bool configured[64] = {}; /* > 48 KB of dynamic shared memory: opt-in per kernel and device */
     int dev_ = 0;
     B200R_CUDA_OK(cudaGetDevice(&dev_));
     if (dev_ < 0 || dev_ >= 64 || !configured[dev_]) {
       B200R_CUDA_OK(cudaFuncSetAttribute(points_fine_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(sizeof(PointChunk) + 32 * TILE_THREADS * 12)));
+                                         (int)(sizeof(PointStage) + (size_t)SMEMQ_MAX_K * QSTRIDE * 12)));
       if (dev_ >= 0 && dev_ < 64) configured[dev_] = true;
     }
-    points_fine_smem_kernel<<<grid, TILE_THREADS, smem, stream>>>(p);
+    p.smem_ints = (int)(smem / sizeof(int));
+  } else {
+    p.smem_ints = (int)(sizeof(PointStage) / sizeof(int));
   }
-  else
-    points_fine_kernel<0><<<grid, TILE_THREADS, 0, stream>>>(p);
+  for (p.n0 = 0; p.n0 < N; p.n0 += 65535) {  // grid.z is limited to 65535 images per launch
+    const dim3 grid3((unsigned)TX, (unsigned)TY, (unsigned)min(N - p.n0, 65535));
+    if (K <= SMEMQ_MAX_K)
+      points_fine_smem_kernel<<<grid3, TILE_THREADS, smem, stream>>>(p);
+    else
+      points_fine_bigk_kernel<<<grid3, TILE_THREADS, 0, stream>>>(p);
+  }
   B200R_LAUNCHED("points_fine_kernel");
   if (prof) {
     phase_timer().record(2, stream);
@@ -549,10 +524,29 @@ extern "C" int b200r_rasterize_points_backward(const float* points, int64_t P, c
   if (TY > 65535) return fail(B200R_ERR_INVALID_ARGUMENT, "image too large");
   const bool prof = profiling_enabled();
   if (prof) phase_timer().record(3, stream);
+  const bool staged = K <= SMEMQ_MAX_K && ((int64_t)W * K) % 4 == 0 && aligned16(idxs) && aligned16(grad_zbuf) &&
+                      aligned16(grad_dists);
+  const size_t smem = staged ? (size_t)K * QSTRIDE * 12 : 0;
+  if (staged) {
+    static bool configured[64] = {};
+    int dev_ = 0;
+    B200R_CUDA_OK(cudaGetDevice(&dev_));
+    if (dev_ < 0 || dev_ >= 64 || !configured[dev_]) {
+      B200R_CUDA_OK(cudaFuncSetAttribute(points_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((size_t)SMEMQ_MAX_K * QSTRIDE * 12)));
+      if (dev_ >= 0 && dev_ < 64) configured[dev_] = true;
+    }
+  }
   for (int n0 = 0; n0 < N; n0 += 65535) {  // grid.z is limited to 65535 images per launch
     const dim3 grid((unsigned)TX, (unsigned)TY, (unsigned)min(N - n0, 65535));
-    points_backward_kernel<<<grid, TILE_THREADS, 0, stream>>>(points, idxs, grad_zbuf, grad_dists, n0, H, W, K,
-                                                             ndc_range(W, H), ndc_range(H, W), grad_points);
+    if (staged)
+      points_backward_kernel<true><<<grid, TILE_THREADS, smem, stream>>>(points, idxs, grad_zbuf, grad_dists, n0, H,
+                                                                       W, K, ndc_range(W, H), ndc_range(H, W),
+                                                                       grad_points);
+    else
+      points_backward_kernel<false><<<grid, TILE_THREADS, 0, stream>>>(points, idxs, grad_zbuf, grad_dists, n0, H,
+                                                                       W, K, ndc_range(W, H), ndc_range(H, W),
+                                                                       grad_points);
   }
   B200R_LAUNCHED("points_backward_kernel");
   if (prof) {

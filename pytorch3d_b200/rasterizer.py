@@ -50,25 +50,25 @@ class RasterizationSettings:
     cull_to_frustum: bool = False
 
 
-class _NdcView:
-    """Packed view of a batch whose vertices were replaced by their NDC positions."""
-
-    def __init__(self, src, verts_packed):
-        self._src = src
-        self._verts_packed = verts_packed
-        self._F = getattr(src, "_F", 0)
-
-    def verts_packed(self):
-        return self._verts_packed
-
-    def faces_packed(self):
-        return self._src.faces_packed()
-
-    def mesh_to_faces_packed_first_idx(self):
-        return self._src.mesh_to_faces_packed_first_idx()
-
-    def num_faces_per_mesh(self):
-        return self._src.num_faces_per_mesh()
+def _world_to_ndc(cameras, pts_world, kwargs):
+    """World -> NDC xy with the view-space z kept as depth (rasterizer.py:196-214, points/rasterizer.py:126-142 of
+    the reference).  Per-call camera overrides in `kwargs` (R, T, focal_length, ...) reach every transform: the
+    projection is taken from `get_projection_transform(**kwargs)` and applied to the view-space points; cameras
+    without a projection matrix (NotImplementedError) go through `transform_points` instead."""
+    eps = kwargs.get("eps", None)
+    pts_view = cameras.get_world_to_view_transform(**kwargs).transform_points(pts_world, eps=eps)
+    to_ndc = cameras.get_ndc_camera_transform(**kwargs)
+    try:
+        projection = cameras.get_projection_transform(**kwargs)
+    except NotImplementedError:
+        projection = None
+    if projection is not None:
+        pts_ndc = projection.compose(to_ndc).transform_points(pts_view, eps=eps)
+    else:
+        pts_proj = cameras.transform_points(pts_world, eps=eps)
+        pts_ndc = to_ndc.transform_points(pts_proj, eps=eps)
+    pts_ndc[..., 2] = pts_view[..., 2]
+    return pts_ndc
 
 
 class MeshRasterizer(nn.Module):
@@ -92,18 +92,12 @@ class MeshRasterizer(nn.Module):
         n_cameras = len(cameras)
         if n_cameras != 1 and n_cameras != len(meshes_world):
             raise ValueError("Wrong number (%r) of cameras for %r meshes" % (n_cameras, len(meshes_world)))
-        if hasattr(meshes_world, "update_padded"):  # a PyTorch3D Meshes object
-            verts_world = meshes_world.verts_padded()
-            eps = kwargs.get("eps", None)
-            verts_view = cameras.get_world_to_view_transform(**kwargs).transform_points(verts_world, eps=eps)
-            to_ndc = cameras.get_ndc_camera_transform(**kwargs)
-            verts_proj = cameras.transform_points(verts_world, eps=eps)
-            verts_ndc = to_ndc.transform_points(verts_proj, eps=eps)
-            verts_ndc[..., 2] = verts_view[..., 2]
-            return meshes_world.update_padded(new_verts_padded=verts_ndc)
-        # packed containers: cameras must map packed points (P,3) -> NDC xy and view-space z
-        verts = meshes_world.verts_packed()
-        return _NdcView(meshes_world, cameras.transform_points_ndc_packed(verts, meshes_world))
+        if not hasattr(meshes_world, "update_padded"):
+            raise ValueError(
+                "MeshRasterizer with cameras needs a batch with verts_padded() / update_padded() (a PyTorch3D Meshes "
+                "object); packed containers are only accepted with cameras=None, i.e. already in NDC")
+        verts_ndc = _world_to_ndc(cameras, meshes_world.verts_padded(), kwargs)
+        return meshes_world.update_padded(new_verts_padded=verts_ndc)
 
     def forward(self, meshes_world, **kwargs) -> Fragments:
         meshes_proj = self.transform(meshes_world, **kwargs)
@@ -178,14 +172,7 @@ class PointsRasterizer(nn.Module):
         cameras = kwargs.get("cameras", self.cameras)
         if cameras is None:
             return point_clouds
-        pts_world = point_clouds.points_padded()
-        eps = kwargs.get("eps", None)
-        pts_view = cameras.get_world_to_view_transform(**kwargs).transform_points(pts_world, eps=eps)
-        to_ndc = cameras.get_ndc_camera_transform(**kwargs)
-        pts_proj = cameras.transform_points(pts_world, eps=eps)
-        pts_ndc = to_ndc.transform_points(pts_proj, eps=eps)
-        pts_ndc[..., 2] = pts_view[..., 2]
-        return point_clouds.update_padded(pts_ndc)
+        return point_clouds.update_padded(_world_to_ndc(cameras, point_clouds.points_padded(), kwargs))
 
     def forward(self, point_clouds, **kwargs) -> PointFragments:
         points_proj = self.transform(point_clouds, **kwargs)

@@ -62,6 +62,20 @@ MESH_MATRIX = [  # persp, clip, cull, blur, K, H, W, F, N
     (0, 1, 0, 0.0, 2, 50, 19, 400, 1),
     (0, 0, 0, 0.0, 8, 100, 70, 30, 2),
     (0, 0, 1, 0.0, 6, 70, 100, 2000, 2),
+    # 8 < K <= 32: queue keys in shared memory (mesh_fine_smemq_kernel); K % 8 == 0 takes the paired group stores
+    (0, 0, 0, 1e-3, 16, 48, 48, 600, 2),
+    (1, 0, 0, 0.0, 16, 33, 47, 500, 2),
+    (0, 1, 0, 1e-2, 32, 40, 40, 400, 1),
+    (0, 0, 0, 0.0, 24, 64, 64, 1500, 1),
+    (1, 1, 1, 1e-2, 12, 31, 45, 600, 3),
+    (0, 0, 0, 1e-3, 40, 24, 24, 300, 1),
+    # tile lists longer than one chunk: sorted by the CTA in shared memory (3000 faces on 4 tiles) ...
+    (0, 0, 0, 1e-2, 8, 32, 32, 3000, 1),
+    (0, 0, 0, 0.0, 4, 32, 32, 3000, 1),
+    (0, 0, 0, 1e-2, 16, 32, 32, 3000, 1),
+    # ... or, beyond the kernel's shared memory, in place in global memory (20000 faces on one tile)
+    (0, 0, 0, 1e-3, 2, 16, 16, 20000, 1),
+    (0, 0, 0, 1e-3, 40, 16, 16, 6000, 1),
 ]
 
 
@@ -310,7 +324,11 @@ def test_mesh_indexed_entry_points(ops, dev):
 # ------------------------------------------------------------------------------------ points
 
 POINT_MATRIX = [(2000, 2, 32, 48, 5), (5000, 1, 64, 64, 10), (3000, 3, 40, 24, 1), (3000, 1, 50, 50, 40),
-                (3000, 1, 20, 20, 150), (20000, 2, 128, 128, 8), (1000, 1, 17, 33, 3)]
+                (3000, 1, 20, 20, 150), (20000, 2, 128, 128, 8), (1000, 1, 17, 33, 3),
+                # row segments that are / are not 16-byte multiples (W * K % 4), partial tiles, K = 32
+                (4000, 2, 40, 50, 10), (4000, 1, 33, 47, 7), (3000, 1, 31, 36, 32), (2000, 1, 24, 20, 2),
+                # tile lists longer than one chunk: in-kernel sort in shared / global memory
+                (3000, 1, 32, 32, 6), (12000, 1, 16, 16, 3), (5000, 1, 16, 16, 40)]
 
 
 @pytest.mark.parametrize("P,N,H,W,K", POINT_MATRIX)
