@@ -8,8 +8,11 @@
 Workload ("ns", the configuration the metric is quoted on): a batch of 8 meshes of 69,938 faces each
 (seeded tori in NDC), 512 x 512, faces_per_pixel = 8, blur_radius = 0, forward + backward with dense
 upstream gradients on zbuf / bary / dists.  One "step" = one forward+backward pass over the batch.
-Multi-GPU is weak scaling: every rank renders its own batch of 8 (no data-path collective); `value` is
-frames of all ranks / max-over-ranks device time.
+Multi-GPU is weak scaling: every rank renders a batch of 8 (the SAME seeded batch on every rank, so that the
+scaling figure isolates the machine; no data-path collective); `value` is frames of all ranks / max-over-ranks
+device time.  The path's one collective -- gathering the rendered frames on every rank -- is timed beside it
+(`value_with_gather`), and BASELINE config 4 (32 heterogeneous meshes sharded over the ranks: strong scaling)
+is reported as `c4_sharded` at every N.
 
 Prints ONE JSON line (see README / the task contract for the keys).
 """
@@ -33,6 +36,8 @@ WORKLOADS = {
     # name: (meshes per rank, torus rings, torus sides, H, W, K, blur)
     "ns": (8, 187, 187, 512, 512, 8, 0.0),
     "c2": (8, 54, 54, 256, 256, 8, 1e-4),
+    "ns_blur": (8, 187, 187, 512, 512, 8, 1e-4),
+    "c5": (1, 707, 707, 1024, 1024, 16, 1e-3),
     "tiny": (2, 24, 24, 64, 64, 4, 0.0),
 }
 
@@ -53,14 +58,20 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+NCU_SUMMARIES = ["ncu_r02_ns_metrics.json", "ncu_r01_ns_metrics.json"]  # newest first
+
+
 def ncu_traffic_bytes(kernel):
-    """dram read+write bytes per launch of `kernel` from the committed ncu capture summary, or None."""
-    path = os.path.join(ROOT, "profiles", "ncu_r01_ns_metrics.json")
-    try:
-        with open(path) as fh:
-            return json.load(fh)["kernels"][kernel]["dram_bytes_per_launch"]
-    except Exception:
-        return None
+    """(dram read+write bytes per launch of `kernel`, source file) from the committed ncu capture summary of the
+    same workload -- measured under the profiler, not in this run -- or (None, None)."""
+    for name in NCU_SUMMARIES:
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            with open(path) as fh:
+                return json.load(fh)["kernels"][kernel]["dram_bytes_per_launch"], "profiles/" + name
+        except Exception:
+            continue
+    return None, None
 
 
 class ClockSampler:
@@ -180,7 +191,8 @@ def pick_strip_rows(face_verts, n_faces, H, W, K, blur, ref, budget_s, steps):
 def build_workload(name, rank):
     from pytorch3d_b200 import synthetic
     nm, rings, sides, H, W, K, blur = WORKLOADS[name]
-    meshes = synthetic.torus_batch(nm, rings, sides, seed=rank)
+    del rank  # every rank renders the same seeded batch: per-rank seeds made the slowest rank set the time
+    meshes = synthetic.torus_batch(nm, rings, sides, seed=0)
     return meshes, (nm, rings * sides * 2, H, W, K, blur)
 
 
@@ -189,7 +201,8 @@ def config_dict(name, world, nm, F1, H, W, K, blur):
         "workload": "%s: %d meshes/GPU x %d faces (seeded tori in NDC), %dx%d, faces_per_pixel=%d, "
                     "blur_radius=%g, fwd+bwd" % (name, nm, F1, H, W, K, blur),
         "meshes_per_gpu": nm, "faces_per_mesh": F1, "image_size": [H, W], "faces_per_pixel": K,
-        "blur_radius": blur, "global_batch": nm * world, "parallelism": "batch-sharded x%d (no collective)" % world,
+        "blur_radius": blur, "global_batch": nm * world,
+        "parallelism": "batch-sharded x%d (no data-path collective; every rank renders the same seeded batch)" % world,
         "l2": "no explicit flush: each step streams ~%.0f MB of fragments + upstream gradients per GPU "
               "(>> 126 MB L2); the %.0f MB of face_verts stay L2-resident as in a real optimisation loop"
               % (nm * H * W * K * 48 / 1e6, nm * F1 * 36 / 1e6),
@@ -323,15 +336,24 @@ def run_ours(args, rank, local_rank, world):
     fine_bytes = 28.0 * slots + 36.0 * nm * F1            # fwd: write 28 B/slot, read face_verts once
     bwd_bytes = 28.0 * slots + 72.0 * nm * F1             # bwd: read 28 B/slot + face_verts, write grads
     fine_gbs = fine_bytes / (ph[1] * 1e-3) / 1e9 if ph[1] > 0 else 0.0
+    fine_traffic, traffic_src = ncu_traffic_bytes("mesh_fine_kernel")
+    bwd_traffic, _ = ncu_traffic_bytes("mesh_backward_kernel")
+    bwd = {"ms": float(ph[2]), "algorithmic_bytes": bwd_bytes,
+           "achieved": bwd_bytes / (ph[2] * 1e-3) / 1e9 if ph[2] > 0 else 0.0,
+           "frac": (bwd_bytes / (ph[2] * 1e-3) / 1e9 / peak) if ph[2] > 0 else 0.0,
+           # the kernel skips the 20 B/slot of upstream gradients of empty slots: what it really moves (ncu dram
+           # bytes of the committed capture of this workload) over this run's launch time
+           "traffic": bwd_traffic,
+           "frac_by_dram_bytes": (bwd_traffic / (ph[2] * 1e-3) / 1e9 / peak) if (bwd_traffic and ph[2] > 0) else None}
     roofline = {
         "kernel": "mesh_fine_kernel<8>", "bound": "hbm", "achieved": fine_gbs, "peak": peak, "unit": "GB/s",
-        "frac": fine_gbs / peak, "traffic": ncu_traffic_bytes("mesh_fine_kernel"),
+        "frac": fine_gbs / peak, "traffic": fine_traffic,
+        "traffic_source": ("%s (ncu --set full capture of this workload; not measured in this run)" % traffic_src)
+        if traffic_src else None,
         "algorithmic_bytes_per_launch": fine_bytes, "ms_per_launch": float(ph[1]), "peak_source": peak_src,
         "other_kernels": {
-            "binning(setup+scan+fill+sort)": {"ms": float(ph[0])},
-            "mesh_backward_kernel": {"ms": float(ph[2]), "algorithmic_bytes": bwd_bytes,
-                                     "achieved": bwd_bytes / (ph[2] * 1e-3) / 1e9 if ph[2] > 0 else 0.0,
-                                     "frac": (bwd_bytes / (ph[2] * 1e-3) / 1e9 / peak) if ph[2] > 0 else 0.0},
+            "binning(memset+setup+scan+fill; the list sort runs inside the fine kernel)": {"ms": float(ph[0])},
+            "mesh_backward_kernel": bwd,
         },
         "step": {"algorithmic_bytes": fine_bytes + bwd_bytes,
                  "achieved": (fine_bytes + bwd_bytes) * args.steps / (ms * 1e-3) / 1e9,
@@ -339,12 +361,16 @@ def run_ours(args, rank, local_rank, world):
     }
 
     # ---------------- the other single-GPU configs (device-resident; before the CUDA-graph section below)
-    others = None
+    others, ref_cuda = None, None
     if rank == 0 and world == 1 and not args.skip_others:
         try:
-            others = other_workloads(dev)
+            others = other_workloads(dev, lib, peak)
         except Exception as ex:
             others = {"error": str(ex)}
+        try:
+            ref_cuda = reference_cuda_leg(dev, fv, first, num, F1, H, W, K, blur, gz, gb, gd, nm)
+        except Exception as ex:
+            ref_cuda = {"error": str(ex)[:300]}
         # those workloads leave differently sized blocks in torch's caching allocator; start the end-to-end
         # section from the same allocator state as a run without them
         import gc
@@ -520,34 +546,20 @@ def run_ours(args, rank, local_rank, world):
                "sample": "rows [%d,%d) of frame 0 (%d of %d rows, all %d faces), fwd+bwd, %.1f s of CPU work" % (
                    (H - rows) // 2, (H - rows) // 2 + rows, rows, H, F1, dtc)}
 
-    # ---------------- optional: all-gather of the rendered frames over NCCL (the only collective the path has)
+    # ---------------- the path's one collective: every rank gathers the rendered frames of all ranks
     gather = None
     if world > 1:
-        p2f, zb, ba, di = fwd()
-        tensors = [p2f, zb, ba, di]
-        bufs = [t.new_empty((world,) + tuple(t.shape)) for t in tensors]
-        def gather_step():
-            f = fwd()
-            for t, b in zip(f, bufs):
-                dist.all_gather_into_tensor(b, t)
-            return _C.rasterize_meshes_backward(fv, f[0], gz, gb, gd, False, False)
-        for _ in range(3):
-            gather_step()
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_g = max(3, min(args.steps, 20))
-        g0.record()
-        for _ in range(n_g):
-            gather_step()
-        g1.record()
-        barrier()
-        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        bytes_per_rank = sum(t.numel() * t.element_size() for t in tensors)
-        gather = {"value": world * nm * n_g / (float(tg.item()) * 1e-3), "unit": UNIT, "steps": n_g,
-                  "bytes_gathered_per_rank_per_step": int(bytes_per_rank * world),
-                  "what": "same step with every rank all-gathering all four Fragments tensors of all ranks "
-                          "(all_gather_into_tensor, NCCL) between forward and backward"}
+        try:
+            gather = gather_leg(args, dev, rank, world, nm, fwd, fv, gz, gb, gd, barrier)
+        except Exception as ex:
+            gather = {"error": str(ex)[:300]}
+    # ---------------- BASELINE config 4: 32 heterogeneous meshes sharded over the ranks (strong scaling)
+    c4 = None
+    if not args.skip_c4:
+        try:
+            c4 = c4_leg(args, dev, rank, world, barrier)
+        except Exception as ex:
+            c4 = {"error": str(ex)[:300]}
 
     if rank == 0:
         line = {
@@ -556,7 +568,8 @@ def run_ours(args, rank, local_rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(name, world, nm, F1, H, W, K, blur),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline,
-            "cpu_baseline": cpu, "e2e_host_abi": e2e_abi, "other_workloads": others, "with_frame_gather": gather,
+            "cpu_baseline": cpu, "e2e_host_abi": e2e_abi, "other_workloads": others, "reference_cuda": ref_cuda,
+            "value_with_gather": (gather or {}).get("value"), "with_frame_gather": gather, "c4_sharded": c4,
             "impl": "pytorch3d_b200",
         }
         print(json.dumps(line), flush=True)
@@ -575,26 +588,60 @@ def _time_ms(fn, steps=20, warm=3):
     return e0.elapsed_time(e1) / steps
 
 
-def other_workloads(dev):
-    """Device-resident fwd+bwd throughput of the other BASELINE configs that fit one GPU (context, not the metric)."""
+def _phase_ms(lib, fn, n=5):
+    """(binning, fine, backward) ms of `fn` from the library's phase events on the launch stream."""
+    import ctypes
+    lib.b200r_set_profiling(1)
+    buf = (ctypes.c_float * 3)()
+    acc = np.zeros(3)
+    for _ in range(n):
+        torch.cuda._sleep(400000)
+        fn()
+        lib.b200r_last_phase_ms(buf)
+        acc += np.array(list(buf))
+    lib.b200r_set_profiling(0)
+    return (acc / n).tolist()
+
+
+def _mesh_workload_numbers(dev, lib, peak, name, steps=20, warm=3):
     from pytorch3d_b200 import _C, synthetic
-    out = {}
-    # config 2: 8 x ~6k-face meshes, 256^2, K=8, blur 1e-4
-    meshes, (nm, F1, H, W, K, blur) = build_workload("c2", 0)
+    meshes, (nm, F1, H, W, K, blur) = build_workload(name, 0)
     fv = synthetic.face_verts_of(meshes).to(dev)
     first, num = meshes.mesh_to_faces_packed_first_idx().to(dev), meshes.num_faces_per_mesh().to(dev)
     nb = torch.full((fv.shape[0],), -1, dtype=torch.int64, device=dev)
     nb._b200_all_minus_one = True
     frag = _C.rasterize_meshes(fv, first, num, nb, (H, W), blur, K, 0, 0, False, False, False)
-    gz, gb, gd = torch.randn_like(frag[1]), torch.randn_like(frag[2]), torch.randn_like(frag[3])
+    g = torch.Generator(device=dev).manual_seed(231)
+    gz = torch.randn(frag[1].shape, generator=g, device=dev)
+    gb = torch.randn(frag[2].shape, generator=g, device=dev)
+    gd = torch.randn(frag[3].shape, generator=g, device=dev)
+    hits = int((frag[0] >= 0).sum())
+    del frag
 
-    def step_c2():
+    def step():
         f = _C.rasterize_meshes(fv, first, num, nb, (H, W), blur, K, 0, 0, False, False, False)
         _C.rasterize_meshes_backward(fv, f[0], gz, gb, gd, False, False)
 
-    ms = _time_ms(step_c2)
-    out["config2_meshes_8x%d_faces_%d2_K%d_blur%g" % (F1, H, K, blur)] = {"ms_per_step": ms, "frames_per_s": nm * 1e3 / ms}
-    # config 3: 8 x 100k points, 512^2, K=10, r=0.01, + alpha_composite (4 channels), fwd+bwd
+    ms = _time_ms(step, steps=steps, warm=warm)
+    ph = _phase_ms(lib, step, n=min(5, steps))
+    slots = nm * H * W * K
+    alg = 56.0 * slots + 108.0 * nm * F1
+    return {"workload": "%d x %d faces, %dx%d, K=%d, blur=%g, fwd+bwd" % (nm, F1, H, W, K, blur),
+            "ms_per_step": ms, "frames_per_s": nm * 1e3 / ms, "hit_slots": hits, "slots": slots,
+            "phase_ms": {"binning": ph[0], "fine": ph[1], "backward": ph[2]},
+            "roofline": {"bound": "hbm", "algorithmic_bytes_per_step": alg, "achieved": alg / (ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak}}
+
+
+def other_workloads(dev, lib, peak):
+    """Device-resident fwd+bwd throughput of the other BASELINE configs that fit one GPU, and of the north-star batch
+    with a blur band (context next to the metric, each with its own HBM-roofline fraction)."""
+    from pytorch3d_b200 import _C, synthetic
+    out = {}
+    out["config2_meshes_8x5832_faces_256_K8_blur1e-4"] = _mesh_workload_numbers(dev, lib, peak, "c2")
+    out["ns_blur1e-4"] = _mesh_workload_numbers(dev, lib, peak, "ns_blur")
+    out["config5_1M_faces_1024_K16_blur1e-3"] = _mesh_workload_numbers(dev, lib, peak, "c5", steps=3, warm=1)
+    # config 3: 8 x 100k points, 512^2, K=10, r=0.01 -- rasterization alone, then with alpha_composite (4 channels)
     pc = synthetic.random_pointclouds(8, 100000, seed=0)
     pts = pc.points_packed().to(dev)
     pf, pn = pc.cloud_to_packed_first_idx().to(dev), pc.num_points_per_cloud().to(dev)
@@ -604,6 +651,19 @@ def other_workloads(dev):
     idx, zb, d2 = _C.rasterize_points(pts, pf, pn, (512, 512), rad, 10, 0, 0)
     g_img = torch.randn(8, 4, 512, 512, device=dev)
     g_z = torch.randn_like(zb)
+    g_d = torch.randn_like(d2)
+
+    def raster_c3():
+        i, z, d = _C.rasterize_points(pts, pf, pn, (512, 512), rad, 10, 0, 0)
+        _C.rasterize_points_backward(pts, i, g_z, g_d)
+
+    ms = _time_ms(raster_c3)
+    ph = _phase_ms(lib, raster_c3)
+    alg = 8 * (24.0 * 512 * 512 * 10 + 40.0 * 100000)
+    out["config3_points_8x100k_512_K10_r0.01_raster_only"] = {
+        "ms_per_step": ms, "frames_per_s": 8e3 / ms, "phase_ms": {"binning": ph[0], "fine": ph[1], "backward": ph[2]},
+        "roofline": {"bound": "hbm", "algorithmic_bytes_per_step": alg, "achieved": alg / (ms * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak}}
 
     def step_c3():
         i, z, d = _C.rasterize_points(pts, pf, pn, (512, 512), rad, 10, 0, 0)
@@ -611,11 +671,155 @@ def other_workloads(dev):
         il = i.long().permute(0, 3, 1, 2)
         _C.accum_alphacomposite(feats, w, il)
         gf, ga = _C.accum_alphacomposite_backward(g_img, feats, w, il)
-        g_d = (ga * (-1.0 / (r * r))).permute(0, 2, 3, 1).contiguous()
-        _C.rasterize_points_backward(pts, i, g_z, g_d)
+        gdd = (ga * (-1.0 / (r * r))).permute(0, 2, 3, 1).contiguous()
+        _C.rasterize_points_backward(pts, i, g_z, gdd)
 
     ms = _time_ms(step_c3)
     out["config3_points_8x100k_512_K10_r0.01_alpha_composite"] = {"ms_per_step": ms, "frames_per_s": 8e3 / ms}
+    return out
+
+
+def reference_cuda_leg(dev, fv, first, num, F1, H, W, K, blur, gz, gb, gd, nm):
+    """The reference's own CUDA kernels rebuilt for sm_100a (oracle/_ref/ref_raster_cuda.so) on the same GPU and
+    batch, with the reference's default heuristics (rasterize_meshes.py:122-142): the bar SURVEY.md 2.2 names.
+    Timed outside every timed region of `value`."""
+    import oracle
+    ref = oracle.load_reference(cuda=True)
+    if ref is None:
+        return {"unavailable": "oracle/_ref/ref_raster_cuda.so not present on this box"}
+    size = max(H, W)
+    bin_size = 8 if size <= 64 else int(2 ** max(np.ceil(np.log2(size)) - 4, 4))
+    max_faces_per_bin = int(max(10000, F1 / 5))
+    nb = torch.full((fv.shape[0],), -1, dtype=torch.int64, device=dev)
+
+    def fwd():
+        return ref.rasterize_meshes(fv, first, num, nb, (H, W), blur, K, bin_size, max_faces_per_bin, False, False,
+                                    False)
+
+    frag = fwd()
+    t_f = _time_ms(fwd, steps=3, warm=1)
+    t_b = _time_ms(lambda: ref.rasterize_meshes_backward(fv, frag[0], gz, gb, gd, False, False), steps=3, warm=1)
+    return {"fwd_ms": t_f, "bwd_ms": t_b, "frames_per_s": nm * 1e3 / (t_f + t_b), "bin_size": bin_size,
+            "max_faces_per_bin": max_faces_per_bin,
+            "what": "pytorch3d/csrc/rasterize_{coarse,meshes}/*.cu compiled unmodified for sm_100a, coarse-to-fine, "
+                    "same batch, same GPU, CUDA events, 3 repeats"}
+
+
+def gather_leg(args, dev, rank, world, nm, fwd, fv, gz, gb, gd, barrier):
+    """The step with every rank receiving the frames of all ranks (dense NCCL all-gather, pix_to_face as int32 on the
+    wire) on a side stream: the gather of step i overlaps the backward pass of step i and the forward pass of
+    step i+1; at most two gathers are in flight."""
+    import torch.distributed as dist
+
+    from pytorch3d_b200 import _C, parallel
+    plan = parallel.ShardPlan([list(range(r * nm, (r + 1) * nm)) for r in range(world)], [0] * (nm * world),
+                              [0] * (nm * world))
+    fg = parallel.FrameGather(plan, rank)
+    f0 = fwd()
+    wire = sum(t.numel() * (4 if t.dtype == torch.int64 else t.element_size()) for t in f0)
+
+    def run(n):
+        prev = None
+        for _ in range(n):
+            f = fwd()
+            h = fg.start(f)
+            _C.rasterize_meshes_backward(fv, f[0], gz, gb, gd, False, False)
+            if prev is not None:
+                prev.wait()
+            prev = h
+        prev.wait()
+
+    run(3)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_g = max(3, min(args.steps, 20))
+    g0.record()
+    run(n_g)
+    g1.record()
+    barrier()
+    tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+    ms = float(tg.item()) / n_g
+    recv = wire * (world - 1)
+    return {"value": world * nm / (ms * 1e-3), "unit": UNIT, "steps": n_g, "ms_per_step": ms,
+            "bytes_received_per_rank_per_step": int(recv),
+            "receive_gb_per_s_per_rank": recv / (ms * 1e-3) / 1e9,
+            "limit": "NVLink ingress of every rank: (N-1)/N of the whole batch's frames, 24 B per (pixel, slot), "
+                     "against ~900 GB/s per direction",
+            "what": "fwd -> [side stream: int32 narrowing, 4 x all_gather_into_tensor (NCCL), widening] overlapped "
+                    "with bwd and the next fwd; every rank ends up with all Fragments of all ranks"}
+
+
+def c4_face_counts(n=32, seed=0):
+    """BASELINE config 4: face counts log-uniform in [5k, 100k]."""
+    g = torch.Generator().manual_seed(seed)
+    u = torch.rand(n, generator=g)
+    return [int(v) for v in torch.exp(np.log(5e3) + u * (np.log(1e5) - np.log(5e3)))]
+
+
+def c4_leg(args, dev, rank, world, barrier):
+    """BASELINE config 4: heterogeneous batch of 32 meshes (5k-100k faces), 512^2, K=8, forward+backward, sharded over
+    the ranks by parallel.ShardPlan (greedy LPT on face counts); total work fixed -> strong scaling."""
+    import torch.distributed as dist
+
+    from pytorch3d_b200 import _C, parallel, synthetic
+    meshes = synthetic.torus_batch_hetero(c4_face_counts(), seed=0)
+    fv_all = synthetic.face_verts_of(meshes).to(dev)
+    first, num = meshes.mesh_to_faces_packed_first_idx(), meshes.num_faces_per_mesh()
+    plan = parallel.ShardPlan.build(first.tolist(), num.tolist(), world)
+    loc = plan.local_inputs(fv_all, rank)
+    del fv_all
+    H = W = 512
+    K = 8
+    nb = torch.full((loc.face_verts.shape[0],), -1, dtype=torch.int64, device=dev)
+    nb._b200_all_minus_one = True
+    n_loc = len(loc.mesh_ids)
+    g = torch.Generator(device=dev).manual_seed(231)
+    gz = torch.randn((n_loc, H, W, K), generator=g, device=dev)
+    gb = torch.randn((n_loc, H, W, K, 3), generator=g, device=dev)
+    gd = torch.randn((n_loc, H, W, K), generator=g, device=dev)
+    fg = parallel.FrameGather(plan, rank)
+
+    def step(gather):
+        f = _C.rasterize_meshes(loc.face_verts, loc.first, loc.num, nb, (H, W), 0.0, K, 0, 0, False, False, False)
+        h = None
+        if gather:
+            h = fg.start([plan.rebase(f[0], rank), f[1], f[2], f[3]])
+        _C.rasterize_meshes_backward(loc.face_verts, f[0], gz, gb, gd, False, False)
+        return h
+
+    def timed(gather, n):
+        for _ in range(3):
+            h = step(gather)
+            if h is not None:
+                h.wait()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        prev = None
+        for _ in range(n):
+            h = step(gather)
+            if prev is not None:
+                prev.wait()
+            prev = h
+        if prev is not None:
+            prev.wait()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n
+
+    n = max(3, min(args.steps, 20))
+    ms = timed(False, n)
+    out = {"workload": "32 tori, faces log-uniform 5k-100k (total %d), 512x512, K=8, blur 0, fwd+bwd" % int(num.sum()),
+           "scaling": "strong", "n_gpus": world, "ms_per_step": ms, "frames_per_s": 32e3 / ms,
+           "faces_per_rank": [int(sum(plan.num[i] for i in ids)) for ids in plan.assignment],
+           "meshes_per_rank": [len(ids) for ids in plan.assignment]}
+    if world > 1:
+        ms_g = timed(True, n)
+        out["with_frame_gather"] = {"ms_per_step": ms_g, "frames_per_s": 32e3 / ms_g}
     return out
 
 
@@ -666,7 +870,8 @@ def main():
     ap.add_argument("--workload", default="ns", choices=sorted(WORKLOADS))
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-host-abi", action="store_true")
-    ap.add_argument("--skip-others", action="store_true", help="skip the config-2 / config-3 context numbers")
+    ap.add_argument("--skip-others", action="store_true", help="skip the other configs / reference-CUDA legs")
+    ap.add_argument("--skip-c4", action="store_true", help="skip the sharded config-4 leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

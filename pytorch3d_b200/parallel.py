@@ -5,13 +5,16 @@ its own image, forward and backward are independent per mesh, so the batch shard
 collective.  The only communication is the one BASELINE.json's north_star names: an optional all-gather
 of the rendered frames (NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests).
 
-    plan  = ShardPlan.build(num_faces_per_mesh, world_size)          # greedy LPT on a cost model
-    local = plan.local_inputs(face_verts, first, num, rank)          # this rank's packed slice
+    plan  = ShardPlan.build(first, num, world_size)                  # greedy LPT on a cost model
+    local = plan.local_inputs(face_verts, rank)                      # this rank's packed slice
     frag  = raster_fn(local.face_verts, local.first, local.num, ...) # any rasterize_meshes op
-    frag  = plan.rebase(frag, rank)                                  # pix_to_face -> global packed ids
-    full  = plan.all_gather(frag, group)                             # optional: whole batch on every rank
+    p2f   = plan.rebase(frag[0], rank)                               # pix_to_face -> global packed ids
+    h     = FrameGather(plan, rank).start((p2f,) + frag[1:])         # whole batch on every rank, on a side stream
+    full  = h.wait()                                                 # ... while the backward pass runs
 
 `pix_to_face` of the gathered result is bit-identical to a single-GPU render of the whole batch.
+Two transports: `FrameGather` (dense NCCL all-gather, pix_to_face narrowed to int32 on the wire) and
+`peer.PackedFrameExchange` (the valid slots only, pushed into every peer's memory over NVLink by one kernel).
 """
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
@@ -68,48 +71,105 @@ class ShardPlan:
             first[1:] = torch.cumsum(num, 0)[:-1]
         return LocalInputs(fv.contiguous(), first, num, list(ids))
 
-    def rebase(self, pix_to_face: torch.Tensor, rank: int) -> torch.Tensor:
-        """Local packed face ids -> global packed face ids (padding -1 kept)."""
-        ids = self.assignment[rank]
-        if not ids:
-            return pix_to_face
-        out = pix_to_face.clone()
-        local_first = 0
-        for j, i in enumerate(ids):
-            shift = self.first[i] - local_first
-            img = out[j]
-            img[img >= 0] += shift
+    def local_shifts(self, rank: int) -> List[int]:
+        """Per local mesh: (first global packed face) - (first local packed face)."""
+        out, local_first = [], 0
+        for i in self.assignment[rank]:
+            out.append(self.first[i] - local_first)
             local_first += self.num[i]
         return out
 
-    def all_gather(self, tensors: Sequence[torch.Tensor], rank: int, group=None) -> List[torch.Tensor]:
-        """All-gather per-rank (n_local, H, W, ...) tensors into (n_meshes, H, W, ...) in batch order.
+    def rebase(self, pix_to_face: torch.Tensor, rank: int) -> torch.Tensor:
+        """Local packed face ids -> global packed face ids (padding -1 kept); one fused elementwise pass."""
+        shifts = self.local_shifts(rank)
+        if not shifts or not any(shifts):
+            return pix_to_face
+        s = torch.tensor(shifts, dtype=pix_to_face.dtype, device=pix_to_face.device).view(-1, 1, 1, 1)
+        return torch.where(pix_to_face >= 0, pix_to_face + s, pix_to_face)
 
-        Ranks may own different numbers of meshes: each contribution is padded to `max_local` images so
-        that one fixed-size collective per tensor suffices (all_gather_into_tensor on NCCL)."""
-        outs = []
-        for t in tensors:
-            pad = self.max_local - t.shape[0]
-            if pad > 0:
-                t = torch.cat([t, t.new_zeros((pad,) + tuple(t.shape[1:]))], 0)
-            t = t.contiguous()
-            if self.world_size == 1 or not dist.is_initialized():
-                gathered = t.unsqueeze(0)
+    def scatter_to_batch_order(self, gathered: torch.Tensor) -> torch.Tensor:
+        """(world, max_local, ...) per-rank blocks -> (n_meshes, ...) in batch order."""
+        if all(self.assignment[r] == list(range(r * self.max_local, (r + 1) * self.max_local))
+               for r in range(self.world_size)):
+            return gathered.reshape((self.n_meshes,) + tuple(gathered.shape[2:]))  # already in order: a view
+        full = gathered.new_empty((self.n_meshes,) + tuple(gathered.shape[2:]))
+        for r, ids in enumerate(self.assignment):
+            if ids:
+                full[torch.tensor(ids, device=gathered.device)] = gathered[r, : len(ids)]
+        return full
+
+    def all_gather(self, tensors: Sequence[torch.Tensor], rank: int, group=None) -> List[torch.Tensor]:
+        """Synchronous all-gather of per-rank (n_local, H, W, ...) tensors into (n_meshes, H, W, ...) in batch
+        order (see FrameGather for the overlapped form)."""
+        return FrameGather(self, rank, group=group, overlap=False).start(tensors).wait()
+
+
+class _GatherHandle:
+    def __init__(self, outs, event, stream):
+        self._outs, self._event, self._stream = outs, event, stream
+
+    def wait(self) -> List[torch.Tensor]:
+        """Make the current stream wait for the gather; returns the full-batch tensors."""
+        if self._event is not None:
+            torch.cuda.current_stream().wait_event(self._event)
+            for t in self._outs:
+                t.record_stream(torch.cuda.current_stream())
+        return self._outs
+
+
+class FrameGather:
+    """All-gather of the rendered frames (the path's only collective), off the critical path.
+
+    Ranks may own different numbers of meshes: each contribution is padded to `max_local` images so that one
+    fixed-size collective per tensor suffices (all_gather_into_tensor on NCCL).  int64 tensors whose values fit
+    32 bits (pix_to_face: packed face ids < 2^31) travel as int32 and are widened on arrival: 24 instead of 28
+    bytes per slot on the wire.  With `overlap` (CUDA only) everything runs on a side stream: `start()` returns at
+    once and the caller's stream only waits in `handle.wait()` -- e.g. after the backward pass of the same batch."""
+
+    def __init__(self, plan: ShardPlan, rank: int, group=None, overlap: bool = True):
+        self.plan, self.rank, self.group = plan, rank, group
+        self.overlap = overlap
+        self._stream = None
+
+    def _gather_one(self, t: torch.Tensor) -> torch.Tensor:
+        plan = self.plan
+        narrow = t.dtype == torch.int64
+        if narrow:
+            t = t.to(torch.int32)
+        pad = plan.max_local - t.shape[0]
+        if pad > 0:
+            t = torch.cat([t, t.new_zeros((pad,) + tuple(t.shape[1:]))], 0)
+        t = t.contiguous()
+        if plan.world_size == 1 or not dist.is_initialized():
+            gathered = t.unsqueeze(0)
+        else:
+            buf = t.new_empty((plan.world_size,) + tuple(t.shape))
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_gather_into_tensor(buf, t, group=self.group)
             else:
-                buf = t.new_empty((self.world_size,) + tuple(t.shape))
-                if dist.get_backend(group) == "nccl":
-                    dist.all_gather_into_tensor(buf, t, group=group)
-                else:
-                    chunks = list(buf.unbind(0))
-                    dist.all_gather(chunks, t, group=group)
-                    buf = torch.stack(chunks, 0)
-                gathered = buf
-            full = t.new_empty((self.n_meshes,) + tuple(t.shape[1:]))
-            for r, ids in enumerate(self.assignment):
-                for j, i in enumerate(ids):
-                    full[i] = gathered[r, j]
-            outs.append(full)
-        return outs
+                chunks = list(buf.unbind(0))
+                dist.all_gather(chunks, t, group=self.group)
+                buf = torch.stack(chunks, 0)
+            gathered = buf
+        full = plan.scatter_to_batch_order(gathered)
+        return full.to(torch.int64) if narrow else full
+
+    def start(self, tensors: Sequence[torch.Tensor]) -> _GatherHandle:
+        tensors = list(tensors)
+        if not (self.overlap and tensors and tensors[0].is_cuda):
+            return _GatherHandle([self._gather_one(t) for t in tensors], None, None)
+        dev = tensors[0].device
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=dev)
+        side = self._stream
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for t in tensors:
+                t.record_stream(side)
+            outs = [self._gather_one(t) for t in tensors]
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return _GatherHandle(outs, ev, side)
 
 
 def rasterize_meshes_sharded(face_verts: torch.Tensor, first: torch.Tensor, num: torch.Tensor, image_size,
@@ -120,11 +180,13 @@ def rasterize_meshes_sharded(face_verts: torch.Tensor, first: torch.Tensor, num:
     """Render this rank's share of the batch; optionally all-gather the frames.
 
     `first` / `num` describe the WHOLE batch (same on every rank); `face_verts` may be the whole packed
-    tensor (only this rank's slices are read).  `raster_fn` has the signature of
-    pytorch3d_b200._C.rasterize_meshes (default); the CPU tests inject the oracle."""
-    if raster_fn is None:
-        from . import _C
-        raster_fn = _C.rasterize_meshes
+    tensor (only this rank's slices are read).  The local render goes through the autograd Function of
+    `pytorch3d_b200.rasterize_meshes`, so zbuf / bary / dists of THIS rank's meshes carry gradients back to
+    `face_verts` (no collective in the backward pass: every rank owns its meshes' vertices); frames of other
+    ranks arrive as constants.  `raster_fn` (signature of pytorch3d_b200._C.rasterize_meshes) replaces the
+    native op -- the CPU tests inject the oracle; it is not differentiable.
+
+    Returns (pix_to_face, zbuf, bary, dists, plan): local frames if `gather` is False, else the whole batch."""
     if rank is None:
         rank = dist.get_rank(group) if dist.is_initialized() else 0
     if world_size is None:
@@ -134,10 +196,24 @@ def rasterize_meshes_sharded(face_verts: torch.Tensor, first: torch.Tensor, num:
     loc = plan.local_inputs(face_verts, rank)
     nb = torch.full((loc.face_verts.shape[0],), -1, dtype=torch.int64, device=face_verts.device)
     nb._b200_all_minus_one = True
-    p2f, zbuf, bary, dists = raster_fn(loc.face_verts, loc.first, loc.num, nb, (H, W), blur_radius, faces_per_pixel,
-                                       0, 0, perspective_correct, clip_barycentric_coords, cull_backfaces)
+    if raster_fn is None:
+        from .rasterize_meshes import _RasterizeFaceVerts
+        p2f, zbuf, bary, dists = _RasterizeFaceVerts.apply(
+            loc.face_verts, loc.first, loc.num, nb, (H, W), blur_radius, faces_per_pixel, 0, 0, perspective_correct,
+            clip_barycentric_coords, cull_backfaces)
+    else:
+        p2f, zbuf, bary, dists = raster_fn(loc.face_verts, loc.first, loc.num, nb, (H, W), blur_radius,
+                                           faces_per_pixel, 0, 0, perspective_correct, clip_barycentric_coords,
+                                           cull_backfaces)
     p2f = plan.rebase(p2f, rank)
     if not gather:
         return p2f, zbuf, bary, dists, plan
-    full = plan.all_gather([p2f, zbuf, bary, dists], rank, group)
+    full = FrameGather(plan, rank, group=group).start(
+        [p2f, zbuf.detach(), bary.detach(), dists.detach()]).wait()
+    if zbuf.requires_grad and loc.mesh_ids:
+        # this rank's own frames stay differentiable inside the gathered batch
+        ids = torch.tensor(loc.mesh_ids, device=zbuf.device)
+        full[1] = full[1].index_copy(0, ids, zbuf)
+        full[2] = full[2].index_copy(0, ids, bary)
+        full[3] = full[3].index_copy(0, ids, dists)
     return full[0], full[1], full[2], full[3], plan
