@@ -177,6 +177,30 @@ int b200r_alpha_composite_backward(const float* grad_out, const float* features,
                                    const int64_t* idx_strides, int32_t N, int32_t K, int32_t H, int32_t W,
                                    float* grad_features, float* grad_alphas, void* stream);
 
+/*
+ * Replace pytorch3d._C.accum_weightedsum / accum_weightedsum_backward
+ *   (weightedSumForward / Backward, pytorch3d/csrc/compositing/weighted_sum.h:57-78, 80-110) and
+ * pytorch3d._C.accum_weightedsumnorm / accum_weightedsumnorm_backward
+ *   (weightedSumNormForward / Backward, compositing/norm_weighted_sum.h:57-79, 81-112):
+ *   result[n,c,y,x] = sum_k alpha[n,k,y,x] * features[c, idx[n,k,y,x]]   (norm: / max(sum_k alpha, 1e-4)),
+ * slots with idx < 0 skipped.  Arguments and layouts exactly as b200r_alpha_composite_forward / _backward.
+ */
+int b200r_weighted_sum_forward(const float* features, int64_t C, int64_t P, const float* alphas,
+                               const int64_t* alpha_strides, const int64_t* points_idx, const int64_t* idx_strides,
+                               int32_t N, int32_t K, int32_t H, int32_t W, float* result, void* stream);
+int b200r_weighted_sum_backward(const float* grad_outputs, const float* features, int64_t C, int64_t P,
+                                const float* alphas, const int64_t* alpha_strides, const int64_t* points_idx,
+                                const int64_t* idx_strides, int32_t N, int32_t K, int32_t H, int32_t W,
+                                float* grad_features, float* grad_alphas, void* stream);
+int b200r_norm_weighted_sum_forward(const float* features, int64_t C, int64_t P, const float* alphas,
+                                    const int64_t* alpha_strides, const int64_t* points_idx,
+                                    const int64_t* idx_strides, int32_t N, int32_t K, int32_t H, int32_t W,
+                                    float* result, void* stream);
+int b200r_norm_weighted_sum_backward(const float* grad_outputs, const float* features, int64_t C, int64_t P,
+                                     const float* alphas, const int64_t* alpha_strides, const int64_t* points_idx,
+                                     const int64_t* idx_strides, int32_t N, int32_t K, int32_t H, int32_t W,
+                                     float* grad_features, float* grad_alphas, void* stream);
+
 /* ------------------------------------------------------------------ face attribute interpolation */
 
 /*
@@ -198,6 +222,48 @@ int b200r_interp_face_attrs_forward(const int64_t* pix_to_face, const float* bar
 int b200r_interp_face_attrs_backward(const int64_t* pix_to_face, const float* barycentric_coords,
                                      const float* face_attrs, const float* grad_pix_attrs, int64_t P, int64_t F,
                                      int64_t D, float* grad_barycentric_coords, float* grad_face_attrs, void* stream);
+
+/* ------------------------------------------------------------------ frame exchange between GPUs ---------- */
+
+/*
+ * The path's only collective (BASELINE.json north_star: "NCCL over NVLink only to gather rendered frames"; the
+ * reference has no counterpart, tests/test_render_multigpu.py:120-185 only moves modules between devices).
+ * Fragments are exchanged in a packed, lossless form -- 1 byte per pixel (number of valid slots) + 24 bytes per
+ * VALID slot -- that one kernel writes straight into the memory of every peer over NVLink.
+ *
+ * Peer memory: b200r_peer_alloc cudaMallocs `bytes` on the current device and returns a 64-byte CUDA IPC handle
+ * that another process of the same node turns into a device pointer with b200r_peer_open (peer access is enabled
+ * on first use).  b200r_peer_close / b200r_peer_free undo them.
+ */
+int b200r_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int b200r_peer_open(const unsigned char* handle64, void** ptr);
+int b200r_peer_close(void* ptr);
+int b200r_peer_free(void* ptr);
+
+/* Bytes of one packed-stream region sized for `n_images` frames of H x W x K slots (worst case: every slot valid). */
+size_t b200r_packed_frames_bytes(int64_t n_images, int32_t H, int32_t W, int32_t K);
+
+/*
+ * Pack the Fragments of `n_images` local frames (the four outputs of b200r_rasterize_meshes_forward; valid slots
+ * first in every pixel, as the rasterizer writes them) and store the stream into each of the `n_dst` regions
+ * (HOST array of device pointers: local memory or b200r_peer_open'ed peer memory; each region laid out for
+ * `n_images_layout` >= n_images frames).  `cursor`: one device int32 of scratch.  K <= 32, n_dst <= 16.
+ * Completion of the kernel on `stream` + any cross-rank synchronisation (e.g. an NCCL barrier enqueued behind it)
+ * makes the stream readable on the destination.
+ */
+int b200r_fragments_pack_push(const int64_t* pix_to_face, const float* zbuf, const float* bary, const float* dists,
+                              int32_t n_images, int32_t H, int32_t W, int32_t K, int64_t n_images_layout,
+                              void* const* dst_regions, int32_t n_dst, int32_t* cursor, void* stream);
+
+/*
+ * Expand a packed stream (device pointer `region`, written by b200r_fragments_pack_push with the same H, W, K and
+ * n_images_layout) into dense full-batch buffers: frame j of the stream lands at batch position image_index[j]
+ * (device int32 (n_images,)), its face ids shifted by face_shift[j] (device int64 (n_images,): first global packed face
+ * of the mesh minus its first face in the sender's local packing); empty slots are written as -1.
+ */
+int b200r_fragments_unpack(const void* region, int32_t n_images, int32_t H, int32_t W, int32_t K,
+                           int64_t n_images_layout, const int32_t* image_index, const int64_t* face_shift,
+                           int64_t* pix_to_face, float* zbuf, float* bary, float* dists, void* stream);
 
 /* ------------------------------------------------------------------ host-buffer entry points - */
 

@@ -157,6 +157,31 @@ def alpha_composite_backward(grad_out, features, alphas, points_idx):
     return gf, ga
 
 
+def weighted_sum(features, alphas, points_idx, norm=False):
+    """features (C,P), alphas / points_idx (N,K,H,W) -> (N,C,H,W); norm: divided by max(sum of alphas, 1e-4)."""
+    f, a = _f32(features), _f32(alphas)
+    idx = _i64(points_idx)
+    C, P = f.shape
+    N, K, H, W = idx.shape
+    out = np.zeros((N, C, H, W), np.float32)
+    lib().oracle_weighted_sum_forward(_p(f, ctypes.c_float), ctypes.c_int64(C), ctypes.c_int64(P),
+                                      _p(a, ctypes.c_float), _p(idx, ctypes.c_int64), N, K, H, W, int(bool(norm)),
+                                      _p(out, ctypes.c_float))
+    return out
+
+
+def weighted_sum_backward(grad_out, features, alphas, points_idx, norm=False):
+    g, f, a = _f32(grad_out), _f32(features), _f32(alphas)
+    idx = _i64(points_idx)
+    C, P = f.shape
+    N, K, H, W = idx.shape
+    gf, ga = np.zeros_like(f), np.zeros_like(a)
+    lib().oracle_weighted_sum_backward(_p(g, ctypes.c_float), _p(f, ctypes.c_float), ctypes.c_int64(C),
+                                       ctypes.c_int64(P), _p(a, ctypes.c_float), _p(idx, ctypes.c_int64), N, K, H, W,
+                                       int(bool(norm)), _p(gf, ctypes.c_float), _p(ga, ctypes.c_float))
+    return gf, ga
+
+
 def interp_face_attrs(pix_to_face, bary, attrs, arith=ARITH_CPU):
     """pix_to_face (P,), bary (P,3), attrs (F,3,D) -> (P,D)."""
     p2f, b, a = _i64(pix_to_face).reshape(-1), _f32(bary).reshape(-1, 3), _f32(attrs)

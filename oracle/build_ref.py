@@ -35,12 +35,16 @@ CPU_SOURCES = [
     os.path.join(CSRC, "rasterize_meshes", "rasterize_meshes_cpu.cpp"),
     os.path.join(CSRC, "rasterize_points", "rasterize_points_cpu.cpp"),
     os.path.join(CSRC, "compositing", "alpha_composite_cpu.cpp"),
+    os.path.join(CSRC, "compositing", "weighted_sum_cpu.cpp"),
+    os.path.join(CSRC, "compositing", "norm_weighted_sum_cpu.cpp"),
 ]
 CUDA_SOURCES = [
     os.path.join(CSRC, "rasterize_meshes", "rasterize_meshes.cu"),
     os.path.join(CSRC, "rasterize_coarse", "rasterize_coarse.cu"),
     os.path.join(CSRC, "rasterize_points", "rasterize_points.cu"),
     os.path.join(CSRC, "compositing", "alpha_composite.cu"),
+    os.path.join(CSRC, "compositing", "weighted_sum.cu"),
+    os.path.join(CSRC, "compositing", "norm_weighted_sum.cu"),
     os.path.join(CSRC, "interp_face_attrs", "interp_face_attrs.cu"),
 ]
 SHIM = os.path.join(HERE, "ref_shim.cpp")

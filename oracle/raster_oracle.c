@@ -779,6 +779,72 @@ int oracle_alpha_composite_backward(const float* grad_out, const float* features
   return 0;
 }
 
+/* ------------------------------------------------------------------ weighted sums */
+/* Restates pytorch3d/csrc/compositing/weighted_sum_cpu.cpp:17-55 / :57-103 and norm_weighted_sum_cpu.cpp:19-68 /
+ * :70-137 (the CUDA kernels weighted_sum.cu:22-103, norm_weighted_sum.cu:24-160 perform the same operations in the
+ * same order: (alpha * f) [/ total], summed over ascending k -- one arithmetic flavour).  norm != 0: divide by
+ * max(sum of the valid alphas, 1e-4). */
+int oracle_weighted_sum_forward(const float* features, int64_t C, int64_t P, const float* alphas,
+                                const int64_t* points_idx, int N, int K, int H, int W, int norm, float* result) {
+  const int64_t plane = (int64_t)H * W;
+  for (int b = 0; b < N; ++b)
+    for (int64_t c = 0; c < C; ++c)
+      for (int64_t px = 0; px < plane; ++px) {
+        float t_alpha = 0.0f;
+        for (int k = 0; k < K; ++k) {
+          if (points_idx[((int64_t)b * K + k) * plane + px] < 0) continue;
+          t_alpha += alphas[((int64_t)b * K + k) * plane + px];
+        }
+        if (t_alpha < 1e-4f) t_alpha = 1e-4f;
+        float acc = 0.0f;
+        for (int k = 0; k < K; ++k) {
+          const int64_t id = points_idx[((int64_t)b * K + k) * plane + px];
+          if (id < 0) continue;
+          const float a = alphas[((int64_t)b * K + k) * plane + px];
+          const float t = a * features[c * P + id];
+          acc += norm ? t / t_alpha : t;
+        }
+        result[((int64_t)b * C + c) * plane + px] = acc;
+      }
+  return 0;
+}
+
+int oracle_weighted_sum_backward(const float* grad_out, const float* features, int64_t C, int64_t P,
+                                 const float* alphas, const int64_t* points_idx, int N, int K, int H, int W, int norm,
+                                 float* grad_features, float* grad_alphas) {
+  const int64_t plane = (int64_t)H * W;
+  memset(grad_features, 0, sizeof(float) * (size_t)(C * P));
+  memset(grad_alphas, 0, sizeof(float) * (size_t)N * K * plane);
+  for (int b = 0; b < N; ++b)
+    for (int64_t c = 0; c < C; ++c)
+      for (int64_t px = 0; px < plane; ++px) {
+        const float g = grad_out[((int64_t)b * C + c) * plane + px];
+        float t_alpha = 0.0f, t_alphafs = 0.0f;
+        for (int k = 0; k < K; ++k) {
+          const int64_t id = points_idx[((int64_t)b * K + k) * plane + px];
+          if (id < 0) continue;
+          const float a = alphas[((int64_t)b * K + k) * plane + px];
+          t_alpha += a;
+          t_alphafs += a * features[c * P + id];
+        }
+        if (t_alpha < 1e-4f) t_alpha = 1e-4f;
+        for (int k = 0; k < K; ++k) {
+          const int64_t id = points_idx[((int64_t)b * K + k) * plane + px];
+          if (id < 0) continue;
+          const float a = alphas[((int64_t)b * K + k) * plane + px];
+          if (norm) {
+            grad_alphas[((int64_t)b * K + k) * plane + px] +=
+                g * (features[c * P + id] * t_alpha - t_alphafs) / (t_alpha * t_alpha);
+            grad_features[c * P + id] += g * a / t_alpha;
+          } else {
+            grad_alphas[((int64_t)b * K + k) * plane + px] += g * features[c * P + id];
+            grad_features[c * P + id] += g * a;
+          }
+        }
+      }
+  return 0;
+}
+
 /* ------------------------------------------------------------------ face attribute interpolation */
 /* Restates InterpFaceAttrsForwardKernel / BackwardKernel (pytorch3d/csrc/interp_face_attrs/interp_face_attrs.cu:15-49,
  * 86-124) and the CPU path interpolate_face_attributes_python (pytorch3d/ops/interp_face_attrs.py:83-102).

@@ -17,6 +17,8 @@
 #include "rasterize_points/rasterize_points.h"
 #include "interp_face_attrs/interp_face_attrs.h"  // CUDA only in the reference (ext.cpp:49-50)
 #include "compositing/alpha_composite.h"  // alphaCompositeForward :59, alphaCompositeBackward :84 (ext.cpp:75-76)
+#include "compositing/norm_weighted_sum.h"  // weightedSumNormForward / Backward (ext.cpp:77-78)
+#include "compositing/weighted_sum.h"  // weightedSumForward / Backward (ext.cpp:79-80)
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rasterize_meshes", &RasterizeMeshes);
@@ -30,6 +32,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("_rasterize_points_naive", &RasterizePointsNaive);
   m.def("accum_alphacomposite", &alphaCompositeForward);
   m.def("accum_alphacomposite_backward", &alphaCompositeBackward);
+  m.def("accum_weightedsumnorm", &weightedSumNormForward);
+  m.def("accum_weightedsumnorm_backward", &weightedSumNormBackward);
+  m.def("accum_weightedsum", &weightedSumForward);
+  m.def("accum_weightedsum_backward", &weightedSumBackward);
 #ifdef WITH_CUDA
   m.def("interp_face_attrs_forward", &InterpFaceAttrsForward);
   m.def("interp_face_attrs_backward", &InterpFaceAttrsBackward);

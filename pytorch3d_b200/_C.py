@@ -316,10 +316,7 @@ def _strides4(t):
     return (ctypes.c_int64 * 4)(*[int(v) for v in t.stride()])
 
 
-def accum_alphacomposite(features: torch.Tensor, alphas: torch.Tensor, points_idx: torch.Tensor):
-    """pytorch3d._C.accum_alphacomposite (alphaCompositeForward, csrc/compositing/alpha_composite.h:59-82).
-
-    features (C,P) f32, alphas (N,K,H,W) f32, points_idx (N,K,H,W) i64 (any strides) -> (N,C,H,W) f32."""
+def _composite_forward(fn_name, features, alphas, points_idx):
     dev = _require_cuda(("features", features), ("alphas", alphas), ("points_idx", points_idx))
     if features.dtype != torch.float32 or alphas.dtype != torch.float32:
         raise RuntimeError("expected scalar type Float")
@@ -337,15 +334,13 @@ def accum_alphacomposite(features: torch.Tensor, alphas: torch.Tensor, points_id
             return result
         if K == 0:
             return result.zero_()
-        _lib.check(lib.b200r_alpha_composite_forward(
+        _lib.check(getattr(lib, fn_name)(
             _ptr(feat), C, P, alphas.data_ptr(), _strides4(alphas), points_idx.data_ptr(), _strides4(points_idx),
             N, K, H, W, _ptr(result), _stream_ptr(dev)))
     return result
 
 
-def accum_alphacomposite_backward(grad_outputs: torch.Tensor, features: torch.Tensor, alphas: torch.Tensor,
-                                  points_idx: torch.Tensor):
-    """pytorch3d._C.accum_alphacomposite_backward (alpha_composite.h:84-116) -> (grad_features, grad_alphas)."""
+def _composite_backward(fn_name, grad_outputs, features, alphas, points_idx):
     dev = _require_cuda(("grad_outputs", grad_outputs), ("features", features), ("alphas", alphas),
                         ("points_idx", points_idx))
     lib = _lib.load()
@@ -357,10 +352,45 @@ def accum_alphacomposite_backward(grad_outputs: torch.Tensor, features: torch.Te
         grad_alphas = torch.empty((N, K, H, W), dtype=torch.float32, device=dev)
         if C * P == 0 or grad_alphas.numel() == 0:
             return grad_features.zero_(), grad_alphas.zero_()
-        _lib.check(lib.b200r_alpha_composite_backward(
+        _lib.check(getattr(lib, fn_name)(
             _ptr(go), _ptr(feat), C, P, alphas.data_ptr(), _strides4(alphas), points_idx.data_ptr(),
             _strides4(points_idx), N, K, H, W, _ptr(grad_features), _ptr(grad_alphas), _stream_ptr(dev)))
     return grad_features, grad_alphas
+
+
+def accum_alphacomposite(features: torch.Tensor, alphas: torch.Tensor, points_idx: torch.Tensor):
+    """pytorch3d._C.accum_alphacomposite (alphaCompositeForward, csrc/compositing/alpha_composite.h:59-82).
+
+    features (C,P) f32, alphas (N,K,H,W) f32, points_idx (N,K,H,W) i64 (any strides) -> (N,C,H,W) f32."""
+    return _composite_forward("b200r_alpha_composite_forward", features, alphas, points_idx)
+
+
+def accum_alphacomposite_backward(grad_outputs: torch.Tensor, features: torch.Tensor, alphas: torch.Tensor,
+                                  points_idx: torch.Tensor):
+    """pytorch3d._C.accum_alphacomposite_backward (alpha_composite.h:84-116) -> (grad_features, grad_alphas)."""
+    return _composite_backward("b200r_alpha_composite_backward", grad_outputs, features, alphas, points_idx)
+
+
+def accum_weightedsum(features: torch.Tensor, alphas: torch.Tensor, points_idx: torch.Tensor):
+    """pytorch3d._C.accum_weightedsum (weightedSumForward, csrc/compositing/weighted_sum.h:57-78)."""
+    return _composite_forward("b200r_weighted_sum_forward", features, alphas, points_idx)
+
+
+def accum_weightedsum_backward(grad_outputs: torch.Tensor, features: torch.Tensor, alphas: torch.Tensor,
+                               points_idx: torch.Tensor):
+    """pytorch3d._C.accum_weightedsum_backward (weighted_sum.h:80-110) -> (grad_features, grad_alphas)."""
+    return _composite_backward("b200r_weighted_sum_backward", grad_outputs, features, alphas, points_idx)
+
+
+def accum_weightedsumnorm(features: torch.Tensor, alphas: torch.Tensor, points_idx: torch.Tensor):
+    """pytorch3d._C.accum_weightedsumnorm (weightedSumNormForward, csrc/compositing/norm_weighted_sum.h:57-79)."""
+    return _composite_forward("b200r_norm_weighted_sum_forward", features, alphas, points_idx)
+
+
+def accum_weightedsumnorm_backward(grad_outputs: torch.Tensor, features: torch.Tensor, alphas: torch.Tensor,
+                                   points_idx: torch.Tensor):
+    """pytorch3d._C.accum_weightedsumnorm_backward (norm_weighted_sum.h:81-112) -> (grad_features, grad_alphas)."""
+    return _composite_backward("b200r_norm_weighted_sum_backward", grad_outputs, features, alphas, points_idx)
 
 
 def interp_face_attrs_forward(pix_to_face: torch.Tensor, barycentric_coords: torch.Tensor, face_attrs: torch.Tensor):

@@ -43,8 +43,25 @@ SIGNATURES = {
         ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "b200r_alpha_composite_backward": (
         ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "b200r_weighted_sum_forward": (
+        ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "b200r_weighted_sum_backward": (
+        ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "b200r_norm_weighted_sum_forward": (
+        ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "b200r_norm_weighted_sum_backward": (
+        ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b200r_interp_face_attrs_forward": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "b200r_interp_face_attrs_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "b200r_peer_alloc": (ctypes.c_int, [_sz, ctypes.POINTER(_vp), ctypes.c_char_p]),
+    "b200r_peer_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "b200r_peer_close": (ctypes.c_int, [_vp]),
+    "b200r_peer_free": (ctypes.c_int, [_vp]),
+    "b200r_packed_frames_bytes": (_sz, [_i64, _i32, _i32, _i32]),
+    "b200r_fragments_pack_push": (
+        ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, ctypes.POINTER(_vp), _i32, _vp, _vp]),
+    "b200r_fragments_unpack": (
+        ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200r_rasterize_meshes_forward_host": (
         ctypes.c_int,
         [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),

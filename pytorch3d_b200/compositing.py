@@ -1,5 +1,6 @@
-"""Alpha compositing of point features, same API as the reference:
-pytorch3d/renderer/compositing.py:19-96 (`alpha_composite`) and points/compositor.py:22-66 (`AlphaCompositor`).
+"""Compositing of point features, same API as the reference:
+pytorch3d/renderer/compositing.py:19-250 (`alpha_composite`, `norm_weighted_sum`, `weighted_sum`) and
+points/compositor.py:22-116 (`AlphaCompositor`, `NormWeightedCompositor`).
 """
 import torch
 import torch.nn as nn
@@ -29,6 +30,44 @@ def alpha_composite(pointsidx, alphas, pt_clds) -> torch.Tensor:
     return _CompositeAlphaPoints.apply(pt_clds, alphas, pointsidx)
 
 
+def _make_composite(forward_op, backward_op, doc):
+    class _Composite(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, features, alphas, points_idx):
+            pt_cld = forward_op(features, alphas, points_idx)
+            ctx.save_for_backward(features.clone(), alphas.clone(), points_idx.clone())
+            return pt_cld
+
+        @staticmethod
+        def backward(ctx, grad_output):
+            features, alphas, points_idx = ctx.saved_tensors
+            grad_features, grad_alphas = backward_op(grad_output, features, alphas, points_idx)
+            return grad_features, grad_alphas, None
+
+    _Composite.__doc__ = doc
+    return _Composite
+
+
+_CompositeNormWeightedSumPoints = _make_composite(
+    _C.accum_weightedsumnorm, _C.accum_weightedsumnorm_backward,
+    "weighted_fs[b,c,i,j] = sum_k alphas[b,k,i,j] * features[c, pointsidx[b,k,i,j]] / max(sum_k alphas[b,k,i,j], 1e-4)"
+    "   (compositing.py:99-146 of the reference).")
+_CompositeWeightedSumPoints = _make_composite(
+    _C.accum_weightedsum, _C.accum_weightedsum_backward,
+    "weighted_fs[b,c,i,j] = sum_k alphas[b,k,i,j] * features[c, pointsidx[b,k,i,j]]"
+    "   (compositing.py:177-222 of the reference).")
+
+
+def norm_weighted_sum(pointsidx, alphas, pt_clds) -> torch.Tensor:
+    """Normalised weighted sum (compositing.py:149-174 of the reference): same arguments as `alpha_composite`."""
+    return _CompositeNormWeightedSumPoints.apply(pt_clds, alphas, pointsidx)
+
+
+def weighted_sum(pointsidx, alphas, pt_clds) -> torch.Tensor:
+    """Weighted sum (compositing.py:225-250 of the reference): same arguments as `alpha_composite`."""
+    return _CompositeWeightedSumPoints.apply(pt_clds, alphas, pointsidx)
+
+
 class AlphaCompositor(nn.Module):
     """Accumulate points using alpha compositing (points/compositor.py:22-66 of the reference)."""
 
@@ -39,6 +78,21 @@ class AlphaCompositor(nn.Module):
     def forward(self, fragments, alphas, ptclds, **kwargs) -> torch.Tensor:
         background_color = kwargs.get("background_color", self.background_color)
         images = alpha_composite(fragments, alphas, ptclds)
+        if background_color is not None:
+            images = _add_background_color_to_images(fragments, images, background_color)
+        return images
+
+
+class NormWeightedCompositor(nn.Module):
+    """Accumulate points using a normalised weighted sum (points/compositor.py:69-116 of the reference)."""
+
+    def __init__(self, background_color=None) -> None:
+        super().__init__()
+        self.background_color = background_color
+
+    def forward(self, fragments, alphas, ptclds, **kwargs) -> torch.Tensor:
+        background_color = kwargs.get("background_color", self.background_color)
+        images = norm_weighted_sum(fragments, alphas, ptclds)
         if background_color is not None:
             images = _add_background_color_to_images(fragments, images, background_color)
         return images

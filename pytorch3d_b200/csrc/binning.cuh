@@ -56,10 +56,20 @@ __device__ __forceinline__ bool rect_empty(uint2 r) { return (r.x & 0xFFFFu) > (
 // target the same few tiles -- the lanes that agree are found with __match_any_sync and only one of them issues
 // the atomic, with the group's population.  This removes the serialisation of thousands of atomics on the hot
 // tiles of a silhouette.
+// AGG = false (point clouds, whose packed order carries no spatial coherence): every element simply issues its own
+// atomics -- the warp-wide MATCH per round costs more than the 32 uncontended atomics it would merge (8 x 100k
+// uniform points: 49 -> see profiles/README.md).
+template <bool AGG = true>
 __device__ __forceinline__ void warp_count_rect(uint2 r, int n, int TY, int TX, int* __restrict__ tile_count,
                                                 int lane) {
   const bool empty = rect_empty(r);
   const int tx0 = r.x & 0xFFFF, tx1 = r.x >> 16, ty0 = r.y & 0xFFFF, ty1 = r.y >> 16;
+  if (!AGG) {
+    if (empty) return;
+    for (int ty = ty0; ty <= ty1; ++ty)
+      for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(tile_count + (n * TY + ty) * TX + tx, 1);
+    return;
+  }
   const int w = empty ? 1 : tx1 - tx0 + 1;
   const int ntile = empty ? 0 : w * (ty1 - ty0 + 1);
   const int rounds = (int)__reduce_max_sync(0xffffffffu, (unsigned)ntile);
@@ -136,6 +146,7 @@ static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict_
 // Pass 3: scatter element ids into the tile segments (`cursor` starts at each segment's begin).  Same warp
 // aggregation as in the count pass: one returning atomic per (warp, tile); the lanes of a group take
 // consecutive positions in lane (= element) order.
+template <bool AGG>
 static __global__ void __launch_bounds__(256)
     tile_fill_kernel(const uint4* __restrict__ rect, int64_t E, int TY, int TX, int* __restrict__ cursor,
                      int* __restrict__ pairs, int64_t capacity) {
@@ -147,6 +158,15 @@ static __global__ void __launch_bounds__(256)
   const bool empty = rect_empty(r);
   const int n = (int)r4.z;
   const int tx0 = r.x & 0xFFFF, tx1 = r.x >> 16, ty0 = r.y & 0xFFFF, ty1 = r.y >> 16;
+  if (!AGG) {  // one returning atomic per (element, tile), see warp_count_rect
+    if (empty) return;
+    for (int ty = ty0; ty <= ty1; ++ty)
+      for (int tx = tx0; tx <= tx1; ++tx) {
+        const int pos = atomicAdd(cursor + (n * TY + ty) * TX + tx, 1);
+        if (pos >= 0 && (int64_t)pos < capacity) pairs[pos] = (int)e;
+      }
+    return;
+  }
   const int w = empty ? 1 : tx1 - tx0 + 1;
   const int ntile = empty ? 0 : w * (ty1 - ty0 + 1);
   const int rounds = (int)__reduce_max_sync(0xffffffffu, (unsigned)ntile);

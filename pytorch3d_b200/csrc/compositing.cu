@@ -105,6 +105,100 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weighted sum and normalised weighted sum of point features: replace
+//   weightedSumCudaForwardKernel / BackwardKernel          (pytorch3d/csrc/compositing/weighted_sum.cu:22-61, 63-103)
+//   weightedSumNormCudaForwardKernel / BackwardKernel      (norm_weighted_sum.cu:24-82, 84-160)
+// behind pytorch3d._C.accum_weightedsum[_backward] / accum_weightedsumnorm[_backward].
+//   result[n,c,y,x] = sum_k alpha_k * feat[c, idx_k]  (/ max(sum_k alpha_k, 1e-4) when NORM)
+// Same redesign as above: one thread per pixel, every output written once (the reference zero-fills `result` and
+// `grad_alphas` and accumulates both with atomics, one thread per (pixel, channel)); only grad_features scatters.
+// Forward: the reference's operations in its order ((f * alpha) / total, summed over ascending k) -> identical bits.
+// Backward of NORM: grad_alpha_k = sum_c g_c (f_ck S - sum_t alpha_t f_ct) / S^2 = A_k / S - T / S^2 with
+// A_k = sum_c g_c f_ck and T = sum_t alpha_t A_t: two passes over the K slots instead of a per-channel rescan.
+// ------------------------------------------------------------------------------------------------
+constexpr float kNormEps = 1e-4f;  // norm_weighted_sum.cu:20
+
+template <bool NORM>
+__global__ void __launch_bounds__(256)
+    weighted_sum_forward_kernel(const float* __restrict__ features, int64_t C, int64_t P,
+                                const float* __restrict__ alphas, Strides4 sa, const int64_t* __restrict__ points_idx,
+                                Strides4 si, int N, int K, int H, int W, float* __restrict__ result) {
+  const int64_t total = (int64_t)N * H * W;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += stride) {
+    const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
+    const float* ap = alphas + n * sa.n + y * sa.y + x * sa.x;
+    const int64_t* ip = points_idx + n * si.n + y * si.y + x * si.x;
+    float sum_alpha = 1.0f;
+    if (NORM) {
+      sum_alpha = 0.0f;
+      for (int k = 0; k < K; ++k)
+        if ((int)ip[k * si.k] >= 0) sum_alpha = fadd(sum_alpha, ap[k * sa.k]);  // (:54-62; index read into an int)
+      if (sum_alpha < kNormEps) sum_alpha = kNormEps;
+    }
+    for (int64_t c = 0; c < C; ++c) {
+      const float* fc = features + c * P;
+      float acc = 0.0f;
+      for (int k = 0; k < K; ++k) {
+        const int id = (int)ip[k * si.k];
+        if (id < 0) continue;
+        const float t = fmul(__ldg(fc + id), ap[k * sa.k]);
+        acc = fadd(acc, NORM ? fdiv(t, sum_alpha) : t);  // (norm_weighted_sum.cu:78-79, weighted_sum.cu:58)
+      }
+      result[(((int64_t)n * C + c) * H + y) * W + x] = acc;
+    }
+  }
+}
+
+template <bool NORM>
+__global__ void __launch_bounds__(256)
+    weighted_sum_backward_kernel(const float* __restrict__ grad_out, const float* __restrict__ features, int64_t C,
+                                 int64_t P, const float* __restrict__ alphas, Strides4 sa,
+                                 const int64_t* __restrict__ points_idx, Strides4 si, int N, int K, int H, int W,
+                                 float* __restrict__ grad_features, float* __restrict__ grad_alphas) {
+  const int64_t total = (int64_t)N * H * W;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t plane = (int64_t)H * W;
+  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += stride) {
+    const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / plane);
+    const float* ap = alphas + n * sa.n + y * sa.y + x * sa.x;
+    const int64_t* ip = points_idx + n * si.n + y * si.y + x * si.x;
+    const float* go = grad_out + (int64_t)n * C * plane + (int64_t)y * W + x;  // + c * plane
+    float* ga = grad_alphas + (int64_t)n * K * plane + (int64_t)y * W + x;     // + k * plane (contiguous N,K,H,W)
+    float S = 1.0f;
+    if (NORM) {
+      S = 0.0f;
+      for (int k = 0; k < K; ++k)
+        if ((int)ip[k * si.k] >= 0) S += ap[k * sa.k];
+      if (S < kNormEps) S = kNormEps;
+    }
+    const float inv_s = 1.0f / S;
+    float T = 0.0f;
+    for (int k = 0; k < K; ++k) {
+      const int id = (int)ip[k * si.k];
+      if (id < 0) {
+        ga[k * plane] = 0.0f;
+        continue;
+      }
+      const float a = ap[k * sa.k];
+      float A = 0.0f;
+      for (int64_t c = 0; c < C; ++c) {
+        const float g = go[c * plane];
+        A += g * __ldg(features + c * P + id);
+        atomicAdd(grad_features + c * P + id, NORM ? a * g * inv_s : a * g);  // (weighted_sum.cu:99-100, norm:155-157)
+      }
+      ga[k * plane] = NORM ? A * inv_s : A;
+      T += a * A;
+    }
+    if (NORM) {
+      const float corr = T * inv_s * inv_s;
+      for (int k = 0; k < K; ++k)
+        if ((int)ip[k * si.k] >= 0) ga[k * plane] -= corr;
+    }
+  }
+}
+
 }  // namespace b200r
 
 using namespace b200r;
@@ -152,4 +246,76 @@ extern "C" int b200r_alpha_composite_backward(const float* grad_out, const float
                                                                       si, N, K, H, W, grad_features, grad_alphas);
   B200R_LAUNCHED("alpha_composite_backward_kernel");
   return B200R_OK;
+}
+
+template <bool NORM>
+static int weighted_sum_forward_impl(const float* features, int64_t C, int64_t P, const float* alphas,
+                                     const int64_t* alpha_strides, const int64_t* points_idx,
+                                     const int64_t* idx_strides, int32_t N, int32_t K, int32_t H, int32_t W,
+                                     float* result, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_comp_args(C, P, N, K, H, W);
+  if (rc != B200R_OK) return rc;
+  const int64_t total = (int64_t)N * H * W;
+  if (total == 0 || C == 0) return B200R_OK;
+  const Strides4 sa = {alpha_strides[0], alpha_strides[1], alpha_strides[2], alpha_strides[3]};
+  const Strides4 si = {idx_strides[0], idx_strides[1], idx_strides[2], idx_strides[3]};
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  weighted_sum_forward_kernel<NORM><<<(unsigned)blocks, 256, 0, stream>>>(features, C, P, alphas, sa, points_idx, si, N,
+                                                                        K, H, W, result);
+  B200R_LAUNCHED("weighted_sum_forward_kernel");
+  return B200R_OK;
+}
+
+template <bool NORM>
+static int weighted_sum_backward_impl(const float* grad_out, const float* features, int64_t C, int64_t P,
+                                      const float* alphas, const int64_t* alpha_strides, const int64_t* points_idx,
+                                      const int64_t* idx_strides, int32_t N, int32_t K, int32_t H, int32_t W,
+                                      float* grad_features, float* grad_alphas, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_comp_args(C, P, N, K, H, W);
+  if (rc != B200R_OK) return rc;
+  if (C * P > 0) B200R_CUDA_OK(cudaMemsetAsync(grad_features, 0, sizeof(float) * (size_t)(C * P), stream));
+  const int64_t total = (int64_t)N * H * W;
+  if (total == 0 || K == 0) return B200R_OK;
+  const Strides4 sa = {alpha_strides[0], alpha_strides[1], alpha_strides[2], alpha_strides[3]};
+  const Strides4 si = {idx_strides[0], idx_strides[1], idx_strides[2], idx_strides[3]};
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  weighted_sum_backward_kernel<NORM><<<(unsigned)blocks, 256, 0, stream>>>(
+      grad_out, features, C, P, alphas, sa, points_idx, si, N, K, H, W, grad_features, grad_alphas);
+  B200R_LAUNCHED("weighted_sum_backward_kernel");
+  return B200R_OK;
+}
+
+extern "C" int b200r_weighted_sum_forward(const float* features, int64_t C, int64_t P, const float* alphas,
+                                          const int64_t* alpha_strides, const int64_t* points_idx,
+                                          const int64_t* idx_strides, int32_t N, int32_t K, int32_t H, int32_t W,
+                                          float* result, void* stream) {
+  return weighted_sum_forward_impl<false>(features, C, P, alphas, alpha_strides, points_idx, idx_strides, N, K, H, W,
+                                          result, stream);
+}
+extern "C" int b200r_weighted_sum_backward(const float* grad_out, const float* features, int64_t C, int64_t P,
+                                           const float* alphas, const int64_t* alpha_strides,
+                                           const int64_t* points_idx, const int64_t* idx_strides, int32_t N, int32_t K,
+                                           int32_t H, int32_t W, float* grad_features, float* grad_alphas,
+                                           void* stream) {
+  return weighted_sum_backward_impl<false>(grad_out, features, C, P, alphas, alpha_strides, points_idx, idx_strides, N,
+                                           K, H, W, grad_features, grad_alphas, stream);
+}
+extern "C" int b200r_norm_weighted_sum_forward(const float* features, int64_t C, int64_t P, const float* alphas,
+                                               const int64_t* alpha_strides, const int64_t* points_idx,
+                                               const int64_t* idx_strides, int32_t N, int32_t K, int32_t H, int32_t W,
+                                               float* result, void* stream) {
+  return weighted_sum_forward_impl<true>(features, C, P, alphas, alpha_strides, points_idx, idx_strides, N, K, H, W,
+                                         result, stream);
+}
+extern "C" int b200r_norm_weighted_sum_backward(const float* grad_out, const float* features, int64_t C, int64_t P,
+                                                const float* alphas, const int64_t* alpha_strides,
+                                                const int64_t* points_idx, const int64_t* idx_strides, int32_t N,
+                                                int32_t K, int32_t H, int32_t W, float* grad_features,
+                                                float* grad_alphas, void* stream) {
+  return weighted_sum_backward_impl<true>(grad_out, features, C, P, alphas, alpha_strides, points_idx, idx_strides, N,
+                                          K, H, W, grad_features, grad_alphas, stream);
 }

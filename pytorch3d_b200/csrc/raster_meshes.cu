@@ -168,8 +168,9 @@ struct Hit {
 // `full` / `max_z`: the pixel's queue already holds K hits, the farthest at depth max_z.  The reference
 // discards a further hit unless pz < q_max_z (rasterize_meshes.cu:226), so such a face is dropped right after
 // its depth is known -- before the three point-segment distances, the expensive part when blur_radius > 0.
+// `tie` is raised when the depth EQUALS the queue's farthest one (the outcome then depends on arrival order).
 __device__ __forceinline__ bool eval_pixel_face(float px, float py, const Face& f, float den, float blur_radius,
-                                                bool persp, bool clip, bool full, float max_z, Hit& h) {
+                                                bool persp, bool clip, bool full, float max_z, Hit& h, bool& tie) {
   float w0, w1, w2;
   bary_coords(px, py, f, den, w0, w1, w2);
   if (persp) bary_persp(w0, w1, w2, f.z0, f.z1, f.z2);
@@ -177,7 +178,10 @@ __device__ __forceinline__ bool eval_pixel_face(float px, float py, const Face& 
   if (clip) bary_clip(c0, c1, c2);
   const float pz = ffma(f.z2, c2, ffma(f.z0, c0, fmul(f.z1, c1)));
   if (!(pz >= 0.0f)) return false;  // behind the image plane (:163)
-  if (full && !(pz < max_z)) return false;
+  if (full && !(pz < max_z)) {
+    tie |= pz == max_z;  // (whether this face or the queued one survives depends on arrival order, see fine_tile_body)
+    return false;
+  }
   const bool inside = w0 > 0.0f && w1 > 0.0f && w2 > 0.0f;
   if (!inside && !(blur_radius > 0.0f)) return false;  // dist >= 0 >= blur_radius always rejects (:175)
   const float dist = point_tri_dist(px, py, f);
@@ -209,6 +213,7 @@ struct TopK {
   int size;
   float max_z;
   int max_idx;
+  bool tie;  // an exact depth tie at the queue's far end was seen: the content may depend on arrival order
 
   __device__ __forceinline__ void init() {
 #pragma unroll
@@ -219,6 +224,7 @@ struct TopK {
     size = 0;
     max_z = -1000.0f;  // (:292)
     max_idx = -1;
+    tie = false;
   }
   __device__ __forceinline__ void put(int slot, const Hit& h, int f, float4* pay) {
 #pragma unroll
@@ -239,6 +245,7 @@ struct TopK {
       }
       ++size;
     } else if (h.z < max_z) {
+      const float evicted = max_z;
       put(max_idx, h, f, pay);
       max_z = h.z;
 #pragma unroll
@@ -248,6 +255,9 @@ struct TopK {
           max_idx = i;
         }
       }
+      tie |= max_z == evicted;  // another entry shares the evicted depth: which of them left depends on the order
+    } else {
+      tie |= h.z == max_z;
     }
   }
   // Clipped-face neighbour handling (:186-215): if the other half of a clipped quad is already queued,
@@ -311,6 +321,8 @@ struct RegQueue {
   TopK<KMAX> q;
   float4* pay;  // this thread's payload column
   int K;
+  __device__ __forceinline__ void reset() { q.init(); }
+  __device__ __forceinline__ bool& tie() { return q.tie; }
   __device__ __forceinline__ bool full() const { return q.size >= K; }
   __device__ __forceinline__ float max_z() const { return q.max_z; }
   __device__ __forceinline__ void offer(const Hit& h, int f) { q.offer(h, f, K, pay); }
@@ -329,15 +341,21 @@ struct SmemQueue {
   float* qd;  // NB only
   int K, size, max_idx;
   float max_zv;
+  bool tie_;
   __device__ __forceinline__ void init(unsigned char* base, int K_, int tid) {
     K = K_;
     qz = reinterpret_cast<float*>(base) + tid;
     qi = reinterpret_cast<int*>(base) + K_ * TILE_THREADS + tid;
     qd = NB ? reinterpret_cast<float*>(base) + 2 * K_ * TILE_THREADS + tid : nullptr;
+    reset();
+  }
+  __device__ __forceinline__ void reset() {
     size = 0;
     max_idx = -1;
     max_zv = -1000.0f;  // (:292)
+    tie_ = false;
   }
+  __device__ __forceinline__ bool& tie() { return tie_; }
   __device__ __forceinline__ bool full() const { return size >= K; }
   __device__ __forceinline__ float max_z() const { return max_zv; }
   __device__ __forceinline__ void put(int slot, const Hit& h, int f) {
@@ -354,6 +372,7 @@ struct SmemQueue {
       }
       ++size;
     } else if (h.z < max_zv) {
+      const float evicted = max_zv;
       put(max_idx, h, f);
       max_zv = h.z;
       for (int i = 0; i < K; ++i) {
@@ -363,6 +382,9 @@ struct SmemQueue {
           max_idx = i;
         }
       }
+      tie_ |= max_zv == evicted;
+    } else {
+      tie_ |= h.z == max_zv;
     }
   }
   __device__ __forceinline__ bool offer_neighbor(const Hit& h, int f, int nb) {  // (:186-215)
@@ -602,14 +624,25 @@ __device__ __forceinline__ void consider_face(const FineStage& sh, int j, float 
   const int nb = NB ? __float_as_int(fc.w) : -1;
   Hit h;
   // (a face with a clipped-face neighbour may replace that neighbour whatever its depth: no early rejection)
-  if (!eval_pixel_face(px, py, f, fb.z, blur_radius, persp, clip, q.full() && nb == -1, q.max_z(), h)) return;
+  if (!eval_pixel_face(px, py, f, fb.z, blur_radius, persp, clip, q.full() && nb == -1, q.max_z(), h, q.tie())) return;
   const int fi = __float_as_int(fb.w);
   if (NB && nb != -1 && q.offer_neighbor(h, fi, nb)) return;
   q.offer(h, fi);
 }
 
-// The body shared by the fine kernels: sort the tile's list, stage it chunk by chunk, find every pixel's
-// candidates and offer the hits to the pixel's queue `q`.
+// The body shared by the fine kernels: stage the tile's list chunk by chunk, find every pixel's candidates and offer
+// the hits to the pixel's queue `q`.
+//
+// Order of the list.  The fill pass scatters with atomics, so a tile's list arrives in arbitrary order, while the
+// reference's naive kernel offers faces in ascending index order (rasterize_meshes.cu:301).  Its queue keeps the K
+// nearest hits whatever the order UNLESS two hits share, bit for bit, the depth at the queue's far end (a full queue
+// meets a hit with z == q_max_z, or evicts one of several entries at q_max_z); the final sort on (z, face) is
+// order-free.  So without a blur band -- where such ties are rare: none on the north-star batch -- the tile is first
+// walked in arrival order with the queues watching for exactly those events (`q.tie()`); only if some pixel saw one
+// is the list sorted and the tile walked again.  With a blur band (structured meshes tie often there: the two
+// triangles of a quad extrapolate to the same depth) and with clipped-face neighbours (whose replace-in-queue rule
+// depends on the order by itself) the list is sorted up front.  Either way the result is the one the sorted walk
+// gives; sorting every list cost 30 % of the kernel's instructions.
 template <class Q, bool NB, bool SCAN>
 __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& sh, Q& q, int tile_x, int tile_y,
                                                int seg_begin, int count, bool overflow, int64_t mesh_first,
@@ -617,9 +650,14 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
   const int tid = threadIdx.x, lane = tid & 31;
   const bool persp = p.persp != 0, clip = p.clip != 0;
   const float blur_radius = p.blur_radius;
-  const bool sort_staged = !overflow && count <= CHUNK;  // (an overflowed tile walks the mesh's faces in order)
-  // (the long-list sort may use all of the kernel's shared memory: nothing lives there yet)
-  if (!overflow && count > CHUNK) cta_sort_segment(p.pairs + seg_begin, count, reinterpret_cast<int*>(&sh), p.smem_ints);
+  constexpr bool OPTIMISTIC = SCAN && !NB;
+ for (int pass = 0;; ++pass) {
+  // (an overflowed tile walks the mesh's own faces: already in order)
+  const bool sorted_walk = overflow || !OPTIMISTIC || pass == 1;
+  const bool sort_staged = sorted_walk && !overflow && count <= CHUNK;
+  // (the long-list sort may use all of the kernel's shared memory: nothing lives there yet / any more)
+  if (sorted_walk && !overflow && count > CHUNK)
+    cta_sort_segment(p.pairs + seg_begin, count, reinterpret_cast<int*>(&sh), p.smem_ints);
   // NDC coordinates of the tile's 16 pixel columns and rows (two IEEE divisions each): computed once per tile
   // by 32 threads, read by every thread after the barriers of the first chunk
   if (tid < 2 * TILE) {
@@ -746,6 +784,10 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
       }
     }
   }
+  if (sorted_walk) break;
+  if (!__syncthreads_or((int)q.tie())) break;  // no depth tie anywhere in the tile: the arrival-order walk stands
+  q.reset();
+ }
 }
 
 // Which tile, which faces: grid = (tiles per row, tile rows, images) -- no integer divisions.
@@ -880,7 +922,8 @@ __device__ __forceinline__ void recompute_hit(const FineParams& p, int fi, float
   const float4* r = p.rec + (int64_t)fi * 4;
   const float4 fa = __ldg(r + 0), fb = __ldg(r + 1), fc = __ldg(r + 2);
   const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
-  eval_pixel_face(px, py, f, fb.z, p.blur_radius, p.persp != 0, p.clip != 0, false, 0.0f, h);
+  bool unused = false;
+  eval_pixel_face(px, py, f, fb.z, p.blur_radius, p.persp != 0, p.clip != 0, false, 0.0f, h, unused);
 }
 
 template <bool NB, bool SCAN>
@@ -1029,7 +1072,9 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const Fine
         const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
         Hit h;
         const int nb = __float_as_int(fc.w);
-        if (!eval_pixel_face(px, py, f, fb.z, p.blur_radius, persp, clip, qn >= K && nb == -1, q_max_z, h)) continue;
+        bool unused = false;  // (this kernel always walks sorted lists)
+        if (!eval_pixel_face(px, py, f, fb.z, p.blur_radius, persp, clip, qn >= K && nb == -1, q_max_z, h, unused))
+          continue;
         const int fi = __float_as_int(fb.w);
         int at = -1;
         if (nb != -1)
@@ -1093,7 +1138,8 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const Fine
       const float* v = p.face_verts + (int64_t)qi[k] * 9;
       const Face f = {__ldg(v + 0), __ldg(v + 1), __ldg(v + 2), __ldg(v + 3), __ldg(v + 4),
                       __ldg(v + 5), __ldg(v + 6), __ldg(v + 7), __ldg(v + 8)};
-      eval_pixel_face(px, py, f, bary_denominator(f), p.blur_radius, persp, clip, false, 0.0f, h);
+      bool unused = false;
+      eval_pixel_face(px, py, f, bary_denominator(f), p.blur_radius, persp, clip, false, 0.0f, h, unused);
       id = qi[k];
     }
     p.pix_to_face[o + k] = id;
@@ -1399,7 +1445,7 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
   tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles);
   B200R_LAUNCHED("tile_scan_kernel");
   if (F > 0) {
-    tile_fill_kernel<<<(unsigned)((F + 255) / 256), 256, 0, stream>>>(ws.rect, F, TY, TX, ws.tile_count, ws.pairs,
+    tile_fill_kernel<true><<<(unsigned)((F + 255) / 256), 256, 0, stream>>>(ws.rect, F, TY, TX, ws.tile_count, ws.pairs,
                                                                     ws.capacity);
     B200R_LAUNCHED("tile_fill_kernel");
   }

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(SETUP_POINTS)
     rect[pi] = make_uint4(rc.x, rc.y, (uint32_t)max(n, 0), 0u);
     prec[pi] = make_float4(x, y, z, r);
   }
-  warp_count_rect(rc, n, TY, TX, tile_count, tid & 31);  // all lanes participate
+  warp_count_rect<false>(rc, n, TY, TX, tile_count, tid & 31);
 }
 
 // One staged chunk of points.
@@ -112,16 +112,20 @@ __device__ __forceinline__ int thread_of_pixel(int r, int c) {
 // The tile body shared by the point kernels: sort the tile's list, stage it chunk by chunk, box-test (pass A: one
 // lane per point against the warp's footprint + bit-matrix transpose, see raster_meshes.cu) and offer every hit
 // to `offer(z, point, dist2)` in ascending point order.
+// `sort_list`: put the tile's list in ascending point order first (the order of the reference's naive kernel,
+// rasterize_points.cu:128); without it the points are offered in arrival order (see points_fine_smem_kernel).
+// Returns true if the walk was in ascending order (sorted, or an overflowed tile walking the cloud itself).
 template <class Offer>
-__device__ __forceinline__ void points_tile_body(const PointFineParams& p, PointStage& s, int* smem_ints_base,
-                                                 int tile, int n, bool valid, float px, float py, Offer offer) {
+__device__ __forceinline__ bool points_tile_body(const PointFineParams& p, PointStage& s, int* smem_ints_base,
+                                                 int tile, int n, bool valid, float px, float py, bool sort_list,
+                                                 Offer offer) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int seg_begin = p.tile_offset[tile], seg_end = p.tile_offset[tile + 1];
   const bool overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
   const int64_t cloud_first = p.first[n];
   const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
-  const bool sort_staged = !overflow && count <= PCHUNK;
-  if (!overflow && count > PCHUNK) cta_sort_segment(p.pairs + seg_begin, count, smem_ints_base, p.smem_ints);
+  const bool sort_staged = sort_list && !overflow && count <= PCHUNK;
+  if (sort_list && !overflow && count > PCHUNK) cta_sort_segment(p.pairs + seg_begin, count, smem_ints_base, p.smem_ints);
 
   for (int base = 0; base < count; base += PCHUNK) {
     const int nc = min(PCHUNK, count - base);
@@ -163,6 +167,7 @@ __device__ __forceinline__ void points_tile_body(const PointFineParams& p, Point
       }
     }
   }
+  return sort_list || overflow || count <= 1;
 }
 
 // K <= 32: the reference's queue (rasterize_points.cu:61-79) -- an UNSORTED array of K slots plus the tracked
@@ -191,47 +196,65 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_smem_kernel(const Po
   const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
   const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
 
-  int size = 0, max_idx = -1;
-  float max_z = -1000.0f;
-  points_tile_body(p, s, reinterpret_cast<int*>(smem_raw), tile, n, valid, px, py,
-                   [&](float pz, int pi, float d2) {
-                     if (size < K) {  // (:61-67)
-                       qz[size * QSTRIDE] = pz;
-                       qi[size * QSTRIDE] = pi;
-                       qd[size * QSTRIDE] = d2;
-                       if (pz > max_z) {
-                         max_z = pz;
-                         max_idx = size;
-                       }
-                       ++size;
-                     } else if (pz < max_z) {  // (:68-78)
-                       qz[max_idx * QSTRIDE] = pz;
-                       qi[max_idx * QSTRIDE] = pi;
-                       qd[max_idx * QSTRIDE] = d2;
-                       max_z = pz;
-                       for (int i = 0; i < K; ++i) {
-                         const float v = qz[i * QSTRIDE];
-                         if (v > max_z) {
-                           max_z = v;
-                           max_idx = i;
-                         }
-                       }
-                     }
-                   });
-  // BubbleSort on z only (rasterize_points.cu:26-28): stable -> insertion sort over the thread's own column
-  for (int i = 1; i < size; ++i) {
-    const float tz = qz[i * QSTRIDE], td = qd[i * QSTRIDE];
-    const int ti = qi[i * QSTRIDE];
-    int j = i - 1;
-    while (j >= 0 && tz < qz[j * QSTRIDE]) {
-      qz[(j + 1) * QSTRIDE] = qz[j * QSTRIDE];
-      qi[(j + 1) * QSTRIDE] = qi[j * QSTRIDE];
-      qd[(j + 1) * QSTRIDE] = qd[j * QSTRIDE];
-      --j;
+  // Order of the list: the queue keeps the K nearest points whatever the arrival order unless two points share,
+  // bit for bit, the depth at the queue's far end, and the final stable sort on z orders them the same way unless two
+  // kept points share a depth.  Point depths rarely tie, so the tile is first walked in arrival order while
+  // watching for exactly those events; only if some pixel saw one is the list sorted (ascending point index, the
+  // order of the reference's naive kernel) and the tile walked again.
+  int size, max_idx;
+  float max_z;
+  for (int pass = 0;; ++pass) {
+    size = 0;
+    max_idx = -1;
+    max_z = -1000.0f;
+    bool tie = false;
+    const bool in_order = points_tile_body(
+        p, s, reinterpret_cast<int*>(smem_raw), tile, n, valid, px, py, pass == 1, [&](float pz, int pi, float d2) {
+          if (size < K) {  // (:61-67)
+            qz[size * QSTRIDE] = pz;
+            qi[size * QSTRIDE] = pi;
+            qd[size * QSTRIDE] = d2;
+            if (pz > max_z) {
+              max_z = pz;
+              max_idx = size;
+            }
+            ++size;
+          } else if (pz < max_z) {  // (:68-78)
+            const float evicted = max_z;
+            qz[max_idx * QSTRIDE] = pz;
+            qi[max_idx * QSTRIDE] = pi;
+            qd[max_idx * QSTRIDE] = d2;
+            max_z = pz;
+            for (int i = 0; i < K; ++i) {
+              const float v = qz[i * QSTRIDE];
+              if (v > max_z) {
+                max_z = v;
+                max_idx = i;
+              }
+            }
+            tie |= max_z == evicted;
+          } else {
+            tie |= pz == max_z;
+          }
+        });
+    // BubbleSort on z only (rasterize_points.cu:26-28): stable -> insertion sort over the thread's own column
+    for (int i = 1; i < size; ++i) {
+      const float tz = qz[i * QSTRIDE], td = qd[i * QSTRIDE];
+      const int ti = qi[i * QSTRIDE];
+      int j = i - 1;
+      while (j >= 0 && tz < qz[j * QSTRIDE]) {
+        qz[(j + 1) * QSTRIDE] = qz[j * QSTRIDE];
+        qi[(j + 1) * QSTRIDE] = qi[j * QSTRIDE];
+        qd[(j + 1) * QSTRIDE] = qd[j * QSTRIDE];
+        --j;
+      }
+      tie |= j >= 0 && tz == qz[j * QSTRIDE];  // equal depths keep their arrival order
+      qz[(j + 1) * QSTRIDE] = tz;
+      qi[(j + 1) * QSTRIDE] = ti;
+      qd[(j + 1) * QSTRIDE] = td;
     }
-    qz[(j + 1) * QSTRIDE] = tz;
-    qi[(j + 1) * QSTRIDE] = ti;
-    qd[(j + 1) * QSTRIDE] = td;
+    if (in_order) break;                        // (CTA-uniform)
+    if (!__syncthreads_or((int)tie)) break;     // no depth tie anywhere in the tile: the arrival-order walk stands
   }
   if (!p.vec_ok) {
     if (!valid) return;
@@ -292,7 +315,7 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_bigk_kernel(const Po
   int li[B200R_MAX_K];
   int ln = 0, l_max_idx = -1;
   float l_max_z = -1000.0f;
-  points_tile_body(p, s, reinterpret_cast<int*>(&s), tile, n, valid, px, py, [&](float pz, int pi, float d2) {
+  points_tile_body(p, s, reinterpret_cast<int*>(&s), tile, n, valid, px, py, true, [&](float pz, int pi, float d2) {
     if (ln < K) {
       lz[ln] = pz;
       li[ln] = pi;
@@ -469,7 +492,7 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
   tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles);
   B200R_LAUNCHED("tile_scan_kernel");
   if (P > 0) {
-    tile_fill_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(ws.rect, P, TY, TX, ws.tile_count, ws.pairs,
+    tile_fill_kernel<false><<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(ws.rect, P, TY, TX, ws.tile_count, ws.pairs,
                                                                     ws.capacity);
     B200R_LAUNCHED("tile_fill_kernel");
   }

@@ -88,14 +88,11 @@ class MeshRasterizer(nn.Module):
         """World -> view -> NDC with the view-space z kept as depth (rasterizer.py:171-217)."""
         cameras = kwargs.get("cameras", self.cameras)
         if cameras is None:
-            return meshes_world  # already NDC
+            raise ValueError("Cameras must be specified either at initialization or in the forward pass of "
+                             "MeshRasterizer")  # (rasterizer.py:183-186 of the reference)
         n_cameras = len(cameras)
         if n_cameras != 1 and n_cameras != len(meshes_world):
             raise ValueError("Wrong number (%r) of cameras for %r meshes" % (n_cameras, len(meshes_world)))
-        if not hasattr(meshes_world, "update_padded"):
-            raise ValueError(
-                "MeshRasterizer with cameras needs a batch with verts_padded() / update_padded() (a PyTorch3D Meshes "
-                "object); packed containers are only accepted with cameras=None, i.e. already in NDC")
         verts_ndc = _world_to_ndc(cameras, meshes_world.verts_padded(), kwargs)
         return meshes_world.update_padded(new_verts_padded=verts_ndc)
 
@@ -109,13 +106,14 @@ class MeshRasterizer(nn.Module):
         if rs.perspective_correct is not None:
             perspective_correct = rs.perspective_correct
         else:
-            perspective_correct = cameras.is_perspective() if cameras is not None else False
-        z_clip = rs.z_clip_value
-        if z_clip is None and cameras is not None and perspective_correct:
+            perspective_correct = cameras.is_perspective()
+        if rs.z_clip_value is not None:
+            z_clip = rs.z_clip_value
+        else:  # (rasterizer.py:240-246 of the reference)
             znear = cameras.get_znear()
             if isinstance(znear, torch.Tensor):
                 znear = znear.min().item()
-            z_clip = None if znear is None else znear / 2
+            z_clip = None if not perspective_correct or znear is None else znear / 2
         pix_to_face, zbuf, bary_coords, dists = rasterize_meshes(
             meshes_proj,
             image_size=rs.image_size,
@@ -171,7 +169,8 @@ class PointsRasterizer(nn.Module):
     def transform(self, point_clouds, **kwargs):
         cameras = kwargs.get("cameras", self.cameras)
         if cameras is None:
-            return point_clouds
+            raise ValueError("Cameras must be specified either at initialization or in the forward pass of "
+                             "PointsRasterizer")  # (points/rasterizer.py:115-118 of the reference)
         return point_clouds.update_padded(_world_to_ndc(cameras, point_clouds.points_padded(), kwargs))
 
     def forward(self, point_clouds, **kwargs) -> PointFragments:

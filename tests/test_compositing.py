@@ -1,4 +1,5 @@
-"""Alpha compositing: oracle pinned to the reference CPU op; CUDA path against oracle/reference."""
+"""Compositing of point features (alpha, weighted sum, normalised weighted sum): oracle pinned to the
+reference CPU ops; CUDA path against oracle / reference."""
 import numpy as np
 import pytest
 import torch
@@ -105,3 +106,68 @@ def test_points_renderer_pipeline(built_lib):
     got = img.cpu().numpy()
     assert np.array_equal(got.transpose(0, 2, 3, 1)[covered][:, :4], want.transpose(0, 2, 3, 1)[covered])
     assert (got.transpose(0, 2, 3, 1)[~covered][:, :3] == 0).all()
+
+
+# ------------------------------------------------------------------------------------ weighted sums
+
+@pytest.mark.parametrize("norm", [False, True])
+@pytest.mark.parametrize("N,K,H,W,C,P", [(2, 5, 9, 11, 3, 40), (1, 1, 4, 4, 1, 5), (1, 10, 16, 8, 4, 100)])
+def test_weighted_sum_oracle_equals_reference_cpu(ref_cpu, norm, N, K, H, W, C, P):
+    if not hasattr(ref_cpu, "accum_weightedsum"):
+        pytest.skip("reference CPU build without the weighted-sum ops")
+    feats, alphas, idx = scene(N, K, H, W, C, P, seed=K + 7)
+    if norm:
+        alphas[:, :, 0, 0] = 1e-6  # total below the 1e-4 floor
+    fwd = ref_cpu.accum_weightedsumnorm if norm else ref_cpu.accum_weightedsum
+    bwd = ref_cpu.accum_weightedsumnorm_backward if norm else ref_cpu.accum_weightedsum_backward
+    want = fwd(feats, alphas, idx)
+    got = oracle.weighted_sum(feats.numpy(), alphas.numpy(), idx.numpy(), norm=norm)
+    assert np.array_equal(got, want.numpy())
+    go = torch.rand(want.shape, generator=torch.Generator().manual_seed(1))
+    rf, ra = bwd(go, feats, alphas, idx)
+    of, oa = oracle.weighted_sum_backward(go.numpy(), feats.numpy(), alphas.numpy(), idx.numpy(), norm=norm)
+    assert np.array_equal(of, rf.numpy()) and np.array_equal(oa, ra.numpy())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("norm", [False, True])
+@pytest.mark.parametrize("N,K,H,W,C,P,permuted", [(2, 5, 9, 11, 3, 40, False), (2, 10, 33, 17, 4, 500, True),
+                                                  (1, 1, 4, 4, 1, 5, False), (3, 8, 20, 20, 8, 300, True)])
+def test_weighted_sum_cuda_forward_backward(built_lib, norm, N, K, H, W, C, P, permuted):
+    from pytorch3d_b200 import _C, compositing
+    dev = torch.device("cuda:0")
+    feats, alphas, idx = scene(N, K, H, W, C, P, seed=N + K + 3)
+    if norm:
+        alphas[:, :, 0, 0] = 1e-6
+    fd = feats.to(dev)
+    if permuted:
+        ad = alphas.permute(0, 2, 3, 1).contiguous().to(dev).permute(0, 3, 1, 2)
+        idd = idx.permute(0, 2, 3, 1).contiguous().to(dev).permute(0, 3, 1, 2)
+    else:
+        ad, idd = alphas.to(dev), idx.to(dev)
+    fwd = _C.accum_weightedsumnorm if norm else _C.accum_weightedsum
+    bwd = _C.accum_weightedsumnorm_backward if norm else _C.accum_weightedsum_backward
+    out = fwd(fd, ad, idd)
+    want = oracle.weighted_sum(feats.numpy(), alphas.numpy(), idx.numpy(), norm=norm)
+    assert np.array_equal(out.cpu().numpy(), want), "forward must be bit-identical to the oracle"
+    ref = oracle.load_reference(cuda=True)
+    if ref is not None and hasattr(ref, "accum_weightedsum"):
+        rfwd = ref.accum_weightedsumnorm if norm else ref.accum_weightedsum
+        assert torch.equal(out, rfwd(fd, alphas.to(dev), idx.to(dev))), "forward must equal the reference CUDA kernel"
+    go = torch.rand(out.shape, generator=torch.Generator().manual_seed(1))
+    gf, ga = bwd(go.to(dev), fd, ad, idd)
+    of, oa = oracle.weighted_sum_backward(go.numpy(), feats.numpy(), alphas.numpy(), idx.numpy(), norm=norm)
+    np.testing.assert_allclose(gf.cpu().numpy(), of, rtol=1e-4, atol=1e-4 * np.abs(of).max())
+    np.testing.assert_allclose(ga.cpu().numpy(), oa, rtol=2e-4, atol=2e-4 * np.abs(oa).max())
+    # autograd wrappers + compositor module
+    fa = fd.clone().requires_grad_(True)
+    aa = ad.clone().requires_grad_(True)
+    img = (compositing.norm_weighted_sum if norm else compositing.weighted_sum)(idd, aa, fa)
+    (img * go.to(dev)).sum().backward()
+    np.testing.assert_allclose(fa.grad.cpu().numpy(), of, rtol=1e-4, atol=1e-4 * np.abs(of).max())
+    np.testing.assert_allclose(aa.grad.cpu().numpy(), oa, rtol=2e-4, atol=2e-4 * np.abs(oa).max())
+    if norm:
+        img2 = compositing.NormWeightedCompositor(background_color=(0.5,) * C)(idd, ad, fd)
+        bg = (idx[:, 0] < 0).to(dev)
+        assert torch.equal(img2.permute(0, 2, 3, 1)[~bg], out.permute(0, 2, 3, 1)[~bg])
+        assert (img2.permute(0, 2, 3, 1)[bg] == 0.5).all()

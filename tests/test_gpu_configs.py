@@ -113,8 +113,10 @@ def test_config5_stress_full_size(ops, dev, ref_cuda):
     both = valid[..., :-1] & valid[..., 1:]
     assert (zbuf[..., :-1][both] <= zbuf[..., 1:][both]).all()
     assert (dists[valid] < 1e-3).all()
-    zi = (bary * fv[p2f.clamp_min(0)][..., 2]).sum(-1)
-    assert (zi - zbuf)[valid].abs().max() < 1e-3  # (barycentrics extrapolate up to ~50 in the blur band)
+    # z is the barycentric interpolation of the vertex depths (the barycentrics of sliver faces extrapolate to ~1e4
+    # in the blur band: bound the error relative to the magnitudes that were summed)
+    terms = bary * fv[p2f.clamp_min(0)][..., 2]
+    assert ((terms.sum(-1) - zbuf).abs() <= 1e-5 + 2e-6 * terms.abs().sum(-1))[valid].all()
     gz, gb, gd = torch.randn_like(zbuf), torch.randn_like(bary), torch.randn_like(dists)
     g1 = ops.rasterize_meshes_backward(fv, p2f, gz, gb, gd, False, False)
     assert torch.isfinite(g1).all()

@@ -1,5 +1,5 @@
-"""install() rebinds `_C` inside PyTorch3D's two wrapper modules; checked here against stand-in modules
-(PyTorch3D itself is not installed on the test machines)."""
+"""install() rebinds `_C` inside PyTorch3D's wrapper modules (rasterizers, compositing, interp_face_attrs); checked
+here against stand-in modules (tests/test_gpu_modules.py runs it against the real package on the GPU box)."""
 import sys
 import types
 
@@ -16,13 +16,16 @@ def _fake_pytorch3d(monkeypatch):
         knn_points_idx=lambda *a, **k: "untouched",
     )
     names = ["pytorch3d", "pytorch3d.renderer", "pytorch3d.renderer.mesh", "pytorch3d.renderer.mesh.rasterize_meshes",
-             "pytorch3d.renderer.points", "pytorch3d.renderer.points.rasterize_points"]
+             "pytorch3d.renderer.points", "pytorch3d.renderer.points.rasterize_points",
+             "pytorch3d.renderer.compositing", "pytorch3d.ops", "pytorch3d.ops.interp_face_attrs"]
     for n in names:
         m = types.ModuleType(n)
         m.__path__ = []
         monkeypatch.setitem(sys.modules, n, m)
     sys.modules["pytorch3d.renderer.mesh.rasterize_meshes"]._C = orig
     sys.modules["pytorch3d.renderer.points.rasterize_points"]._C = orig
+    sys.modules["pytorch3d.renderer.compositing"]._C = orig
+    sys.modules["pytorch3d.ops.interp_face_attrs"]._C = orig
     return orig, calls
 
 
@@ -30,7 +33,7 @@ def test_install_and_uninstall(monkeypatch, built_lib):
     from pytorch3d_b200 import install as inst
     orig, calls = _fake_pytorch3d(monkeypatch)
     patched = inst.install()
-    assert len(patched) == 2
+    assert len(patched) == 4
     rm = sys.modules["pytorch3d.renderer.mesh.rasterize_meshes"]
     assert rm._C is not orig
     # CPU tensors keep the reference's CPU implementation; unrelated ops pass through untouched
