@@ -165,12 +165,18 @@ struct Hit {
   float z, dist, b0, b1, b2;
 };
 
+// An exact depth tie at the far end of some pixel's queue was seen: the tile's result may depend on the order in which
+// the faces arrive (see fine_tile_body).  One flag per CTA at a fixed place in the fine kernels' dynamic shared memory
+// (FineStage::tie), written on the (rare) event itself: watching costs no register.
+__device__ __forceinline__ void flag_tie();
+
 // `full` / `max_z`: the pixel's queue already holds K hits, the farthest at depth max_z.  The reference
 // discards a further hit unless pz < q_max_z (rasterize_meshes.cu:226), so such a face is dropped right after
 // its depth is known -- before the three point-segment distances, the expensive part when blur_radius > 0.
-// `tie` is raised when the depth EQUALS the queue's farthest one (the outcome then depends on arrival order).
+// WATCH: flag the tile when the depth EQUALS the queue's farthest one (the outcome then depends on arrival order).
+template <bool WATCH>
 __device__ __forceinline__ bool eval_pixel_face(float px, float py, const Face& f, float den, float blur_radius,
-                                                bool persp, bool clip, bool full, float max_z, Hit& h, bool& tie) {
+                                                bool persp, bool clip, bool full, float max_z, Hit& h) {
   float w0, w1, w2;
   bary_coords(px, py, f, den, w0, w1, w2);
   if (persp) bary_persp(w0, w1, w2, f.z0, f.z1, f.z2);
@@ -179,7 +185,7 @@ __device__ __forceinline__ bool eval_pixel_face(float px, float py, const Face& 
   const float pz = ffma(f.z2, c2, ffma(f.z0, c0, fmul(f.z1, c1)));
   if (!(pz >= 0.0f)) return false;  // behind the image plane (:163)
   if (full && !(pz < max_z)) {
-    tie |= pz == max_z;  // (whether this face or the queued one survives depends on arrival order, see fine_tile_body)
+    if (WATCH && pz == max_z) flag_tie();
     return false;
   }
   const bool inside = w0 > 0.0f && w1 > 0.0f && w2 > 0.0f;
@@ -213,7 +219,6 @@ struct TopK {
   int size;
   float max_z;
   int max_idx;
-  bool tie;  // an exact depth tie at the queue's far end was seen: the content may depend on arrival order
 
   __device__ __forceinline__ void init() {
 #pragma unroll
@@ -224,7 +229,6 @@ struct TopK {
     size = 0;
     max_z = -1000.0f;  // (:292)
     max_idx = -1;
-    tie = false;
   }
   __device__ __forceinline__ void put(int slot, const Hit& h, int f, float4* pay) {
 #pragma unroll
@@ -255,9 +259,9 @@ struct TopK {
           max_idx = i;
         }
       }
-      tie |= max_z == evicted;  // another entry shares the evicted depth: which of them left depends on the order
-    } else {
-      tie |= h.z == max_z;
+      if (max_z == evicted) flag_tie();  // another entry shares the evicted depth: which one left depends on the order
+    } else if (h.z == max_z) {
+      flag_tie();
     }
   }
   // Clipped-face neighbour handling (:186-215): if the other half of a clipped quad is already queued,
@@ -322,7 +326,6 @@ struct RegQueue {
   float4* pay;  // this thread's payload column
   int K;
   __device__ __forceinline__ void reset() { q.init(); }
-  __device__ __forceinline__ bool& tie() { return q.tie; }
   __device__ __forceinline__ bool full() const { return q.size >= K; }
   __device__ __forceinline__ float max_z() const { return q.max_z; }
   __device__ __forceinline__ void offer(const Hit& h, int f) { q.offer(h, f, K, pay); }
@@ -341,7 +344,6 @@ struct SmemQueue {
   float* qd;  // NB only
   int K, size, max_idx;
   float max_zv;
-  bool tie_;
   __device__ __forceinline__ void init(unsigned char* base, int K_, int tid) {
     K = K_;
     qz = reinterpret_cast<float*>(base) + tid;
@@ -353,9 +355,7 @@ struct SmemQueue {
     size = 0;
     max_idx = -1;
     max_zv = -1000.0f;  // (:292)
-    tie_ = false;
   }
-  __device__ __forceinline__ bool& tie() { return tie_; }
   __device__ __forceinline__ bool full() const { return size >= K; }
   __device__ __forceinline__ float max_z() const { return max_zv; }
   __device__ __forceinline__ void put(int slot, const Hit& h, int f) {
@@ -382,9 +382,9 @@ struct SmemQueue {
           max_idx = i;
         }
       }
-      tie_ |= max_zv == evicted;
-    } else {
-      tie_ |= h.z == max_zv;
+      if (max_zv == evicted) flag_tie();
+    } else if (h.z == max_zv) {
+      flag_tie();
     }
   }
   __device__ __forceinline__ bool offer_neighbor(const Hit& h, int f, int nb) {  // (:186-215)
@@ -512,7 +512,13 @@ struct FineStage {
   } u;
   unsigned rng[CHUNK];                          // blur = 0: tile-local pixel rectangle c_lo | c_hi<<8 | r_lo<<16 | r_hi<<24
   float col[TILE], row[TILE];                   // NDC coordinates of the tile's 16 pixel columns / rows
+  int tie;                                      // see flag_tie()
 };
+
+__device__ __forceinline__ void flag_tie() {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  reinterpret_cast<FineStage*>(smem_raw)->tie = 1;
+}
 
 // Full-sector output stores.  A pixel's K values of one buffer are P 16-byte pieces; the pixels of two adjacent
 // lanes (x, x+1 of the same row) are adjacent in memory, a run of 2P pieces.  Written lane-by-lane, every store
@@ -624,7 +630,7 @@ __device__ __forceinline__ void consider_face(const FineStage& sh, int j, float 
   const int nb = NB ? __float_as_int(fc.w) : -1;
   Hit h;
   // (a face with a clipped-face neighbour may replace that neighbour whatever its depth: no early rejection)
-  if (!eval_pixel_face(px, py, f, fb.z, blur_radius, persp, clip, q.full() && nb == -1, q.max_z(), h, q.tie())) return;
+  if (!eval_pixel_face<true>(px, py, f, fb.z, blur_radius, persp, clip, q.full() && nb == -1, q.max_z(), h)) return;
   const int fi = __float_as_int(fb.w);
   if (NB && nb != -1 && q.offer_neighbor(h, fi, nb)) return;
   q.offer(h, fi);
@@ -638,22 +644,19 @@ __device__ __forceinline__ void consider_face(const FineStage& sh, int j, float 
 // nearest hits whatever the order UNLESS two hits share, bit for bit, the depth at the queue's far end (a full queue
 // meets a hit with z == q_max_z, or evicts one of several entries at q_max_z); the final sort on (z, face) is
 // order-free.  So without a blur band -- where such ties are rare: none on the north-star batch -- the tile is first
-// walked in arrival order with the queues watching for exactly those events (`q.tie()`); only if some pixel saw one
-// is the list sorted and the tile walked again.  With a blur band (structured meshes tie often there: the two
+// walked in arrival order with the queues watching for exactly those events (flag_tie()); only if some pixel saw one
+// is the list sorted and the tile walked -- and written -- again (the kernels loop: walk, epilogue, tile_saw_tie()).  With a blur band (structured meshes tie often there: the two
 // triangles of a quad extrapolate to the same depth) and with clipped-face neighbours (whose replace-in-queue rule
 // depends on the order by itself) the list is sorted up front.  Either way the result is the one the sorted walk
 // gives; sorting every list cost 30 % of the kernel's instructions.
 template <class Q, bool NB, bool SCAN>
-__device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& sh, Q& q, int tile_x, int tile_y,
-                                               int seg_begin, int count, bool overflow, int64_t mesh_first,
-                                               bool valid, int lc, int lr) {
+__device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& sh, Q& q, int tile_x, int tile_y, int n,
+                                               int seg_begin, int count, bool overflow, bool sorted_walk, bool valid,
+                                               int lc, int lr) {
   const int tid = threadIdx.x, lane = tid & 31;
   const bool persp = p.persp != 0, clip = p.clip != 0;
   const float blur_radius = p.blur_radius;
-  constexpr bool OPTIMISTIC = SCAN && !NB;
- for (int pass = 0;; ++pass) {
   // (an overflowed tile walks the mesh's own faces: already in order)
-  const bool sorted_walk = overflow || !OPTIMISTIC || pass == 1;
   const bool sort_staged = sorted_walk && !overflow && count <= CHUNK;
   // (the long-list sort may use all of the kernel's shared memory: nothing lives there yet / any more)
   if (sorted_walk && !overflow && count > CHUNK)
@@ -667,13 +670,14 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
     else
       sh.row[i] = pix_to_ndc(p.H - 1 - (tile_y * TILE + i), p.H, p.ry);
   }
+  if (tid == 2 * TILE && !sorted_walk) sh.tie = 0;
 
   for (int base = 0; base < count; base += CHUNK) {
     const int nc = min(CHUNK, count - base);
     const int nwords = (nc + 31) >> 5;
     if (base > 0) __syncthreads();  // previous chunk fully consumed
     int f = INT_MAX;
-    if (tid < nc) f = overflow ? (int)(mesh_first + base + tid) : p.pairs[seg_begin + base + tid];
+    if (tid < nc) f = overflow ? (int)(p.first[n] + base + tid) : p.pairs[seg_begin + base + tid];
     if (sort_staged) {
       f = cta_sort256(f, nc, sh.u.sort_buf);
       if (nc > 32) __syncthreads();  // the exchange buffers alias the masks / boxes written next
@@ -784,11 +788,12 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
       }
     }
   }
-  if (sorted_walk) break;
-  if (!__syncthreads_or((int)q.tie())) break;  // no depth tie anywhere in the tile: the arrival-order walk stands
-  q.reset();
- }
 }
+
+// After the epilogue of an arrival-order walk: did any pixel of the tile see a depth tie?  CTA-uniform: every thread
+// contributes its own view of the flag (the thread that raised it sees it) and nobody reads it after the barrier, which
+// also orders every warp's epilogue reads of the queue payload before the sorted walk reuses shared memory.
+__device__ __forceinline__ bool tile_saw_tie(const FineStage& sh) { return __syncthreads_or(sh.tie) != 0; }
 
 // Which tile, which faces: grid = (tiles per row, tile rows, images) -- no integer divisions.
 struct TileWork {
@@ -829,12 +834,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
   rq.q.init();
   rq.pay = reinterpret_cast<float4*>(smem_raw + sizeof(FineStage)) + tid;
   rq.K = p.K;
-  fine_tile_body<RegQueue<KMAX>, NB, SCAN>(p, sh, rq, tile_x, tile_y, t.seg_begin, t.count, t.overflow, p.first[n],
-                                           valid, lc, lr);
   TopK<KMAX>& q = rq.q;
   float4* pay = rq.pay;
   const int K = p.K;
-
+  // (see fine_tile_body: arrival-order walk first where ties are rare, sorted walk only if one was seen)
+  bool sorted_walk = t.overflow || !(SCAN && !NB);
+  for (;;) {
+  fine_tile_body<RegQueue<KMAX>, NB, SCAN>(p, sh, rq, tile_x, tile_y, n, t.seg_begin, t.count, t.overflow, sorted_walk,
+                                           valid, lc, lr);
+  bool stored = false;
   int slot[KMAX];
   q.sort(slot);
   // ---- epilogue: every output is written with 16-byte stores (all K slots, including the -1 padding)
@@ -891,11 +899,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
       }
       store_pair_run<3 * KMAX / 4>(reinterpret_cast<float4*>(p.bary + oa * 3), piece, odd, vA, vB);
     }
-    return;
+    stored = true;
    }
   }
-  if (!valid) return;
-  {
+  if (!stored && valid) {
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       if (k < K) {
@@ -910,6 +917,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
       }
     }
   }
+  if (sorted_walk || !tile_saw_tie(sh)) return;
+  sorted_walk = true;
+  rq.reset();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -922,8 +933,7 @@ __device__ __forceinline__ void recompute_hit(const FineParams& p, int fi, float
   const float4* r = p.rec + (int64_t)fi * 4;
   const float4 fa = __ldg(r + 0), fb = __ldg(r + 1), fc = __ldg(r + 2);
   const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
-  bool unused = false;
-  eval_pixel_face(px, py, f, fb.z, p.blur_radius, p.persp != 0, p.clip != 0, false, 0.0f, h, unused);
+  eval_pixel_face<false>(px, py, f, fb.z, p.blur_radius, p.persp != 0, p.clip != 0, false, 0.0f, h);
 }
 
 template <bool NB, bool SCAN>
@@ -945,7 +955,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) mesh_fine_smemq_kernel(const 
 
   SmemQueue<NB> q;
   q.init(smem_raw + sizeof(FineStage), K, tid);
-  fine_tile_body<SmemQueue<NB>, NB, SCAN>(p, sh, q, tile_x, tile_y, t.seg_begin, t.count, t.overflow, p.first[n],
+  bool sorted_walk = t.overflow || !(SCAN && !NB);
+  for (;;) {
+  fine_tile_body<SmemQueue<NB>, NB, SCAN>(p, sh, q, tile_x, tile_y, n, t.seg_begin, t.count, t.overflow, sorted_walk,
                                           valid, lc, lr);
   q.sort();
   const float px = sh.col[lc], py = sh.row[lr];
@@ -995,9 +1007,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) mesh_fine_smemq_kernel(const 
       store_pair_split<6>(reinterpret_cast<float4*>(p.bary + (oa + g) * 3),
                           reinterpret_cast<float4*>(p.bary + (ob + g) * 3), pb, odd, vA, vB);
     }
-    return;
-  }
-  if (!valid) return;
+  } else if (valid) {
   for (int k = 0; k < K; ++k) {
     Hit h = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
     long long id = -1;
@@ -1012,6 +1022,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) mesh_fine_smemq_kernel(const 
     p.bary[(o + k) * 3 + 0] = h.b0;
     p.bary[(o + k) * 3 + 1] = h.b1;
     p.bary[(o + k) * 3 + 2] = h.b2;
+  }
+  }
+  if (sorted_walk || !tile_saw_tie(sh)) return;
+  sorted_walk = true;
+  q.reset();
   }
 }
 
@@ -1072,8 +1087,8 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const Fine
         const Face f = {fa.x, fa.y, fc.x, fa.z, fa.w, fc.y, fb.x, fb.y, fc.z};
         Hit h;
         const int nb = __float_as_int(fc.w);
-        bool unused = false;  // (this kernel always walks sorted lists)
-        if (!eval_pixel_face(px, py, f, fb.z, p.blur_radius, persp, clip, qn >= K && nb == -1, q_max_z, h, unused))
+        // (this kernel always walks sorted lists: no tie watching)
+        if (!eval_pixel_face<false>(px, py, f, fb.z, p.blur_radius, persp, clip, qn >= K && nb == -1, q_max_z, h))
           continue;
         const int fi = __float_as_int(fb.w);
         int at = -1;
@@ -1138,8 +1153,7 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const Fine
       const float* v = p.face_verts + (int64_t)qi[k] * 9;
       const Face f = {__ldg(v + 0), __ldg(v + 1), __ldg(v + 2), __ldg(v + 3), __ldg(v + 4),
                       __ldg(v + 5), __ldg(v + 6), __ldg(v + 7), __ldg(v + 8)};
-      bool unused = false;
-      eval_pixel_face(px, py, f, bary_denominator(f), p.blur_radius, persp, clip, false, 0.0f, h, unused);
+      eval_pixel_face<false>(px, py, f, bary_denominator(f), p.blur_radius, persp, clip, false, 0.0f, h);
       id = qi[k];
     }
     p.pix_to_face[o + k] = id;

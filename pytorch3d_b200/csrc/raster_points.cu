@@ -65,7 +65,14 @@ struct __align__(16) PointStage {
   } u;
   float4 rec[PCHUNK];  // x, y, z, r^2
   int id[PCHUNK];
+  int tie;  // points_fine_smem_kernel: some pixel saw a depth tie during an arrival-order walk (flag_point_tie)
 };
+
+// (the stage sits at the start of points_fine_smem_kernel's dynamic shared memory: a fixed address, no register)
+__device__ __forceinline__ void flag_point_tie() {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  reinterpret_cast<PointStage*>(smem_raw)->tie = 1;
+}
 
 struct PointFineParams {
   const float4* prec;  // (x, y, z, r) per point
@@ -203,13 +210,13 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_smem_kernel(const Po
   // order of the reference's naive kernel) and the tile walked again.
   int size, max_idx;
   float max_z;
-  for (int pass = 0;; ++pass) {
+  for (bool sort_list = false;; sort_list = true) {
     size = 0;
     max_idx = -1;
     max_z = -1000.0f;
-    bool tie = false;
+    if (tid == 0 && !sort_list) s.tie = 0;  // (ordered before every offer by the barriers of the tile body)
     const bool in_order = points_tile_body(
-        p, s, reinterpret_cast<int*>(smem_raw), tile, n, valid, px, py, pass == 1, [&](float pz, int pi, float d2) {
+        p, s, reinterpret_cast<int*>(smem_raw), tile, n, valid, px, py, sort_list, [&](float pz, int pi, float d2) {
           if (size < K) {  // (:61-67)
             qz[size * QSTRIDE] = pz;
             qi[size * QSTRIDE] = pi;
@@ -232,9 +239,9 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_smem_kernel(const Po
                 max_idx = i;
               }
             }
-            tie |= max_z == evicted;
-          } else {
-            tie |= pz == max_z;
+            if (max_z == evicted) flag_point_tie();
+          } else if (pz == max_z) {
+            flag_point_tie();
           }
         });
     // BubbleSort on z only (rasterize_points.cu:26-28): stable -> insertion sort over the thread's own column
@@ -248,31 +255,33 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_smem_kernel(const Po
         qd[(j + 1) * QSTRIDE] = qd[j * QSTRIDE];
         --j;
       }
-      tie |= j >= 0 && tz == qz[j * QSTRIDE];  // equal depths keep their arrival order
+      if (j >= 0 && tz == qz[j * QSTRIDE]) flag_point_tie();  // equal depths keep their arrival order
       qz[(j + 1) * QSTRIDE] = tz;
       qi[(j + 1) * QSTRIDE] = ti;
       qd[(j + 1) * QSTRIDE] = td;
     }
-    if (in_order) break;                        // (CTA-uniform)
-    if (!__syncthreads_or((int)tie)) break;     // no depth tie anywhere in the tile: the arrival-order walk stands
-  }
-  if (!p.vec_ok) {
-    if (!valid) return;
-    const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
-    for (int k = 0; k < K; ++k) {
-      const bool e = k >= size;
-      p.idx[o + k] = e ? -1 : qi[k * QSTRIDE];
-      p.zbuf[o + k] = e ? -1.0f : qz[k * QSTRIDE];
-      p.dists[o + k] = e ? -1.0f : qd[k * QSTRIDE];
+    if (!p.vec_ok) {
+      // (CTA-uniform) did any pixel see a tie?  then walk again, sorted, before anything is written.  Every thread
+      // contributes its own view of the flag: the thread that raised it sees it, and nobody reads it after the barrier
+      if (!in_order && __syncthreads_or(s.tie)) continue;
+      if (!valid) return;
+      const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
+      for (int k = 0; k < K; ++k) {
+        const bool e = k >= size;
+        p.idx[o + k] = e ? -1 : qi[k * QSTRIDE];
+        p.zbuf[o + k] = e ? -1.0f : qz[k * QSTRIDE];
+        p.dists[o + k] = e ? -1.0f : qd[k * QSTRIDE];
+      }
+      return;
     }
-    return;
+    for (int k = size; k < K; ++k) {  // the -1 padding of the unused slots
+      qz[k * QSTRIDE] = -1.0f;
+      qi[k * QSTRIDE] = -1;
+      qd[k * QSTRIDE] = -1.0f;
+    }
+    // (barrier: the columns are complete; OR of every thread's view of the flag, which nobody reads afterwards)
+    if (!__syncthreads_or(in_order ? 0 : s.tie)) break;  // no depth tie anywhere: the arrival-order walk stands
   }
-  for (int k = size; k < K; ++k) {  // the -1 padding of the unused slots
-    qz[k * QSTRIDE] = -1.0f;
-    qi[k * QSTRIDE] = -1;
-    qd[k * QSTRIDE] = -1.0f;
-  }
-  __syncthreads();
   // row-major write-out: row r of the tile is npx * K consecutive values of each output
   const int x0 = tile_x * TILE, y0 = tile_y * TILE;
   const int npx = min(TILE, p.W - x0), nrow = min(TILE, p.H - y0);
