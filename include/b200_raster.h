@@ -48,7 +48,7 @@ const char* b200r_last_error(void);
 /*
  * Scratch bytes needed by b200r_rasterize_meshes_forward for F packed faces, N meshes and an
  * H x W image.  pair_capacity = number of (tile, face) pairs the bin lists can hold; pass <= 0
- * for the default (min(F * tiles_per_image, 8*F + 64*N*tiles_per_image)).  If the real number of
+ * for the default (min(F * tiles_per_image, 32*F + 64*N*tiles_per_image)).  If the real number of
  * pairs exceeds the capacity the affected tiles transparently fall back to testing every face of
  * their mesh, so results never depend on it (the reference drops faces and prints a warning
  * instead, rasterize_coarse.cu:186-201).
@@ -264,6 +264,29 @@ int b200r_fragments_pack_push(const int64_t* pix_to_face, const float* zbuf, con
 int b200r_fragments_unpack(const void* region, int32_t n_images, int32_t H, int32_t W, int32_t K,
                            int64_t n_images_layout, const int32_t* image_index, const int64_t* face_shift,
                            int64_t* pix_to_face, float* zbuf, float* bary, float* dists, void* stream);
+
+/*
+ * Exchange context: one per process, holding the arenas of all ranks (own memory + b200r_peer_open'ed peers; each
+ * arena = 2 halves x `world` regions of b200r_packed_frames_bytes(n_images_layout, H, W, K) bytes), the batch geometry
+ * (HOST arrays: images per rank; for every image of every rank, in rank order, its position in the full batch and its
+ * face-id shift) and the events that order one step:
+ *   b200r_exchange_push    on compute_stream: pack this rank's frames, push them into every arena; side_stream then
+ *                          waits for the pack.  (`consumer_stream`: the stream that reads the results.)
+ *   <cross-rank barrier>   the caller's, enqueued on side_stream: e.g. a 4-byte NCCL all-reduce
+ *   b200r_exchange_expand  on side_stream: expand all ranks' streams into the dense full-batch buffers
+ *   b200r_exchange_wait    make a stream wait for that expansion
+ * Arena halves and result buffers alternate with the step's parity; a half is rewritten only behind the NEXT step's
+ * barrier, which every rank enqueues behind its own expansion of this step.
+ */
+int b200r_exchange_create(int32_t world, int32_t rank, int32_t H, int32_t W, int32_t K, int64_t n_images_layout,
+                          const int32_t* n_images_per_rank, const int32_t* image_index, const int64_t* face_shift,
+                          void* const* arenas, void** handle);
+int b200r_exchange_destroy(void* handle);
+int b200r_exchange_push(void* handle, const int64_t* pix_to_face, const float* zbuf, const float* bary,
+                        const float* dists, void* compute_stream, void* side_stream, void* consumer_stream);
+int b200r_exchange_expand(void* handle, int64_t* pix_to_face, float* zbuf, float* bary, float* dists,
+                          void* side_stream, int32_t* parity_out);
+int b200r_exchange_wait(void* handle, int32_t parity, void* stream);
 
 /* ------------------------------------------------------------------ host-buffer entry points - */
 

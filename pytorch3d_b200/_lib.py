@@ -62,6 +62,12 @@ SIGNATURES = {
         ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, ctypes.POINTER(_vp), _i32, _vp, _vp]),
     "b200r_fragments_unpack": (
         ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200r_exchange_create": (
+        ctypes.c_int, [_i32, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    "b200r_exchange_destroy": (ctypes.c_int, [_vp]),
+    "b200r_exchange_push": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200r_exchange_expand": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_i32)]),
+    "b200r_exchange_wait": (ctypes.c_int, [_vp, _i32, _vp]),
     "b200r_rasterize_meshes_forward_host": (
         ctypes.c_int,
         [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),

@@ -282,10 +282,14 @@ struct BinWorkspace {
   size_t bytes;
 };
 
+// Default capacity of the pair buffer: every element in every tile (the exact bound) or, if smaller, 32 pairs per
+// element.  (A blur band of 16 pixels puts every sub-pixel face of a 10^6-face mesh into ~9.4 tiles: with the former
+// 8 pairs per element the last 12 % of the tiles overflowed and walked the whole mesh -- 64 ms instead of ~10.)
+// The buffer is scratch that only the used part of is ever touched.
 inline int64_t default_pair_capacity(int64_t E, int N, int H, int W) {
   const int64_t tiles = (int64_t)div_up(H, TILE) * div_up(W, TILE);
   const int64_t exact = E * tiles;
-  const int64_t heur = 8 * E + 64 * (int64_t)N * tiles;
+  const int64_t heur = 32 * E + 64 * (int64_t)N * tiles;
   int64_t c = exact < heur ? exact : heur;
   if (c < 16) c = 16;
   if (c > 0x7fffffff) c = 0x7fffffff;  // positions are int32

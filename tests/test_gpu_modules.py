@@ -287,8 +287,10 @@ def test_install_rebinds_the_real_pytorch3d(built_lib, dev, masks, real_pytorch3
     fz = rasterizer(ico_sphere(5, dev), R=Rz, T=Tz)
     assert np.array_equal((fz.pix_to_face[0, ..., 0] >= 0).cpu().numpy(),
                           masks["test_rasterized_sphere_zoom_MeshRasterizer"])
-    # our own module with the real cameras and Meshes gives the same Fragments
+    # our own module with the real cameras and Meshes gives the same Fragments (fresh cameras: the reference's
+    # get_world_to_view_transform stores per-call R / T overrides in the camera object, cameras.py:196-209)
     import pytorch3d_b200 as p3b
+    cameras = FoVPerspectiveCameras(device=dev, R=R, T=T)
     mine = p3b.MeshRasterizer(cameras=cameras, raster_settings=p3b.RasterizationSettings(
         image_size=512, blur_radius=0.0, faces_per_pixel=1, bin_size=0))(ico_sphere(5, dev))
     assert torch.equal(mine.pix_to_face, f5.pix_to_face) and torch.equal(mine.zbuf, f5.zbuf)

@@ -46,14 +46,23 @@ out = {}
 # ---- packed path components
 ex = peer.PackedFrameExchange(plan, rank, (H, W), K)
 cur = torch.cuda.current_stream(dev)
-dst_self = (ctypes.c_void_p * 1)(ex._region(rank, 0, rank))
-dst_all = (ctypes.c_void_p * world)(*[ex._region(r, 0, rank) for r in range(world)])
-dst_peer = (ctypes.c_void_p * 1)(ex._region((rank + 1) % world, 0, rank))
+
+
+def region(holder, parity, source):
+    return ex._arena[holder] + parity * ex.half_bytes + source * ex.region_bytes
+
+
+cursor = torch.zeros(1, dtype=torch.int32, device=dev)
+image_index = [torch.tensor(plan.assignment[r], dtype=torch.int32, device=dev) for r in range(world)]
+face_shift = [torch.zeros(nm, dtype=torch.int64, device=dev) for r in range(world)]
+dst_self = (ctypes.c_void_p * 1)(region(rank, 0, rank))
+dst_all = (ctypes.c_void_p * world)(*[region(r, 0, rank) for r in range(world)])
+dst_peer = (ctypes.c_void_p * 1)(region((rank + 1) % world, 0, rank))
 
 
 def pack(dst, n):
     _lib.check(lib.b200r_fragments_pack_push(f[0].data_ptr(), f[1].data_ptr(), f[2].data_ptr(), f[3].data_ptr(), nm, H, W,
-                                             K, ex.n_layout, dst, n, ex._cursor.data_ptr(), cur.cuda_stream))
+                                             K, ex.n_layout, dst, n, cursor.data_ptr(), cur.cuda_stream))
 
 
 out["pack_to_self_ms"] = gpu_ms(lambda: pack(dst_self, 1))
@@ -68,8 +77,8 @@ dist.barrier()
 
 def unpack_all():
     for r in range(world):
-        _lib.check(lib.b200r_fragments_unpack(ex._region(rank, 0, r), nm, H, W, K, ex.n_layout,
-                                              ex._image_index[r].data_ptr(), ex._face_shift[r].data_ptr(),
+        _lib.check(lib.b200r_fragments_unpack(region(rank, 0, r), nm, H, W, K, ex.n_layout,
+                                              image_index[r].data_ptr(), face_shift[r].data_ptr(),
                                               full[0].data_ptr(), full[1].data_ptr(), full[2].data_ptr(),
                                               full[3].data_ptr(), cur.cuda_stream))
 
