@@ -218,25 +218,32 @@ __global__ void __launch_bounds__(SEG)
     const int j = (int)(pix / HW);
     obase = ((long long)image_index[j] * HW + (pix - (int64_t)j * HW)) * K;
     const long long shift = face_shift[j];
-    for (int k = 0; k < K; ++k) {
-      long long id = -1;
-      float z = -1.0f, dd = -1.0f, b0 = -1.0f, b1 = -1.0f, b2 = -1.0f;
-      if (k < cnt) {
-        const uint2 a = e[k * 3], c = e[k * 3 + 1], g = e[k * 3 + 2];
-        id = (long long)(int)a.x + shift;
-        z = __uint_as_float(a.y);
-        dd = __uint_as_float(c.x);
-        b0 = __uint_as_float(c.y);
-        b1 = __uint_as_float(g.x);
-        b2 = __uint_as_float(g.y);
+    // four slots at a time, laid out with 16-byte shared-memory stores (7 per group of four slots)
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      long long id[4];
+      float z[4], dd[4], b[12];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        id[u] = -1;
+        z[u] = dd[u] = b[3 * u] = b[3 * u + 1] = b[3 * u + 2] = -1.0f;
+        if (k0 + u < cnt) {
+          const uint2 a = e[(k0 + u) * 3], c = e[(k0 + u) * 3 + 1], g = e[(k0 + u) * 3 + 2];
+          id[u] = (long long)(int)a.x + shift;
+          z[u] = __uint_as_float(a.y);
+          dd[u] = __uint_as_float(c.x);
+          b[3 * u] = __uint_as_float(c.y);
+          b[3 * u + 1] = __uint_as_float(g.x);
+          b[3 * u + 2] = __uint_as_float(g.y);
+        }
       }
-      const int at = tid * K + k;
-      s_id[at] = id;
-      s_z[at] = z;
-      s_d[at] = dd;
-      s_b[at * 3] = b0;
-      s_b[at * 3 + 1] = b1;
-      s_b[at * 3 + 2] = b2;
+      const int at = tid * K + k0;
+      reinterpret_cast<longlong2*>(s_id + at)[0] = make_longlong2(id[0], id[1]);
+      reinterpret_cast<longlong2*>(s_id + at)[1] = make_longlong2(id[2], id[3]);
+      *reinterpret_cast<float4*>(s_z + at) = make_float4(z[0], z[1], z[2], z[3]);
+      *reinterpret_cast<float4*>(s_d + at) = make_float4(dd[0], dd[1], dd[2], dd[3]);
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+        reinterpret_cast<float4*>(s_b + at * 3)[u] = make_float4(b[4 * u], b[4 * u + 1], b[4 * u + 2], b[4 * u + 3]);
     }
   }
   s_base[tid] = obase;

@@ -184,10 +184,14 @@ __device__ __forceinline__ bool eval_pixel_face(float px, float py, const Face& 
   if (clip) bary_clip(c0, c1, c2);
   const float pz = ffma(f.z2, c2, ffma(f.z0, c0, fmul(f.z1, c1)));
   if (!(pz >= 0.0f)) return false;  // behind the image plane (:163)
+#ifdef B200R_EXP_NOEARLYZ
+  (void)full; (void)max_z;
+#else
   if (full && !(pz < max_z)) {
     if (WATCH && pz == max_z) flag_tie();
     return false;
   }
+#endif
   const bool inside = w0 > 0.0f && w1 > 0.0f && w2 > 0.0f;
   if (!inside && !(blur_radius > 0.0f)) return false;  // dist >= 0 >= blur_radius always rejects (:175)
   const float dist = point_tri_dist(px, py, f);
@@ -516,8 +520,10 @@ struct FineStage {
 };
 
 __device__ __forceinline__ void flag_tie() {
+#ifndef B200R_EXP_NOWATCH  // (timing experiment of tools/variant_time.py: no tie watching at all)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   reinterpret_cast<FineStage*>(smem_raw)->tie = 1;
+#endif
 }
 
 // Full-sector output stores.  A pixel's K values of one buffer are P 16-byte pieces; the pixels of two adjacent
@@ -810,7 +816,13 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
 // After the epilogue of an arrival-order walk: did any pixel of the tile see a depth tie?  CTA-uniform: every thread
 // contributes its own view of the flag (the thread that raised it sees it) and nobody reads it after the barrier, which
 // also orders every warp's epilogue reads of the queue payload before the sorted walk reuses shared memory.
-__device__ __forceinline__ bool tile_saw_tie(const FineStage& sh) { return __syncthreads_or(sh.tie) != 0; }
+__device__ __forceinline__ bool tile_saw_tie(const FineStage& sh) {
+#ifdef B200R_EXP_NOWATCH
+  return false;
+#else
+  return __syncthreads_or(sh.tie) != 0;
+#endif
+}
 
 // Which tile, which faces: grid = (tiles per row, tile rows, images) -- no integer divisions.
 struct TileWork {
