@@ -330,6 +330,12 @@ int64_t b200r_kernel_launch_count(void);
 void b200r_set_profiling(int32_t enabled);
 int b200r_last_phase_ms(float out[3]);
 
+/*
+ * Programmatic dependent launch between the kernels of one call (setup -> scan -> fill -> fine; backward -> scatter):
+ * the next kernel is made resident while its predecessor drains.  On by default; results never depend on it.
+ */
+void b200r_set_pdl(int32_t enabled);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ SIGNATURES = {
     "b200r_last_error": (ctypes.c_char_p, []),
     "b200r_kernel_launch_count": (_i64, []),
     "b200r_set_profiling": (None, [_i32]),
+    "b200r_set_pdl": (None, [_i32]),
     "b200r_last_phase_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "b200r_rasterize_meshes_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i64]),
     "b200r_rasterize_meshes_forward": (

@@ -94,6 +94,8 @@ static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict_
   __shared__ long long carry_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) carry_s = 0;
+  pdl_trigger();  // (see common.cuh: the fill kernel may become resident now)
+  pdl_wait();     // the counters are complete
   __syncthreads();
   // 64-bit running sums, saturated to INT_MAX on output: a batch whose (tile, element) pairs would overflow
   // int32 simply marks the remaining tiles as "does not fit" (they rasterise from the whole mesh range).
@@ -152,6 +154,8 @@ static __global__ void __launch_bounds__(256)
                      int* __restrict__ pairs, int64_t capacity) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();  // (see common.cuh: the fine kernel may become resident now)
+  pdl_wait();     // the segment starts (scan kernel) and, transitively, the rectangles (setup kernel) are complete
   uint4 r4 = make_uint4(RECT_EMPTY_X, 0u, 0u, 0u);
   if (e < E) r4 = __ldg(rect + e);
   const uint2 r = make_uint2(r4.x, r4.y);

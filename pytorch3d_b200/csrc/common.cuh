@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdio>
 #include <string>
+#include <utility>
 
 #include "../../include/b200_raster.h"
 
@@ -49,6 +50,33 @@ struct PhaseTimer {
 };
 bool profiling_enabled();
 PhaseTimer& phase_timer();
+
+// Programmatic dependent launch: the small dependent launches of one call (setup -> scan -> fill -> fine) are chained
+// with cudaLaunchAttributeProgrammaticStreamSerialization, so that the next kernel's CTAs are already resident when
+// the previous grid drains -- the launch latency between them (a few microseconds each, a quarter of the binning
+// time) overlaps the predecessor's tail.  Every chained kernel executes pdl_wait() before it touches anything a
+// predecessor wrote (it returns only when the whole preceding grid has completed and its writes are visible; a
+// no-op for a normally launched kernel) and every thread of every kernel in a chain executes it, so completion is
+// transitive along the chain.  pdl_trigger() lets the successor start once all CTAs of this grid have issued it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -22,6 +22,8 @@ std::atomic<int64_t>& launch_counter() {
   return c;
 }
 
+static std::atomic<int> g_pdl{1};
+bool pdl_enabled() { return g_pdl.load() != 0; }
 static std::atomic<int> g_profiling{0};
 bool profiling_enabled() { return g_profiling.load() != 0; }
 PhaseTimer& phase_timer() {
@@ -110,6 +112,7 @@ extern "C" const char* b200r_version(void) { return "b200raster 0.1.0 sm_100a"; 
 extern "C" const char* b200r_last_error(void) { return last_error_ref().c_str(); }
 extern "C" int64_t b200r_kernel_launch_count(void) { return launch_counter().load(); }
 extern "C" void b200r_set_profiling(int32_t enabled) { g_profiling.store(enabled ? 1 : 0); }
+extern "C" void b200r_set_pdl(int32_t enabled) { g_pdl.store(enabled ? 1 : 0); }
 extern "C" int b200r_last_phase_ms(float out[3]) {
   PhaseTimer& t = phase_timer();
   out[0] = out[1] = out[2] = 0.0f;

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(SETUP_FACES)
   const int tid = threadIdx.x;
   const int64_t f0 = (int64_t)blockIdx.x * SETUP_FACES;
   const int nf = (int)min((int64_t)SETUP_FACES, F - f0);
+  pdl_trigger();  // (see common.cuh: the scan kernel may become resident; it waits for this grid to complete)
   if (INDEXED) {
     // one (face, corner) per step and thread: coalesced index reads, 12-byte vertex gathers (the vertex array
     // is small and L2-resident), then the gathered block is written out as 9 * nf contiguous floats
@@ -830,6 +831,7 @@ struct TileWork {
   bool overflow;
 };
 __device__ __forceinline__ TileWork tile_work(const FineParams& p) {
+  pdl_wait();  // the tile lists (fill kernel) and, transitively, the face records are complete (see common.cuh)
   TileWork t;
   t.tile_x = blockIdx.x;
   t.tile_y = blockIdx.y;
@@ -1076,6 +1078,7 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const Fine
   const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
   const float fx_lo = warp_min(valid ? px : FLT_MAX), fx_hi = warp_max(valid ? px : -FLT_MAX);
   const float fy_lo = warp_min(valid ? py : FLT_MAX), fy_hi = warp_max(valid ? py : -FLT_MAX);
+  pdl_wait();
   const int seg_begin = p.tile_offset[t], seg_end = p.tile_offset[t + 1];
   const bool overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
   const int64_t mesh_first = p.first[n];
@@ -1485,11 +1488,12 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
     }
     B200R_LAUNCHED("mesh_setup_count_kernel");
   }
-  tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles);
+  B200R_CUDA_OK(launch_chained(tile_scan_kernel, dim3(1), dim3(1024), 0, stream, ws.tile_count, ws.tile_offset,
+                               (int)ntiles));
   B200R_LAUNCHED("tile_scan_kernel");
   if (F > 0) {
-    tile_fill_kernel<true><<<(unsigned)((F + 255) / 256), 256, 0, stream>>>(ws.rect, F, TY, TX, ws.tile_count, ws.pairs,
-                                                                    ws.capacity);
+    B200R_CUDA_OK(launch_chained(tile_fill_kernel<true>, dim3((unsigned)((F + 255) / 256)), dim3(256), 0, stream,
+                                 ws.rect, F, TY, TX, ws.tile_count, ws.pairs, ws.capacity));
     B200R_LAUNCHED("tile_fill_kernel");
   }
   // (no sort launch: every fine CTA puts its own tile list in ascending face order, see cta_sort256)
@@ -1524,7 +1528,7 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
     p.smem_ints = (int)((SMEM) / sizeof(int));                                                           \
     for (p.n0 = 0; p.n0 < N; p.n0 += 65535) {                                                            \
       const dim3 grid3((unsigned)TX, (unsigned)TY, (unsigned)min(N - p.n0, 65535));                      \
-      KERNEL<<<grid3, TILE_THREADS, (SMEM), stream>>>(p);                                                \
+      B200R_CUDA_OK(launch_chained(KERNEL, grid3, dim3(TILE_THREADS), (SMEM), stream, p));               \
     }                                                                                                    \
   } while (0)
 #define B200R_FINE(KM)                                                                                    \
@@ -1562,7 +1566,7 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
     else
       B200R_FINE_LAUNCH((mesh_fine_smemq_kernel<false, false>), smem_max, smem);
   } else
-    mesh_fine_bigk_kernel<<<grid, TILE_THREADS, 0, stream>>>(p);
+    B200R_CUDA_OK(launch_chained(mesh_fine_bigk_kernel, dim3(grid), dim3(TILE_THREADS), 0, stream, p));
 #undef B200R_FINE
 #undef B200R_FINE_LAUNCH
   B200R_LAUNCHED("mesh_fine_kernel");

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(SETUP_POINTS)
   const int tid = threadIdx.x;
   const int64_t p0 = (int64_t)blockIdx.x * SETUP_POINTS;
   const int np = (int)min((int64_t)SETUP_POINTS, P - p0);
+  pdl_trigger();  // (see common.cuh: the scan kernel may become resident; it waits for this grid to complete)
   if (tid == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
@@ -127,6 +128,7 @@ __device__ __forceinline__ bool points_tile_body(const PointFineParams& p, Point
                                                  int tile, int n, bool valid, float px, float py, bool sort_list,
                                                  Offer offer) {
   const int tid = threadIdx.x, lane = tid & 31;
+  pdl_wait();  // the tile lists (fill kernel) and, transitively, the point records are complete (see common.cuh)
   const int seg_begin = p.tile_offset[tile], seg_end = p.tile_offset[tile + 1];
   const bool overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
   const int64_t cloud_first = p.first[n];
@@ -498,11 +500,12 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
         points, radius, P, first, num, N, H, W, TY, TX, rx, ry, ws.rect, ws.tile_count, prec);
     B200R_LAUNCHED("points_setup_count_kernel");
   }
-  tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_offset, (int)ntiles);
+  B200R_CUDA_OK(launch_chained(tile_scan_kernel, dim3(1), dim3(1024), 0, stream, ws.tile_count, ws.tile_offset,
+                               (int)ntiles));
   B200R_LAUNCHED("tile_scan_kernel");
   if (P > 0) {
-    tile_fill_kernel<false><<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(ws.rect, P, TY, TX, ws.tile_count, ws.pairs,
-                                                                    ws.capacity);
+    B200R_CUDA_OK(launch_chained(tile_fill_kernel<false>, dim3((unsigned)((P + 255) / 256)), dim3(256), 0, stream,
+                                 ws.rect, P, TY, TX, ws.tile_count, ws.pairs, ws.capacity));
     B200R_LAUNCHED("tile_fill_kernel");
   }
   // (no sort launch: every fine CTA puts its own tile list in ascending point order, see cta_sort256)
@@ -531,9 +534,9 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
   for (p.n0 = 0; p.n0 < N; p.n0 += 65535) {  // grid.z is limited to 65535 images per launch
     const dim3 grid3((unsigned)TX, (unsigned)TY, (unsigned)min(N - p.n0, 65535));
     if (K <= SMEMQ_MAX_K)
-      points_fine_smem_kernel<<<grid3, TILE_THREADS, smem, stream>>>(p);
+      B200R_CUDA_OK(launch_chained(points_fine_smem_kernel, grid3, dim3(TILE_THREADS), smem, stream, p));
     else
-      points_fine_bigk_kernel<<<grid3, TILE_THREADS, 0, stream>>>(p);
+      B200R_CUDA_OK(launch_chained(points_fine_bigk_kernel, grid3, dim3(TILE_THREADS), 0, stream, p));
   }
   B200R_LAUNCHED("points_fine_kernel");
   if (prof) {
