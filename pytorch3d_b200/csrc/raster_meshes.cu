@@ -643,6 +643,45 @@ __device__ __forceinline__ void consider_face(const FineStage& sh, int j, float 
   q.offer(h, fi);
 }
 
+// Depth culling for a whole warp (blur > 0: every face in the blur band of a pixel is a hit, tens to thousands per pixel,
+// of which only the K nearest survive).  Once every pixel of the warp's footprint holds K hits, a face can only matter if
+// its depth at some pixel of the footprint is below `zcut`, the largest of those pixels' farthest kept depths -- the
+// queue itself discards a hit unless pz < max_z (rasterize_meshes.cu:226).  face_depth_lower_bound returns a rigorous lower
+// bound of the depth the kernel would COMPUTE for any pixel of the footprint (so dropping the face cannot change any
+// result, whatever the order of the walk), or -FLT_MAX when no bound is available:
+//   clip_barycentric_coords: the clipped, renormalised barycentrics are a convex combination (each in [0, 1], sum within
+//     3 ulp of 1), and drawable faces have zmin >= 1e-8 > 0: pz >= zmin * (1 - 1e-6).
+//   neither clip nor perspective correction: pz is, in exact arithmetic, the affine function
+//     (z0 E0(p) + z1 E1(p) + z2 E2(p)) / den of the pixel; its minimum over the footprint's rectangle is the value at the
+//     centre minus |gradient| . half-extent; the float evaluation of any pixel differs from the exact value by at most
+//     27 ulp-units of zabs * M / |den| (M bounds every product inside the edge functions over the footprint) -- the
+//     margin below takes 1e-5 (> 160 * 2^-24) of that plus 1e-5 of the bound's own terms.
+//   perspective correction without clipping: no bound (the face is kept).
+__device__ __forceinline__ float face_depth_lower_bound(const float4 fa, const float4 fb, const float4 fc, float cx,
+                                                        float cy, float hx, float hy, bool persp, bool clip) {
+  const float z0 = fc.x, z1 = fc.y, z2 = fc.z;
+  if (clip) return fminf(fminf(z0, z1), z2) * (1.0f - 1e-6f);
+  if (persp) return -FLT_MAX;
+  const float x0 = fa.x, y0 = fa.y, x1 = fa.z, y1 = fa.w, x2 = fb.x, y2 = fb.y;
+  const float rd = 1.0f / fabsf(fb.z);
+  const float e0 = (cx - x1) * (y2 - y1) - (cy - y1) * (x2 - x1);
+  const float e1 = (cx - x2) * (y0 - y2) - (cy - y2) * (x0 - x2);
+  const float e2 = (cx - x0) * (y1 - y0) - (cy - y0) * (x1 - x0);
+  const float num = z0 * e0 + z1 * e1 + z2 * e2;
+  const float gxn = z0 * (y2 - y1) + z1 * (y0 - y2) + z2 * (y1 - y0);
+  const float gyn = z0 * (x2 - x1) + z1 * (x0 - x2) + z2 * (x1 - x0);
+  const float pzc = (fb.z < 0.0f ? -num : num) * rd;
+  const float spread = (fabsf(gxn) * hx + fabsf(gyn) * hy) * rd;
+  const float dx = fmaxf(fmaxf(fabsf(cx - x0), fabsf(cx - x1)), fabsf(cx - x2)) + hx;
+  const float dy = fmaxf(fmaxf(fabsf(cy - y0), fabsf(cy - y1)), fabsf(cy - y2)) + hy;
+  const float lx = fmaxf(fmaxf(x0, x1), x2) - fminf(fminf(x0, x1), x2);
+  const float ly = fmaxf(fmaxf(y0, y1), y2) - fminf(fminf(y0, y1), y2);
+  const float zabs = fmaxf(fmaxf(fabsf(z0), fabsf(z1)), fabsf(z2));
+  const float margin = 1e-5f * (zabs * (dx * ly + dy * lx) * rd + fabsf(pzc) + spread);
+  const float lb = pzc - spread - margin;
+  return lb == lb ? lb : -FLT_MAX;  // (NaN / inf coordinates: no bound)
+}
+
 // The body shared by the fine kernels: stage the tile's list chunk by chunk, find every pixel's candidates and offer
 // the hits to the pixel's queue `q`.
 //
@@ -755,8 +794,12 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
         }
       }
       __syncthreads();
-      // every pixel walks its own candidates, in ascending face order
+      // every pixel walks its own candidates, in ascending face order.  A pixel has a handful of candidates spread
+      // over the chunk's mask words; every lane advances through ITS words on its own (skipping empty ones costs three
+      // instructions), so that the lanes of a warp evaluate their n-th candidates together whatever words those are
+      // in -- looping over the words in lockstep left a third of the lanes active in the evaluation (ncu: 9.8 of 32).
       const float px = sh.col[lc], py = sh.row[lr];
+#ifdef B200R_EXP_OLDWALK  // (timing experiment: the words in lockstep)
       for (int w = 0; w < nwords; ++w) {
         unsigned m = sh.u.mask[w][tid];
         while (m != 0u) {
@@ -765,9 +808,23 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
           consider_face<Q, NB>(sh, j, px, py, blur_radius, persp, clip, q);
         }
       }
+#else
+      {
+        int w = 0;
+        unsigned m = sh.u.mask[0][tid];
+        for (;;) {
+          while (m == 0u && ++w < nwords) m = sh.u.mask[w][tid];
+          if (m == 0u) break;
+          const int j = w * 32 + __ffs((int)m) - 1;
+          m &= m - 1u;
+          consider_face<Q, NB>(sh, j, px, py, blur_radius, persp, clip, q);
+        }
+      }
+#endif
       continue;  // chunk done
     }
     const float px = sh.col[lc], py = sh.row[lr];
+    const bool cull_depth = clip || !persp;
     // extent of the warp's footprint (pixel centres are monotonic in the pixel index)
     const float fc0 = sh.col[lc & 8], fc1 = sh.col[(lc & 8) + 7], fr0 = sh.row[lr & 12], fr1 = sh.row[(lr & 12) + 3];
     const float cmin = fminf(fc0, fc1), cmax = fmaxf(fc0, fc1), rmin = fminf(fr0, fr1), rmax = fmaxf(fr0, fr1);
@@ -782,11 +839,40 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
         float4 b0 = make_float4(FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX), b1 = b0;
         if (h0) b0 = sh.u.box[sub + lane];
         if (h1) b1 = sh.u.box[sub + 32 + lane];
-        const bool all0 = __all_sync(0xffffffffu, cmin >= b0.x && cmax <= b0.y && rmin >= b0.z && rmax <= b0.w);
-        const bool all1 = __all_sync(0xffffffffu, cmin >= b1.x && cmax <= b1.y && rmin >= b1.z && rmax <= b1.w);
-        if (all0 && (all1 || sub + 32 >= nc)) {
-          m0 = 0xffffffffu;
-          m1 = all1 ? 0xffffffffu : 0u;
+        // depth culling (see face_depth_lower_bound): once every pixel of the footprint holds K hits
+        bool keep0 = h0, keep1 = h1;
+#ifndef B200R_EXP_NOCULL
+        if (cull_depth) {
+          const float zcut = warp_max(!valid ? -FLT_MAX : (q.full() ? q.max_z() : FLT_MAX));
+          if (zcut < FLT_MAX) {
+            const float cx = 0.5f * (cmin + cmax), cy = 0.5f * (rmin + rmax);
+            const float hx = 0.5f * (cmax - cmin) * (1.0f + 1e-6f), hy = 0.5f * (rmax - rmin) * (1.0f + 1e-6f);
+            if (h0) {
+              const float4 fc = sh.c[sub + lane];
+              if (!NB || __float_as_int(fc.w) == -1)
+                keep0 = !(face_depth_lower_bound(sh.a[sub + lane], sh.b[sub + lane], fc, cx, cy, hx, hy, persp, clip) >
+                          zcut);
+            }
+            if (h1) {
+              const float4 fc = sh.c[sub + 32 + lane];
+              if (!NB || __float_as_int(fc.w) == -1)
+                keep1 = !(face_depth_lower_bound(sh.a[sub + 32 + lane], sh.b[sub + 32 + lane], fc, cx, cy, hx, hy,
+                                                 persp, clip) > zcut);
+            }
+            if (!keep0) b0 = make_float4(FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX);
+            if (!keep1) b1 = make_float4(FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX);
+            if (!__any_sync(0xffffffffu, keep0 || keep1)) continue;  // the whole round lies behind the footprint
+          }
+        }
+#endif
+        // (every face of the half-round is either absent / culled or contains the whole footprint)
+        const bool all0 =
+            __all_sync(0xffffffffu, !keep0 || (cmin >= b0.x && cmax <= b0.y && rmin >= b0.z && rmax <= b0.w));
+        const bool all1 =
+            __all_sync(0xffffffffu, !keep1 || (cmin >= b1.x && cmax <= b1.y && rmin >= b1.z && rmax <= b1.w));
+        if (all0 && all1) {
+          m0 = __ballot_sync(0xffffffffu, keep0);
+          m1 = __ballot_sync(0xffffffffu, keep1);
         } else {
           // the footprint's 8 column and 4 row coordinates (lane = row * 8 + column); re-gathered per round so
           // that they do not occupy 12 registers during pass B and the epilogue
@@ -795,8 +881,8 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
           for (int c = 0; c < 8; ++c) col[c] = sh.col[(lc & 8) + c];
 #pragma unroll
           for (int r = 0; r < 4; ++r) row[r] = sh.row[(lr & 12) + r];
-          if (h0) m0 = box_pixel_mask(b0, col, row);
-          if (h1) m1 = box_pixel_mask(b1, col, row);
+          if (keep0) m0 = box_pixel_mask(b0, col, row);
+          if (keep1) m1 = box_pixel_mask(b1, col, row);
           m0 = warp_transpose_bits(m0, lane);
           if (sub + 32 < nc) m1 = warp_transpose_bits(m1, lane);
         }

@@ -58,11 +58,56 @@ __global__ void __launch_bounds__(SETUP_POINTS)
   warp_count_rect<false>(rc, n, TY, TX, tile_count, tid & 31);
 }
 
+// The same pass with a private per-CTA histogram (see tile_fill_private_kernel in binning.cuh): BIN_CHUNK points per
+// CTA, eight per thread, read with plain coalesced loads (consecutive lanes consume consecutive 12-byte points).
+__global__ void __launch_bounds__(256)
+    points_setup_count_private_kernel(const float* __restrict__ points, const float* __restrict__ radius, int64_t P,
+                                      const int64_t* __restrict__ first, const int64_t* __restrict__ num, int N, int H,
+                                      int W, int TY, int TX, float rx, float ry, uint4* __restrict__ rect,
+                                      int* __restrict__ tile_count, float4* __restrict__ prec) {
+  extern __shared__ int hist[];  // [TY * TX]
+  const int tid = threadIdx.x, T = TY * TX;
+  const int64_t p0 = (int64_t)blockIdx.x * BIN_CHUNK;
+  pdl_trigger();
+  for (int t = tid; t < T; t += 256) hist[t] = 0;
+  const int n0 = find_owner(first, num, N, p0);  // the chunk's image (uniform); -1: the chunk starts in a gap
+  const int64_t lo0 = n0 >= 0 ? __ldg(first + n0) : 0, hi0 = n0 >= 0 ? lo0 + __ldg(num + n0) : 0;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < BIN_CHUNK / 256; ++i) {
+    const int64_t pi = p0 + i * 256 + tid;
+    if (pi >= P) continue;
+    const float x = __ldg(points + pi * 3 + 0), y = __ldg(points + pi * 3 + 1), z = __ldg(points + pi * 3 + 2);
+    const float r = __ldg(radius + pi);
+    const int n = (pi >= lo0 && pi < hi0) ? n0 : find_owner(first, num, N, pi);
+    uint2 rc = make_uint2(RECT_EMPTY_X, 0u);
+    if (n >= 0 && !(z < 0.0f)) rc = bbox_to_tile_rect(fsub(x, r), fadd(x, r), fsub(y, r), fadd(y, r), H, W, rx, ry);
+    rect[pi] = make_uint4(rc.x, rc.y, (uint32_t)max(n, 0), 0u);
+    prec[pi] = make_float4(x, y, z, r);
+    if (rect_empty(rc)) continue;
+    const int tx0 = rc.x & 0xFFFF, tx1 = rc.x >> 16, ty0 = rc.y & 0xFFFF, ty1 = rc.y >> 16;
+    for (int ty = ty0; ty <= ty1; ++ty)
+      for (int tx = tx0; tx <= tx1; ++tx) {
+        if (n == n0)
+          atomicAdd(hist + ty * TX + tx, 1);
+        else
+          atomicAdd(tile_count + (n * TY + ty) * TX + tx, 1);
+      }
+  }
+  __syncthreads();
+  if (n0 >= 0)
+    for (int t = tid; t < T; t += 256) {
+      const int c = hist[t];
+      if (c > 0) atomicAdd(tile_count + n0 * T + t, c);
+    }
+}
+
 // One staged chunk of points.
 struct __align__(16) PointStage {
   union {
     float4 box[PCHUNK];           // xmin, xmax, ymin, ymax (empty = never hit)
     int sort_buf[2 * TILE_THREADS];  // exchange buffers of cta_sort256 (before the chunk is staged)
+    unsigned long long sort_buf64[2 * TILE_THREADS];  // ... of cta_sort256_u64
   } u;
   float4 rec[PCHUNK];  // x, y, z, r^2
   int id[PCHUNK];
@@ -179,6 +224,75 @@ __device__ __forceinline__ bool points_tile_body(const PointFineParams& p, Point
   return sort_list || overflow || count <= 1;
 }
 
+// Depth-ordered walk of a tile whose list fits one chunk (points_fine_smem_kernel, first attempt).  The CTA sorts the
+// tile's points by (z, index) -- one 64-bit key per thread -- and stages them in that order; every pixel then meets its
+// hits nearest first, so its K nearest are simply the first K: append-only columns, no eviction, no search for the
+// farthest entry, no final sort, and a pixel whose column is full is done.  This equals the reference's result unless two
+// of a pixel's hits share a depth bit for bit (their order then depends on the reference's queue history): such a hit
+// raises the tile's tie flag and the caller falls back to the literal queue on the index-sorted list.
+__device__ __forceinline__ int points_tile_walk_by_depth(const PointFineParams& p, PointStage& s, int seg_begin,
+                                                          int count, bool valid, float px, float py, float* qz, int* qi,
+                                                          float* qd) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int K = p.K;
+  unsigned long long key = ~0ull;  // threads without a point, points behind the camera: sorted to the end, never staged
+  if (tid < count) {
+    const int pi = p.pairs[seg_begin + tid];
+    const float z = __ldg(reinterpret_cast<const float*>(p.prec + pi) + 2);
+    // (z >= 0: the bits are ordered like the values; -0 + 0 = +0)
+    if (!(z < 0.0f)) key = ((unsigned long long)__float_as_uint(fadd(z, 0.0f)) << 32) | (unsigned)pi;
+  }
+  key = cta_sort256_u64(key, count, s.u.sort_buf64);
+  if (count > 32) __syncthreads();  // the exchange buffers alias the boxes written next
+  if (tid < count) {
+    if (key != ~0ull)
+      stage_point(s, tid, p.prec, (int)(unsigned)(key & 0xffffffffull));
+    else
+      s.u.box[tid] = make_float4(FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX);
+  }
+  __syncthreads();
+  int size = 0;
+  float last_z = -1.0f;
+  bool done = !valid;
+  for (int sub = 0; sub < count; sub += 64) {
+    if (__all_sync(0xffffffffu, done)) break;  // every pixel of the footprint has its K nearest
+    unsigned m0 = 0, m1 = 0;
+    {
+      float col[8], row[4];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) col[c] = __shfl_sync(0xffffffffu, px, c);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) row[r] = __shfl_sync(0xffffffffu, py, 8 * r);
+      if (sub + lane < count) m0 = box_pixel_mask(s.u.box[sub + lane], col, row);
+      if (sub + 32 + lane < count) m1 = box_pixel_mask(s.u.box[sub + 32 + lane], col, row);
+    }
+    m0 = warp_transpose_bits(m0, lane);
+    if (sub + 32 < count) m1 = warp_transpose_bits(m1, lane);
+    unsigned long long mine = done ? 0ull : (((unsigned long long)m1 << 32) | m0);
+    while (__any_sync(0xffffffffu, mine != 0ull)) {
+      if (mine == 0ull) continue;
+      const int j = sub + __ffsll((long long)mine) - 1;
+      mine &= mine - 1ull;
+      const float4 r = s.rec[j];
+      const float dx = fsub(px, r.x), dy = fsub(py, r.y);
+      const float d2 = sqnorm2(dx, dy);  // CheckPixelInsidePoint (rasterize_points.cu:49-60)
+      if (!(d2 < r.w)) continue;
+      if (r.z == last_z || r.z != r.z) flag_point_tie();  // equal depths (or NaN): the literal queue decides
+      if (size < K) {
+        qz[size * QSTRIDE] = r.z;
+        qi[size * QSTRIDE] = s.id[j];
+        qd[size * QSTRIDE] = d2;
+        last_z = r.z;
+        ++size;
+      } else {  // the first hit beyond the K nearest: nothing farther can matter
+        mine = 0ull;
+        done = true;
+      }
+    }
+  }
+  return size;
+}
+
 // K <= 32: the reference's queue (rasterize_points.cu:61-79) -- an UNSORTED array of K slots plus the tracked
 // maximum z; a hit fills the next free slot or, when full and pz < q_max_z, overwrites the tracked maximum,
 // which is then searched again -- with its three arrays in dynamic shared memory as per-thread columns, where
@@ -204,19 +318,47 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_smem_kernel(const Po
   const bool valid = xo < p.W && yo < p.H;
   const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
   const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
+  pdl_wait();  // the tile lists (fill kernel) and, transitively, the point records are complete (see common.cuh)
 
   // Order of the list: the queue keeps the K nearest points whatever the arrival order unless two points share,
   // bit for bit, the depth at the queue's far end, and the final stable sort on z orders them the same way unless two
   // kept points share a depth.  Point depths rarely tie, so the tile is first walked in arrival order while
   // watching for exactly those events; only if some pixel saw one is the list sorted (ascending point index, the
   // order of the reference's naive kernel) and the tile walked again.
+  // A list that fits one chunk (all but very dense tiles) is first walked in DEPTH order (points_tile_walk_by_depth),
+  // which needs neither the queue's eviction logic nor a final sort; it is equally exact unless depths tie.
   int size, max_idx;
   float max_z;
-  for (bool sort_list = false;; sort_list = true) {
+  const int seg_begin0 = p.tile_offset[tile], seg_end0 = p.tile_offset[tile + 1];
+  const bool by_depth_ok = !((int64_t)seg_end0 > p.capacity || seg_end0 == INT_MAX) && seg_end0 - seg_begin0 <= PCHUNK;
+  for (int attempt = by_depth_ok ? 0 : 1;; attempt = 2) {  // 0: depth order, 1: arrival order, 2: index order (exact)
+    const bool sort_list = attempt == 2;
     size = 0;
     max_idx = -1;
     max_z = -1000.0f;
     if (tid == 0 && !sort_list) s.tie = 0;  // (ordered before every offer by the barriers of the tile body)
+    if (attempt == 0) {
+      size = points_tile_walk_by_depth(p, s, seg_begin0, seg_end0 - seg_begin0, valid, px, py, qz, qi, qd);
+      if (!p.vec_ok) {
+        if (__syncthreads_or(s.tie)) continue;
+        if (!valid) return;
+        const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
+        for (int k = 0; k < K; ++k) {
+          const bool e = k >= size;
+          p.idx[o + k] = e ? -1 : qi[k * QSTRIDE];
+          p.zbuf[o + k] = e ? -1.0f : qz[k * QSTRIDE];
+          p.dists[o + k] = e ? -1.0f : qd[k * QSTRIDE];
+        }
+        return;
+      }
+      for (int k = size; k < K; ++k) {  // the -1 padding of the unused slots
+        qz[k * QSTRIDE] = -1.0f;
+        qi[k * QSTRIDE] = -1;
+        qd[k * QSTRIDE] = -1.0f;
+      }
+      if (!__syncthreads_or(s.tie)) break;  // no depth tie anywhere: the depth-order walk stands
+      continue;
+    }
     const bool in_order = points_tile_body(
         p, s, reinterpret_cast<int*>(smem_raw), tile, n, valid, px, py, sort_list, [&](float pz, int pi, float d2) {
           if (size < K) {  // (:61-67)
@@ -495,17 +637,28 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
   const bool prof = profiling_enabled();
   if (prof) phase_timer().record(0, stream);
   B200R_CUDA_OK(cudaMemsetAsync(ws.tile_count, 0, sizeof(int) * (size_t)ntiles, stream));
+  // (a private histogram over one image's tiles per CTA, if it fits; see binning.cuh)
+  const bool private_hist = (int64_t)TY * TX <= BIN_MAX_TILES;
+  const size_t hist_bytes = sizeof(int) * (size_t)TY * TX;
   if (P > 0) {
-    points_setup_count_kernel<<<(unsigned)((P + SETUP_POINTS - 1) / SETUP_POINTS), SETUP_POINTS, 0, stream>>>(
-        points, radius, P, first, num, N, H, W, TY, TX, rx, ry, ws.rect, ws.tile_count, prec);
+    if (private_hist)
+      points_setup_count_private_kernel<<<(unsigned)((P + BIN_CHUNK - 1) / BIN_CHUNK), 256, hist_bytes, stream>>>(
+          points, radius, P, first, num, N, H, W, TY, TX, rx, ry, ws.rect, ws.tile_count, prec);
+    else
+      points_setup_count_kernel<<<(unsigned)((P + SETUP_POINTS - 1) / SETUP_POINTS), SETUP_POINTS, 0, stream>>>(
+          points, radius, P, first, num, N, H, W, TY, TX, rx, ry, ws.rect, ws.tile_count, prec);
     B200R_LAUNCHED("points_setup_count_kernel");
   }
   B200R_CUDA_OK(launch_chained(tile_scan_kernel, dim3(1), dim3(1024), 0, stream, ws.tile_count, ws.tile_offset,
                                (int)ntiles));
   B200R_LAUNCHED("tile_scan_kernel");
   if (P > 0) {
-    B200R_CUDA_OK(launch_chained(tile_fill_kernel<false>, dim3((unsigned)((P + 255) / 256)), dim3(256), 0, stream,
-                                 ws.rect, P, TY, TX, ws.tile_count, ws.pairs, ws.capacity));
+    if (private_hist)
+      B200R_CUDA_OK(launch_chained(tile_fill_private_kernel, dim3((unsigned)((P + BIN_CHUNK - 1) / BIN_CHUNK)), dim3(256),
+                                   hist_bytes, stream, ws.rect, P, TY, TX, ws.tile_count, ws.pairs, ws.capacity));
+    else
+      B200R_CUDA_OK(launch_chained(tile_fill_kernel<false>, dim3((unsigned)((P + 255) / 256)), dim3(256), 0, stream,
+                                   ws.rect, P, TY, TX, ws.tile_count, ws.pairs, ws.capacity));
     B200R_LAUNCHED("tile_fill_kernel");
   }
   // (no sort launch: every fine CTA puts its own tile list in ascending point order, see cta_sort256)

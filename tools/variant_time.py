@@ -11,8 +11,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "tools", "_variants")
-VARIANTS = {"round1": None, "base": [], "nowatch": ["-DB200R_EXP_NOWATCH"], "noearlyz": ["-DB200R_EXP_NOEARLYZ"],
-            "nowatch_noearlyz": ["-DB200R_EXP_NOWATCH", "-DB200R_EXP_NOEARLYZ"]}
+VARIANTS = {"oldwalk": ["-DB200R_EXP_OLDWALK"]}
+if len(sys.argv) > 2:  # python tools/variant_time.py build name=-DFLAG,-DFLAG2 ...
+    VARIANTS = {a.split("=")[0]: [f for f in a.split("=")[1].split(",") if f] for a in sys.argv[2:]}
 
 if len(sys.argv) > 1 and sys.argv[1] == "build":
     from pytorch3d_b200 import build as b
