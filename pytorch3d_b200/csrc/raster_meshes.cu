@@ -178,8 +178,10 @@ __device__ __forceinline__ void flag_tie();
 template <bool WATCH>
 __device__ __forceinline__ bool eval_pixel_face(float px, float py, const Face& f, float den, float blur_radius,
                                                 bool persp, bool clip, bool full, float max_z, Hit& h) {
-  float w0, w1, w2;
-  bary_coords(px, py, f, den, w0, w1, w2);
+  const float e0 = edge_fn(px, py, f.x1, f.y1, f.x2, f.y2);
+  const float e1 = edge_fn(px, py, f.x2, f.y2, f.x0, f.y0);
+  const float e2 = edge_fn(px, py, f.x0, f.y0, f.x1, f.y1);
+  float w0 = fdiv(e0, den), w1 = fdiv(e1, den), w2 = fdiv(e2, den);  // BarycentricCoordsForward
   if (persp) bary_persp(w0, w1, w2, f.z0, f.z1, f.z2);
   float c0 = w0, c1 = w1, c2 = w2;
   if (clip) bary_clip(c0, c1, c2);
@@ -759,8 +761,12 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
       //      leaves the candidates of every pixel in ascending face order.  (Measured on the NS workload:
       //      1x2 / 1x4 lanes per face 186 us, 2x2 200 us, 4x4 215 us, 8x2 270 us -- the loop-invariant part of a
       //      face is amortised over more pixels with fewer lanes.)
-      const int dr = tid & 3;
-      for (int fslot = tid >> 2; fslot < nc; fslot += TILE_THREADS / 4) {
+#ifndef B200R_SCAN_LANES
+#define B200R_SCAN_LANES 4  // lanes per face (timing experiments: 1, 2)
+#endif
+      constexpr int SL = B200R_SCAN_LANES;
+      const int dr = tid & (SL - 1);
+      for (int fslot = tid / SL; fslot < nc; fslot += TILE_THREADS / SL) {
         const unsigned rg = sh.rng[fslot];
         const int c_lo = rg & 255, c_hi = (rg >> 8) & 255, r_lo = (rg >> 16) & 255, r_hi = rg >> 24;
         if (c_lo > c_hi) continue;
@@ -773,7 +779,7 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
         const float dx0 = fsub(fb.x, fa.z), dy0 = fsub(fb.y, fa.w);  // v2 - v1
         const float dx1 = fsub(fa.x, fb.x), dy1 = fsub(fa.y, fb.y);  // v0 - v2
         const float dx2 = fsub(fa.z, fa.x), dy2 = fsub(fa.w, fa.y);  // v1 - v0
-        for (int r = r_lo + dr; r <= r_hi; r += 4) {
+        for (int r = r_lo + dr; r <= r_hi; r += SL) {
           const float qy = sh.row[r];
           const float t0 = fmul(fsub(qy, fa.w), dx0), t1 = fmul(fsub(qy, fb.y), dx1), t2 = fmul(fsub(qy, fa.y), dx2);
           unsigned* mpix = mrow + (r >> 2) * 64 + (r & 3) * 8;  // thread of pixel (r, c): + (c / 8) * 32 + c % 8
@@ -824,7 +830,9 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
       continue;  // chunk done
     }
     const float px = sh.col[lc], py = sh.row[lr];
-    const bool cull_depth = clip || !persp;
+    // (worth its ~80 instructions per face and warp only where a pixel has far more candidates than queue slots: long
+    // tile lists -- config 5: 2300 faces per tile, 13.0 -> 9.1 ms; north-star batch with blur 1e-4: none culled, +3 %)
+    const bool cull_depth = (clip || !persp) && count >= 512;
     // extent of the warp's footprint (pixel centres are monotonic in the pixel index)
     const float fc0 = sh.col[lc & 8], fc1 = sh.col[(lc & 8) + 7], fr0 = sh.row[lr & 12], fr1 = sh.row[(lr & 12) + 3];
     const float cmin = fminf(fc0, fc1), cmax = fmaxf(fc0, fc1), rmin = fminf(fr0, fr1), rmax = fmaxf(fr0, fr1);

@@ -105,12 +105,13 @@ __global__ void __launch_bounds__(256)
 // One staged chunk of points.
 struct __align__(16) PointStage {
   union {
-    float4 box[PCHUNK];           // xmin, xmax, ymin, ymax (empty = never hit)
-    int sort_buf[2 * TILE_THREADS];  // exchange buffers of cta_sort256 (before the chunk is staged)
+    unsigned mask[PCHUNK / 32][TILE_THREADS];         // per pixel (thread): one bit per staged point that covers it
+    int sort_buf[2 * TILE_THREADS];                   // exchange buffers of cta_sort256 (before the chunk is staged)
     unsigned long long sort_buf64[2 * TILE_THREADS];  // ... of cta_sort256_u64
   } u;
-  float4 rec[PCHUNK];  // x, y, z, r^2
+  float4 rec[PCHUNK];  // x, y, z, r^2 (z < 0: never drawn)
   int id[PCHUNK];
+  float col[TILE], row[TILE];  // NDC coordinates of the tile's 16 pixel columns / rows
   int tie;  // points_fine_smem_kernel: some pixel saw a depth tie during an arrival-order walk (flag_point_tie)
 };
 
@@ -139,14 +140,6 @@ struct PointFineParams {
 
 __device__ __forceinline__ void stage_point(PointStage& s, int slot, const float4* __restrict__ prec, int pi) {
   const float4 r = __ldg(prec + pi);
-  float xmin = FLT_MAX, xmax = -FLT_MAX, ymin = FLT_MAX, ymax = -FLT_MAX;
-  if (!(r.z < 0.0f)) {  // points behind the camera are not rendered (rasterize_points.cu:55-56)
-    xmin = fsub(r.x, r.w);
-    xmax = fadd(r.x, r.w);
-    ymin = fsub(r.y, r.w);
-    ymax = fadd(r.y, r.w);
-  }
-  s.u.box[slot] = make_float4(xmin, xmax, ymin, ymax);
   s.rec[slot] = make_float4(r.x, r.y, r.z, fmul(r.w, r.w));
   s.id[slot] = pi;
 }
@@ -162,25 +155,95 @@ __device__ __forceinline__ int thread_of_pixel(int r, int c) {
   return ((r >> 2) * 2 + (c >> 3)) * 32 + (r & 3) * 8 + (c & 7);
 }
 
-// The tile body shared by the point kernels: sort the tile's list, stage it chunk by chunk, box-test (pass A: one
-// lane per point against the warp's footprint + bit-matrix transpose, see raster_meshes.cu) and offer every hit
-// to `offer(z, point, dist2)` in ascending point order.
+// Candidates of one staged chunk.  Every staged point is scan-converted by one thread: the pixels of the tile that can
+// lie inside its disc are a small rectangle (pixel_range: the inverse pixel-centre map, a superset), each is tested
+// with the reference's arithmetic -- CheckPixelInsidePoint (rasterize_points.cu:49-60): dist2 = fma(dy, dy, rn(dx*dx))
+// < rn(r*r), points with z < 0 are skipped -- and a pixel that passes gets the point's bit set in ITS mask
+// (mask[point / 32][pixel's thread]).  After one barrier every pixel walks its own mask: its hits, in staging order,
+// are offered to `offer(z, point, dist2)` (returns false to stop this pixel's walk).  The search costs ~(pixels in
+// the disc's box) per point instead of ~(points in the tile) per pixel: the former box test of every point against
+// every warp footprint (one lane per point, a 32x32 bit-matrix transpose per 32 points) was 45 % of the kernel.
+// Must be called by the whole CTA; ends with the chunk consumed by this thread (barrier before restaging).
+template <class Offer>
+__device__ __forceinline__ void points_chunk_scatter_walk(const PointFineParams& p, PointStage& s, int nc, int tile_x,
+                                                          int tile_y, bool valid, int lc, int lr, Offer offer) {
+  const int tid = threadIdx.x;
+  const int nwords = (nc + 31) >> 5;
+  // (called after the staging stores and before the barrier that publishes them: the masks are zeroed alongside)
+  for (int w = 0; w < nwords; ++w) s.u.mask[w][tid] = 0u;
+  __syncthreads();
+  if (tid < nc) {
+    const float4 r = s.rec[tid];
+    if (!(r.z < 0.0f)) {  // points behind the camera are not rendered (rasterize_points.cu:55-56)
+      const float rad = sqrtf(r.w) * (1.0f + 1e-6f);  // (r.w = rn(r*r); only the conservative range needs the radius)
+      int ix_lo, ix_hi, iy_lo, iy_hi;
+      pixel_range(r.x - rad, r.x + rad, p.W, p.rx, ix_lo, ix_hi);
+      pixel_range(r.y - rad, r.y + rad, p.H, p.ry, iy_lo, iy_hi);
+      // output pixel xo = W - 1 - xi; tile-local column c = xo - tile_x * TILE
+      const int c_lo = max(p.W - 1 - ix_hi - tile_x * TILE, 0), c_hi = min(p.W - 1 - ix_lo - tile_x * TILE, TILE - 1);
+      const int r_lo = max(p.H - 1 - iy_hi - tile_y * TILE, 0), r_hi = min(p.H - 1 - iy_lo - tile_y * TILE, TILE - 1);
+      unsigned* mrow = s.u.mask[tid >> 5];
+      const unsigned bit = 1u << (tid & 31);
+      for (int rr = r_lo; rr <= r_hi; ++rr) {
+        const float dy = fsub(s.row[rr], r.y);
+        unsigned* mpix = mrow + (rr >> 2) * 64 + (rr & 3) * 8;  // thread of pixel (rr, c): + (c / 8) * 32 + c % 8
+        for (int c = c_lo; c <= c_hi; ++c) {
+          const float dx = fsub(s.col[c], r.x);
+          if (ffma(dy, dy, fmul(dx, dx)) < r.w) atomicOr(mpix + (c >> 3) * 32 + (c & 7), bit);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (!valid) return;
+  const float px = s.col[lc], py = s.row[lr];
+  int w = 0;
+  unsigned m = nwords > 0 ? s.u.mask[0][tid] : 0u;  // (an empty tile has no mask words)
+  for (;;) {  // (every lane advances through its own words: see the mesh kernel's walk)
+    while (m == 0u && ++w < nwords) m = s.u.mask[w][tid];
+    if (m == 0u) break;
+    const int j = w * 32 + __ffs((int)m) - 1;
+    m &= m - 1u;
+    const float4 r = s.rec[j];
+    const float dx = fsub(px, r.x), dy = fsub(py, r.y);
+    if (!offer(r.z, s.id[j], sqnorm2(dx, dy))) break;
+  }
+}
+
+// NDC coordinates of the tile's pixel columns and rows (two IEEE divisions each), computed once per tile by 32
+// threads; published by the first barrier of the first chunk.
+__device__ __forceinline__ void points_tile_coords(const PointFineParams& p, PointStage& s, int tile_x, int tile_y) {
+  const int tid = threadIdx.x;
+  if (tid < 2 * TILE) {
+    const int i = tid & (TILE - 1);
+    if (tid < TILE)
+      s.col[i] = pix_to_ndc(p.W - 1 - (tile_x * TILE + i), p.W, p.rx);
+    else
+      s.row[i] = pix_to_ndc(p.H - 1 - (tile_y * TILE + i), p.H, p.ry);
+  }
+}
+
+// The tile body shared by the point kernels: stage the tile's list chunk by chunk and offer every pixel's hits to
+// `offer(z, point, dist2)`.
 // `sort_list`: put the tile's list in ascending point order first (the order of the reference's naive kernel,
 // rasterize_points.cu:128); without it the points are offered in arrival order (see points_fine_smem_kernel).
 // Returns true if the walk was in ascending order (sorted, or an overflowed tile walking the cloud itself).
 template <class Offer>
 __device__ __forceinline__ bool points_tile_body(const PointFineParams& p, PointStage& s, int* smem_ints_base,
-                                                 int tile, int n, bool valid, float px, float py, bool sort_list,
-                                                 Offer offer) {
-  const int tid = threadIdx.x, lane = tid & 31;
+                                                 int tile_x, int tile_y, int n, bool valid, int lc, int lr,
+                                                 bool sort_list, Offer offer) {
+  const int tid = threadIdx.x;
   pdl_wait();  // the tile lists (fill kernel) and, transitively, the point records are complete (see common.cuh)
+  const int tile = (n * p.TY + tile_y) * p.TX + tile_x;
   const int seg_begin = p.tile_offset[tile], seg_end = p.tile_offset[tile + 1];
   const bool overflow = (int64_t)seg_end > p.capacity || seg_end == INT_MAX;
   const int64_t cloud_first = p.first[n];
   const int count = overflow ? (int)p.num[n] : seg_end - seg_begin;
   const bool sort_staged = sort_list && !overflow && count <= PCHUNK;
-  if (sort_list && !overflow && count > PCHUNK) cta_sort_segment(p.pairs + seg_begin, count, smem_ints_base, p.smem_ints);
-
+  if (sort_list && !overflow && count > PCHUNK) {
+    cta_sort_segment(p.pairs + seg_begin, count, smem_ints_base, p.smem_ints);
+    points_tile_coords(p, s, tile_x, tile_y);  // (the long-list sort may have used the whole stage as scratch)
+  }
   for (int base = 0; base < count; base += PCHUNK) {
     const int nc = min(PCHUNK, count - base);
     if (base > 0) __syncthreads();  // previous chunk fully consumed
@@ -188,38 +251,10 @@ __device__ __forceinline__ bool points_tile_body(const PointFineParams& p, Point
     if (tid < nc) pi = overflow ? (int)(cloud_first + base + tid) : p.pairs[seg_begin + base + tid];
     if (sort_staged) {
       pi = cta_sort256(pi, nc, s.u.sort_buf);
-      if (nc > 32) __syncthreads();  // the exchange buffers alias the boxes written next
+      if (nc > 32) __syncthreads();  // the exchange buffers alias the masks zeroed next
     }
     if (tid < nc) stage_point(s, tid, p.prec, pi);
-    __syncthreads();
-    for (int sub = 0; sub < nc; sub += 64) {
-      // pass A: 64-bit mask of the points of this round whose box contains my pixel
-      unsigned m0 = 0, m1 = 0;
-      {
-        float col[8], row[4];  // the footprint's 8 column and 4 row coordinates (lane = row * 8 + column)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) col[c] = __shfl_sync(0xffffffffu, px, c);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) row[r] = __shfl_sync(0xffffffffu, py, 8 * r);
-        if (sub + lane < nc) m0 = box_pixel_mask(s.u.box[sub + lane], col, row);
-        if (sub + 32 + lane < nc) m1 = box_pixel_mask(s.u.box[sub + 32 + lane], col, row);
-      }
-      m0 = warp_transpose_bits(m0, lane);
-      if (sub + 32 < nc) m1 = warp_transpose_bits(m1, lane);
-      unsigned long long mine = valid ? (((unsigned long long)m1 << 32) | m0) : 0ull;
-      // pass B: every lane tests and queues its own candidates, in ascending point order
-      while (__any_sync(0xffffffffu, mine != 0ull)) {
-        if (mine == 0ull) continue;
-        const int j = sub + __ffsll((long long)mine) - 1;
-        mine &= mine - 1ull;
-        const float4 r = s.rec[j];
-        // CheckPixelInsidePoint (rasterize_points.cu:49-60): dist2 = fma(dy, dy, rn(dx*dx)) < rn(r*r)
-        const float dx = fsub(px, r.x), dy = fsub(py, r.y);
-        const float d2 = sqnorm2(dx, dy);
-        if (r.z < 0.0f || !(d2 < r.w)) continue;
-        offer(r.z, s.id[j], d2);
-      }
-    }
+    points_chunk_scatter_walk(p, s, nc, tile_x, tile_y, valid, lc, lr, offer);
   }
   return sort_list || overflow || count <= 1;
 }
@@ -231,65 +266,38 @@ __device__ __forceinline__ bool points_tile_body(const PointFineParams& p, Point
 // of a pixel's hits share a depth bit for bit (their order then depends on the reference's queue history): such a hit
 // raises the tile's tie flag and the caller falls back to the literal queue on the index-sorted list.
 __device__ __forceinline__ int points_tile_walk_by_depth(const PointFineParams& p, PointStage& s, int seg_begin,
-                                                          int count, bool valid, float px, float py, float* qz, int* qi,
-                                                          float* qd) {
-  const int tid = threadIdx.x, lane = tid & 31;
+                                                          int count, int tile_x, int tile_y, bool valid, int lc, int lr,
+                                                          float* qz, int* qi, float* qd) {
+  const int tid = threadIdx.x;
   const int K = p.K;
-  unsigned long long key = ~0ull;  // threads without a point, points behind the camera: sorted to the end, never staged
+  unsigned long long key = ~0ull;  // threads without a point, points behind the camera: sorted to the end
+  int pi = -1;
   if (tid < count) {
-    const int pi = p.pairs[seg_begin + tid];
+    pi = p.pairs[seg_begin + tid];
     const float z = __ldg(reinterpret_cast<const float*>(p.prec + pi) + 2);
     // (z >= 0: the bits are ordered like the values; -0 + 0 = +0)
     if (!(z < 0.0f)) key = ((unsigned long long)__float_as_uint(fadd(z, 0.0f)) << 32) | (unsigned)pi;
   }
   key = cta_sort256_u64(key, count, s.u.sort_buf64);
-  if (count > 32) __syncthreads();  // the exchange buffers alias the boxes written next
+  if (count > 32) __syncthreads();  // the exchange buffers alias the masks zeroed next
   if (tid < count) {
     if (key != ~0ull)
       stage_point(s, tid, p.prec, (int)(unsigned)(key & 0xffffffffull));
     else
-      s.u.box[tid] = make_float4(FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX);
+      s.rec[tid] = make_float4(0.0f, 0.0f, -1.0f, 0.0f);  // (z < 0: never drawn)
   }
-  __syncthreads();
   int size = 0;
   float last_z = -1.0f;
-  bool done = !valid;
-  for (int sub = 0; sub < count; sub += 64) {
-    if (__all_sync(0xffffffffu, done)) break;  // every pixel of the footprint has its K nearest
-    unsigned m0 = 0, m1 = 0;
-    {
-      float col[8], row[4];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) col[c] = __shfl_sync(0xffffffffu, px, c);
-#pragma unroll
-      for (int r = 0; r < 4; ++r) row[r] = __shfl_sync(0xffffffffu, py, 8 * r);
-      if (sub + lane < count) m0 = box_pixel_mask(s.u.box[sub + lane], col, row);
-      if (sub + 32 + lane < count) m1 = box_pixel_mask(s.u.box[sub + 32 + lane], col, row);
-    }
-    m0 = warp_transpose_bits(m0, lane);
-    if (sub + 32 < count) m1 = warp_transpose_bits(m1, lane);
-    unsigned long long mine = done ? 0ull : (((unsigned long long)m1 << 32) | m0);
-    while (__any_sync(0xffffffffu, mine != 0ull)) {
-      if (mine == 0ull) continue;
-      const int j = sub + __ffsll((long long)mine) - 1;
-      mine &= mine - 1ull;
-      const float4 r = s.rec[j];
-      const float dx = fsub(px, r.x), dy = fsub(py, r.y);
-      const float d2 = sqnorm2(dx, dy);  // CheckPixelInsidePoint (rasterize_points.cu:49-60)
-      if (!(d2 < r.w)) continue;
-      if (r.z == last_z || r.z != r.z) flag_point_tie();  // equal depths (or NaN): the literal queue decides
-      if (size < K) {
-        qz[size * QSTRIDE] = r.z;
-        qi[size * QSTRIDE] = s.id[j];
-        qd[size * QSTRIDE] = d2;
-        last_z = r.z;
-        ++size;
-      } else {  // the first hit beyond the K nearest: nothing farther can matter
-        mine = 0ull;
-        done = true;
-      }
-    }
-  }
+  points_chunk_scatter_walk(p, s, count, tile_x, tile_y, valid, lc, lr, [&](float pz, int id, float d2) {
+    if (pz == last_z || pz != pz) flag_point_tie();  // equal depths (or NaN): the literal queue decides
+    if (size == K) return false;  // the first hit beyond the K nearest: nothing farther can matter
+    qz[size * QSTRIDE] = pz;
+    qi[size * QSTRIDE] = id;
+    qd[size * QSTRIDE] = d2;
+    last_z = pz;
+    ++size;
+    return true;
+  });
   return size;
 }
 
@@ -316,8 +324,8 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_smem_kernel(const Po
   int xo, yo;
   pthread_pixel(tile_x, tile_y, xo, yo);
   const bool valid = xo < p.W && yo < p.H;
-  const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
-  const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
+  const int lc = xo - tile_x * TILE, lr = yo - tile_y * TILE;  // local column / row of my pixel
+  points_tile_coords(p, s, tile_x, tile_y);
   pdl_wait();  // the tile lists (fill kernel) and, transitively, the point records are complete (see common.cuh)
 
   // Order of the list: the queue keeps the K nearest points whatever the arrival order unless two points share,
@@ -338,7 +346,8 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_smem_kernel(const Po
     max_z = -1000.0f;
     if (tid == 0 && !sort_list) s.tie = 0;  // (ordered before every offer by the barriers of the tile body)
     if (attempt == 0) {
-      size = points_tile_walk_by_depth(p, s, seg_begin0, seg_end0 - seg_begin0, valid, px, py, qz, qi, qd);
+      size = points_tile_walk_by_depth(p, s, seg_begin0, seg_end0 - seg_begin0, tile_x, tile_y, valid, lc, lr, qz, qi,
+                                       qd);
       if (!p.vec_ok) {
         if (__syncthreads_or(s.tie)) continue;
         if (!valid) return;
@@ -360,7 +369,8 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_smem_kernel(const Po
       continue;
     }
     const bool in_order = points_tile_body(
-        p, s, reinterpret_cast<int*>(smem_raw), tile, n, valid, px, py, sort_list, [&](float pz, int pi, float d2) {
+        p, s, reinterpret_cast<int*>(smem_raw), tile_x, tile_y, n, valid, lc, lr, sort_list,
+        [&](float pz, int pi, float d2) {
           if (size < K) {  // (:61-67)
             qz[size * QSTRIDE] = pz;
             qi[size * QSTRIDE] = pi;
@@ -387,6 +397,7 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_smem_kernel(const Po
           } else if (pz == max_z) {
             flag_point_tie();
           }
+          return true;
         });
     // BubbleSort on z only (rasterize_points.cu:26-28): stable -> insertion sort over the thread's own column
     for (int i = 1; i < size; ++i) {
@@ -458,17 +469,17 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_bigk_kernel(const Po
   __shared__ PointStage s;
   const int K = p.K;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = p.n0 + blockIdx.z;
-  const int tile = (n * p.TY + tile_y) * p.TX + tile_x;
   int xo, yo;
   pthread_pixel(tile_x, tile_y, xo, yo);
   const bool valid = xo < p.W && yo < p.H;
-  const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
-  const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
+  const int lc = xo - tile_x * TILE, lr = yo - tile_y * TILE;
+  points_tile_coords(p, s, tile_x, tile_y);
   float lz[B200R_MAX_K], ld[B200R_MAX_K];
   int li[B200R_MAX_K];
   int ln = 0, l_max_idx = -1;
   float l_max_z = -1000.0f;
-  points_tile_body(p, s, reinterpret_cast<int*>(&s), tile, n, valid, px, py, true, [&](float pz, int pi, float d2) {
+  points_tile_body(p, s, reinterpret_cast<int*>(&s), tile_x, tile_y, n, valid, lc, lr, true,
+                   [&](float pz, int pi, float d2) {
     if (ln < K) {
       lz[ln] = pz;
       li[ln] = pi;
@@ -489,6 +500,7 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_bigk_kernel(const Po
           l_max_idx = i;
         }
     }
+    return true;
   });
   if (!valid) return;
   for (int i = 1; i < ln; ++i) {  // stable insertion sort on z only
