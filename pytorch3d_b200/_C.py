@@ -6,7 +6,8 @@ in pytorch3d/csrc/ext.cpp:53-56:
     rasterize_meshes, rasterize_meshes_backward, rasterize_points, rasterize_points_backward
 
 implemented by calling the C ABI of libb200raster.so (include/b200_raster.h) on the tensors' device
-pointers and the current CUDA stream.  PyTorch is used only for device memory and streams.
+pointers and the current CUDA stream -- through the torch C++ extension csrc/torch_ext.cpp (the binding the reference
+uses) or, for the ops it does not cover, through ctypes.  PyTorch is used only for device memory and streams.
 There is no CPU path: CPU tensors raise RuntimeError, like a CUDA-less build of the reference does
 for CUDA tensors (rasterize_meshes.h:137-139, mirrored).
 """
@@ -22,6 +23,38 @@ kMaxPointsPerPixel = 150  # rasterization_utils.cuh:48
 # tiles whose list does not fit fall back to testing every element of their mesh / cloud.  Tests lower it
 # to exercise that path.
 PAIR_CAPACITY = 0
+
+
+# The hot ops go through the torch C++ extension over the C ABI (csrc/torch_ext.cpp, built by
+# `python -m pytorch3d_b200.build` next to libb200raster.so) -- the same kind of binding `pytorch3d._C` is (ext.cpp:53-56).
+# Without it (library built alone) they call the C ABI through ctypes; both run the same kernels of the same library.
+_EXT = None
+_EXT_TRIED = False
+USE_EXT = True  # tests switch it off to exercise the ctypes binding of the same entry points
+
+
+def _ext():
+    global _EXT, _EXT_TRIED
+    if not USE_EXT:
+        return None
+    if not _EXT_TRIED:
+        _EXT_TRIED = True
+        import importlib.util
+        import os
+        from . import build as _build
+        path = _build.ext_path()
+        if os.path.exists(path):
+            _lib.load()  # fails loudly if libb200raster.so itself is missing
+            spec = importlib.util.spec_from_file_location(_build.EXT_NAME, path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            _EXT = mod
+    return _EXT
+
+
+def binding():
+    """'torch-extension' or 'ctypes': which binding of the C ABI the hot ops use in this process."""
+    return "torch-extension" if _ext() is not None else "ctypes"
 
 
 def _ptr(t):
@@ -76,6 +109,14 @@ def rasterize_meshes(
     dev = _require_cuda(("face_verts", face_verts), ("mesh_to_faces_packed_first_idx", mesh_to_face_first_idx),
                         ("num_faces_per_mesh", num_faces_per_mesh),
                         ("clipped_faces_neighbor_idx", clipped_faces_neighbor_idx))
+    ext = _ext()
+    if ext is not None:
+        tagged = getattr(clipped_faces_neighbor_idx, "_b200_all_minus_one", False)
+        return ext.rasterize_meshes(face_verts, mesh_to_face_first_idx, num_faces_per_mesh,
+                                    None if tagged else clipped_faces_neighbor_idx,
+                                    (int(image_size[0]), int(image_size[1])), float(blur_radius), int(faces_per_pixel),
+                                    int(bin_size), int(max_faces_per_bin), bool(perspective_correct),
+                                    bool(clip_barycentric_coords), bool(cull_backfaces), int(PAIR_CAPACITY))
     lib = _lib.load()
     H, W = int(image_size[0]), int(image_size[1])
     K = int(faces_per_pixel)
@@ -128,6 +169,10 @@ def rasterize_meshes_backward(
         raise RuntimeError(
             "RasterizeMeshesBackwardCuda does not have a deterministic implementation, but you set "
             "'torch.use_deterministic_algorithms(True)'.")
+    ext = _ext()
+    if ext is not None:
+        return ext.rasterize_meshes_backward(face_verts, pix_to_face, grad_zbuf, grad_bary, grad_dists,
+                                             bool(perspective_correct), bool(clip_barycentric_coords))
     lib = _lib.load()
     N, H, W, K = (int(s) for s in pix_to_face.shape)
     F = int(face_verts.shape[0])
@@ -175,6 +220,12 @@ def rasterize_meshes_indexed(
     dev = _require_cuda(("verts_packed", verts_packed), ("faces_packed", faces_packed),
                         ("mesh_to_faces_packed_first_idx", mesh_to_face_first_idx),
                         ("num_faces_per_mesh", num_faces_per_mesh))
+    ext = _ext()
+    if ext is not None:
+        return ext.rasterize_meshes_indexed(verts_packed, faces_packed, mesh_to_face_first_idx, num_faces_per_mesh,
+                                            (int(image_size[0]), int(image_size[1])), float(blur_radius),
+                                            int(faces_per_pixel), bool(perspective_correct),
+                                            bool(clip_barycentric_coords), bool(cull_backfaces), int(PAIR_CAPACITY))
     lib = _lib.load()
     H, W = int(image_size[0]), int(image_size[1])
     K = int(faces_per_pixel)
@@ -222,6 +273,11 @@ def rasterize_meshes_backward_indexed(
         raise RuntimeError(
             "RasterizeMeshesBackwardCuda does not have a deterministic implementation, but you set "
             "'torch.use_deterministic_algorithms(True)'.")
+    ext = _ext()
+    if ext is not None:
+        return ext.rasterize_meshes_backward_indexed(face_verts, faces_packed, int(num_verts), pix_to_face, grad_zbuf,
+                                                     grad_bary, grad_dists, bool(perspective_correct),
+                                                     bool(clip_barycentric_coords))
     lib = _lib.load()
     N, H, W, K = (int(s) for s in pix_to_face.shape)
     F, V = int(face_verts.shape[0]), int(num_verts)
@@ -264,6 +320,11 @@ def rasterize_points(
         raise RuntimeError("expected scalar type Float")
     dev = _require_cuda(("points", points), ("cloud_to_packed_first_idx", cloud_to_packed_first_idx),
                         ("num_points_per_cloud", num_points_per_cloud), ("radius", radius))
+    ext = _ext()
+    if ext is not None:
+        return ext.rasterize_points(points, cloud_to_packed_first_idx, num_points_per_cloud,
+                                    (int(image_size[0]), int(image_size[1])), radius, int(points_per_pixel),
+                                    int(bin_size), int(max_points_per_bin), int(PAIR_CAPACITY))
     lib = _lib.load()
     H, W = int(image_size[0]), int(image_size[1])
     K = int(points_per_pixel)
@@ -297,6 +358,9 @@ def rasterize_points_backward(points: torch.Tensor, idxs: torch.Tensor, grad_zbu
         raise RuntimeError(
             "RasterizePointsBackwardCuda does not have a deterministic implementation, but you set "
             "'torch.use_deterministic_algorithms(True)'.")
+    ext = _ext()
+    if ext is not None:
+        return ext.rasterize_points_backward(points, idxs, grad_zbuf, grad_dists)
     lib = _lib.load()
     N, H, W, K = (int(s) for s in idxs.shape)
     P = int(points.shape[0])

@@ -56,3 +56,28 @@ def test_sass_contains_tma_bulk_copy(built_lib):
     sass = subprocess.run([cuobjdump, "-sass", built_lib], stdout=subprocess.PIPE, text=True).stdout
     assert "UBLKCP" in sass
     assert "sm_100a" in sass or "SM100" in sass.upper() or "EF_CUDA_SM100" in sass
+
+
+def test_torch_extension_binding_loads_and_mirrors_the_reference_ops(built_lib):
+    """csrc/torch_ext.cpp: the pybind11 / torch C++ extension over the C ABI (the binding pytorch3d/csrc/ext.cpp:53-56
+    is for the reference) is built next to the library, loads on a CPU-only machine and exports the four ops of the path
+    (+ the fused indexed pair); like a CUDA-less build of the reference it raises RuntimeError for CPU tensors."""
+    import pytest
+    import torch
+    from pytorch3d_b200 import _C, build
+    build.build_ext()
+    assert _C.binding() == "torch-extension"
+    ext = _C._ext()
+    for name in ("rasterize_meshes", "rasterize_meshes_backward", "rasterize_points", "rasterize_points_backward",
+                 "rasterize_meshes_indexed", "rasterize_meshes_backward_indexed"):
+        assert callable(getattr(ext, name))
+    fv = torch.zeros(2, 3, 3)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        ext.rasterize_meshes(fv, torch.zeros(1, dtype=torch.int64), torch.tensor([2]), None, (8, 8), 0.0, 2, 0, 0, False,
+                             False, False)
+    with pytest.raises(RuntimeError, match=r"face_verts must have dimensions \(num_faces, 3, 3\)"):
+        ext.rasterize_meshes(torch.zeros(2, 3), torch.zeros(1, dtype=torch.int64), torch.tensor([2]), None, (8, 8), 0.0,
+                             2, 0, 0, False, False, False)
+    with pytest.raises(RuntimeError, match="Must have points_per_pixel <= 150"):
+        ext.rasterize_meshes(fv, torch.zeros(1, dtype=torch.int64), torch.tensor([2]), None, (8, 8), 0.0, 151, 0, 0,
+                             False, False, False)

@@ -287,3 +287,43 @@ def test_blur_and_k16_north_star_variants(ops, dev, ref_cuda):
         r = ref_cuda.rasterize_meshes(fv, first, num, _minus_one(fv.shape[0], dev, tagged=False), (512, 512), blur, K,
                                       32, 14000, False, False, False)
         _assert_equal_up_to_ties(mine, r, "ns blur=%g K=%d vs reference CUDA" % (blur, K), max_tie_pixels=2e-2)
+
+
+def test_both_bindings_of_the_c_abi_agree(ops, dev):
+    """The hot ops through the torch C++ extension (csrc/torch_ext.cpp, the default) and through ctypes: same library,
+    same kernels -- forward outputs bit-identical, gradients equal up to the order of the atomic additions; and the
+    extension's error behaviour mirrors the reference ops (RuntimeError)."""
+    from pytorch3d_b200 import build
+    build.build_ext()
+    assert ops.binding() == "torch-extension", "the torch extension must be the binding in use on a GPU box"
+    fv, first, num = rand_faces(3000, 2, seed=3)
+    fv, first, num = fv.to(dev), first.to(dev), num.to(dev)
+    pts, pfirst, pnum, rad = (t.to(dev) for t in rand_points(4000, 2, seed=5))
+    nb_plain = _minus_one(fv.shape[0], dev, tagged=False)
+    results = {}
+    for use_ext in (True, False):
+        ops.USE_EXT = use_ext
+        try:
+            assert ops.binding() == ("torch-extension" if use_ext else "ctypes")
+            out = {}
+            for name, nb in (("tagged", _minus_one(fv.shape[0], dev)), ("plain", nb_plain)):
+                f = ops.rasterize_meshes(fv, first, num, nb, (48, 64), 1e-3, 5, 0, 0, True, True, False)
+                g = upstream([tuple(t.shape) for t in f[1:]])
+                out[name] = (f, ops.rasterize_meshes_backward(fv, f[0], g[0].to(dev), g[1].to(dev), g[2].to(dev), True,
+                                                              True))
+            p = ops.rasterize_points(pts, pfirst, pnum, (40, 56), rad, 6, 0, 0)
+            gp = upstream([tuple(t.shape) for t in p[1:]])
+            out["points"] = (p, ops.rasterize_points_backward(pts, p[0], gp[0].to(dev), gp[1].to(dev)))
+            results[use_ext] = out
+            with pytest.raises(RuntimeError, match="face_verts must have dimensions"):
+                ops.rasterize_meshes(fv[:, :2], first, num, nb_plain, (8, 8), 0.0, 2, 0, 0, False, False, False)
+            with pytest.raises(RuntimeError, match="CUDA tensor"):
+                ops.rasterize_points(pts.cpu(), pfirst, pnum, (8, 8), rad, 2, 0, 0)
+        finally:
+            ops.USE_EXT = True
+    for key in ("tagged", "plain", "points"):
+        (fa, ga), (fb, gb) = results[True][key], results[False][key]
+        for a, b in zip(fa, fb):
+            assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b), key
+        assert torch.allclose(ga, gb, rtol=1e-4, atol=1e-5), key
+    assert torch.equal(results[True]["tagged"][0][0], results[True]["plain"][0][0])
