@@ -37,6 +37,7 @@ WORKLOADS = {
     "ns": (8, 187, 187, 512, 512, 8, 0.0),
     "c2": (8, 54, 54, 256, 256, 8, 1e-4),
     "ns_blur": (8, 187, 187, 512, 512, 8, 1e-4),
+    "ns_k16": (8, 187, 187, 512, 512, 16, 0.0),
     "c5": (1, 707, 707, 1024, 1024, 16, 1e-3),
     "tiny": (2, 24, 24, 64, 64, 4, 0.0),
 }
@@ -652,6 +653,7 @@ def other_workloads(dev, lib, peak):
     out = {}
     out["config2_meshes_8x5832_faces_256_K8_blur1e-4"] = _mesh_workload_numbers(dev, lib, peak, "c2")
     out["ns_blur1e-4"] = _mesh_workload_numbers(dev, lib, peak, "ns_blur")
+    out["ns_K16(shared-memory queue kernel)"] = _mesh_workload_numbers(dev, lib, peak, "ns_k16")
     out["config5_1M_faces_1024_K16_blur1e-3"] = _mesh_workload_numbers(dev, lib, peak, "c5", steps=3, warm=1)
     # config 3: 8 x 100k points, 512^2, K=10, r=0.01 -- rasterization alone, then with alpha_composite (4 channels)
     pc = synthetic.random_pointclouds(8, 100000, seed=0)

@@ -99,6 +99,9 @@ __global__ void __launch_bounds__(SETUP_FACES)
                             float sqrt_blur, int cull_backfaces, uint4* __restrict__ rect,
                             int* __restrict__ tile_count, float4* __restrict__ rec) {
   __shared__ __align__(16) float s_fv[SETUP_FACES * 9];
+#ifndef B200R_EXP_DIRECTREC
+  __shared__ __align__(16) float4 s_rec[SETUP_FACES * 4];
+#endif
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x;
   const int64_t f0 = (int64_t)blockIdx.x * SETUP_FACES;
@@ -148,7 +151,11 @@ __global__ void __launch_bounds__(SETUP_FACES)
     rect[fi] = make_uint4(r.x, r.y, (uint32_t)max(n, 0), 0u);
     // the reference reads the int64 neighbour index into an int (rasterize_meshes.cu:186)
     const int nb = neighbor ? (int)__ldg(neighbor + fi) : -1;
+#ifdef B200R_EXP_DIRECTREC
     float4* out = rec + fi * 4;
+#else
+    float4* out = s_rec + tid * 4;
+#endif
     out[0] = make_float4(f.x0, f.y0, f.x1, f.y1);
     out[1] = make_float4(f.x2, f.y2, bary_denominator(f), __int_as_float((int)fi));
     out[2] = make_float4(f.z0, f.z1, f.z2, __int_as_float(nb));
@@ -157,6 +164,13 @@ __global__ void __launch_bounds__(SETUP_FACES)
                                             __int_as_float(rng.w));
   }
   warp_count_rect(r, n, TY, TX, tile_count, tid & 31);  // all lanes participate
+#ifndef B200R_EXP_DIRECTREC
+  // the CTA's records are one contiguous block of the record array: written out with consecutive lanes on consecutive
+  // 16-byte pieces (whole sectors per instruction; per-thread stores at a 64-byte stride filled half of each sector)
+  __syncthreads();
+  float4* dst = rec + f0 * 4;
+  for (int e = tid; e < nf * 4; e += SETUP_FACES) dst[e] = s_rec[e];
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
