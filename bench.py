@@ -661,7 +661,8 @@ def other_workloads(dev, lib, peak):
     pf, pn = pc.cloud_to_packed_first_idx().to(dev), pc.num_points_per_cloud().to(dev)
     r = 0.01
     rad = torch.full((pts.shape[0],), r, device=dev)
-    feats = torch.rand(4, pts.shape[0], device=dev)
+    # (features_packed() is (P, C); the renderer hands its (C, P) view to the compositor, points/renderer.py:66-70)
+    feats = torch.rand(pts.shape[0], 4, device=dev).permute(1, 0)
     idx, zb, d2 = _C.rasterize_points(pts, pf, pn, (512, 512), rad, 10, 0, 0)
     g_img = torch.randn(8, 4, 512, 512, device=dev)
     g_z = torch.randn_like(zb)
@@ -689,7 +690,22 @@ def other_workloads(dev, lib, peak):
         _C.rasterize_points_backward(pts, i, g_z, gdd)
 
     ms = _time_ms(step_c3)
-    out["config3_points_8x100k_512_K10_r0.01_alpha_composite"] = {"ms_per_step": ms, "frames_per_s": 8e3 / ms}
+    out["config3_points_8x100k_512_K10_r0.01_alpha_composite"] = {
+        "ms_per_step": ms, "frames_per_s": 8e3 / ms,
+        "what": "rasterize_points + the reference renderer's chain (weights = 1 - d / r^2 in torch, idx.long(), permuted "
+                "views, accum_alphacomposite) forward + backward"}
+
+    def step_c3_fused():
+        i, z, d = _C.rasterize_points(pts, pf, pn, (512, 512), rad, 10, 0, 0)
+        _C.points_alpha_render(feats, i, d, r)
+        gf, gdd = _C.points_alpha_render_backward(g_img, feats, i, d, r)
+        _C.rasterize_points_backward(pts, i, g_z, gdd)
+
+    ms = _time_ms(step_c3_fused)
+    out["config3_points_8x100k_512_K10_r0.01_alpha_composite_fused"] = {
+        "ms_per_step": ms, "frames_per_s": 8e3 / ms,
+        "what": "rasterize_points + points_alpha_render (weights and compositing fused, on the rasterizer's own "
+                "layout) forward + backward; same images bit for bit"}
     return out
 
 

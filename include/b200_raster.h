@@ -177,6 +177,19 @@ int b200r_alpha_composite_backward(const float* grad_out, const float* features,
                                    const int64_t* idx_strides, int32_t N, int32_t K, int32_t H, int32_t W,
                                    float* grad_features, float* grad_alphas, void* stream);
 
+/* The same with the features addressed through element strides: feature (c, p) at features[c * stride_c + p * stride_p]
+ * (the renderer passes `features_packed().permute(1, 0)`, a (C,P) view of point-major memory); grad_features uses the
+ * same strides.  The two entry points above are the contiguous (C,P) case (stride_c = P, stride_p = 1). */
+int b200r_alpha_composite_forward_strided(const float* features, int64_t C, int64_t P, int64_t feature_stride_c,
+                                          int64_t feature_stride_p, const float* alphas, const int64_t* alpha_strides,
+                                          const int64_t* points_idx, const int64_t* idx_strides, int32_t N, int32_t K,
+                                          int32_t H, int32_t W, float* result, void* stream);
+int b200r_alpha_composite_backward_strided(const float* grad_out, const float* features, int64_t C, int64_t P,
+                                           int64_t feature_stride_c, int64_t feature_stride_p, const float* alphas,
+                                           const int64_t* alpha_strides, const int64_t* points_idx,
+                                           const int64_t* idx_strides, int32_t N, int32_t K, int32_t H, int32_t W,
+                                           float* grad_features, float* grad_alphas, void* stream);
+
 /*
  * Replace pytorch3d._C.accum_weightedsum / accum_weightedsum_backward
  *   (weightedSumForward / Backward, pytorch3d/csrc/compositing/weighted_sum.h:57-78, 80-110) and
@@ -329,6 +342,25 @@ int64_t b200r_kernel_launch_count(void);
  */
 void b200r_set_profiling(int32_t enabled);
 int b200r_last_phase_ms(float out[3]);
+
+/*
+ * Fused point rendering (additional entry points, no counterpart in pytorch3d._C): weights = 1 - dists / radius2 and
+ * alpha compositing of the point features in one kernel per direction -- what PointsRenderer.forward does between the
+ * rasterizer and the image (pytorch3d/renderer/points/renderer.py:63-73) -- reading the rasterizer's outputs as they
+ * are: idx int32 (N,H,W,K), dists float32 (N,H,W,K); images float32 (N,C,H,W); feature (c, p) at
+ * features[c * feature_stride_c + p * feature_stride_p] (the renderer's `features_packed().permute(1, 0)` is a view of
+ * point-major memory: strides (1, C); grad_features uses the same strides).
+ * Forward values are bit-identical to the unfused chain; the backward zero-fills grad_features (C,P), accumulates it
+ * with atomics and writes grad_dists (N,H,W,K) = d loss / d dists.
+ */
+int b200r_points_alpha_render_forward(const float* features, int64_t C, int64_t P, int64_t feature_stride_c,
+                                      int64_t feature_stride_p, const int32_t* idx, const float* dists,
+                                      float radius2, int32_t N, int32_t K, int32_t H, int32_t W, float* images,
+                                      void* stream);
+int b200r_points_alpha_render_backward(const float* grad_images, const float* features, int64_t C, int64_t P,
+                                       int64_t feature_stride_c, int64_t feature_stride_p, const int32_t* idx,
+                                       const float* dists, float radius2, int32_t N, int32_t K, int32_t H, int32_t W,
+                                       float* grad_features, float* grad_dists, void* stream);
 
 /*
  * Programmatic dependent launch between the kernels of one call (setup -> scan -> fill -> fine; backward -> scatter):

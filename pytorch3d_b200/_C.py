@@ -425,14 +425,113 @@ def _composite_backward(fn_name, grad_outputs, features, alphas, points_idx):
 def accum_alphacomposite(features: torch.Tensor, alphas: torch.Tensor, points_idx: torch.Tensor):
     """pytorch3d._C.accum_alphacomposite (alphaCompositeForward, csrc/compositing/alpha_composite.h:59-82).
 
-    features (C,P) f32, alphas (N,K,H,W) f32, points_idx (N,K,H,W) i64 (any strides) -> (N,C,H,W) f32."""
-    return _composite_forward("b200r_alpha_composite_forward", features, alphas, points_idx)
+    features (C,P) f32 (a (C,P) view of point-major memory -- what the renderer passes -- is read in place), alphas
+    (N,K,H,W) f32, points_idx (N,K,H,W) i64 (any strides) -> (N,C,H,W) f32."""
+    dev = _require_cuda(("features", features), ("alphas", alphas), ("points_idx", points_idx))
+    if features.dtype != torch.float32 or alphas.dtype != torch.float32:
+        raise RuntimeError("expected scalar type Float")
+    if points_idx.dtype != torch.int64:
+        raise RuntimeError("expected scalar type Long but found %s" % points_idx.dtype)
+    if features.dim() != 2 or alphas.dim() != 4 or points_idx.dim() != 4 or alphas.shape != points_idx.shape:
+        raise RuntimeError("features must be (C, P); alphas and points_idx must both be (N, K, H, W)")
+    lib = _lib.load()
+    C, P = (int(v) for v in features.shape)
+    N, K, H, W = (int(v) for v in points_idx.shape)
+    feat, fs_c, fs_p = _feature_layout(features)
+    with torch.cuda.device(dev):
+        result = torch.empty((N, C, H, W), dtype=torch.float32, device=dev)
+        if result.numel() == 0:
+            return result
+        if K == 0:
+            return result.zero_()
+        _lib.check(lib.b200r_alpha_composite_forward_strided(
+            _ptr(feat), C, P, fs_c, fs_p, alphas.data_ptr(), _strides4(alphas), points_idx.data_ptr(),
+            _strides4(points_idx), N, K, H, W, _ptr(result), _stream_ptr(dev)))
+    return result
 
 
 def accum_alphacomposite_backward(grad_outputs: torch.Tensor, features: torch.Tensor, alphas: torch.Tensor,
                                   points_idx: torch.Tensor):
-    """pytorch3d._C.accum_alphacomposite_backward (alpha_composite.h:84-116) -> (grad_features, grad_alphas)."""
-    return _composite_backward("b200r_alpha_composite_backward", grad_outputs, features, alphas, points_idx)
+    """pytorch3d._C.accum_alphacomposite_backward (alpha_composite.h:84-116) -> (grad_features, grad_alphas);
+    grad_features (C,P) has the memory layout of `features`."""
+    dev = _require_cuda(("grad_outputs", grad_outputs), ("features", features), ("alphas", alphas),
+                        ("points_idx", points_idx))
+    lib = _lib.load()
+    C, P = (int(v) for v in features.shape)
+    N, K, H, W = (int(v) for v in points_idx.shape)
+    feat, fs_c, fs_p = _feature_layout(features)
+    go = grad_outputs.contiguous()
+    with torch.cuda.device(dev):
+        if fs_c == 1 and C > 1:
+            grad_features = torch.empty((P, C), dtype=torch.float32, device=dev).permute(1, 0)
+        else:
+            grad_features = torch.empty((C, P), dtype=torch.float32, device=dev)
+        grad_alphas = torch.empty((N, K, H, W), dtype=torch.float32, device=dev)
+        if C * P == 0 or grad_alphas.numel() == 0:
+            return grad_features.zero_(), grad_alphas.zero_()
+        _lib.check(lib.b200r_alpha_composite_backward_strided(
+            _ptr(go), _ptr(feat), C, P, fs_c, fs_p, alphas.data_ptr(), _strides4(alphas), points_idx.data_ptr(),
+            _strides4(points_idx), N, K, H, W, grad_features.data_ptr(), _ptr(grad_alphas), _stream_ptr(dev)))
+    return grad_features, grad_alphas
+
+
+def _feature_layout(features):
+    """(tensor to read, stride_c, stride_p): a (C, P) view of point-major memory (`features_packed().permute(1, 0)`,
+    what the renderer passes) is read in place; anything else as a contiguous (C, P) array."""
+    C, P = (int(v) for v in features.shape)
+    if features.stride(0) == 1 and features.stride(1) == C and P > 0:
+        return features, 1, C
+    f = features.contiguous()
+    return f, P, 1
+
+
+def points_alpha_render(features: torch.Tensor, idx: torch.Tensor, dists: torch.Tensor, radius: float):
+    """Fused `accum_alphacomposite(features, 1 - dists / radius**2, idx)` on the rasterizer's own layout (no counterpart
+    in pytorch3d._C): features (C,P) f32, idx (N,H,W,K) i32, dists (N,H,W,K) f32 -> (N,C,H,W) f32."""
+    dev = _require_cuda(("features", features), ("idx", idx), ("dists", dists))
+    if features.dtype != torch.float32 or dists.dtype != torch.float32:
+        raise RuntimeError("expected scalar type Float")
+    if idx.dtype != torch.int32:
+        raise RuntimeError("expected scalar type Int but found %s" % idx.dtype)
+    if features.dim() != 2 or idx.dim() != 4 or idx.shape != dists.shape:
+        raise RuntimeError("features must be (C, P); idx and dists must both be (N, H, W, K)")
+    lib = _lib.load()
+    C, P = (int(v) for v in features.shape)
+    N, H, W, K = (int(v) for v in idx.shape)
+    feat, fs_c, fs_p = _feature_layout(features)
+    ii, dd = idx.contiguous(), dists.contiguous()
+    with torch.cuda.device(dev):
+        images = torch.empty((N, C, H, W), dtype=torch.float32, device=dev)
+        if images.numel() == 0:
+            return images
+        _lib.check(lib.b200r_points_alpha_render_forward(_ptr(feat), C, P, fs_c, fs_p, _ptr(ii), _ptr(dd),
+                                                         float(radius) * float(radius), N, K, H, W, _ptr(images),
+                                                         _stream_ptr(dev)))
+    return images
+
+
+def points_alpha_render_backward(grad_images: torch.Tensor, features: torch.Tensor, idx: torch.Tensor,
+                                 dists: torch.Tensor, radius: float):
+    """Backward of `points_alpha_render` -> (grad_features (C,P) with the memory layout of `features`, grad_dists
+    (N,H,W,K))."""
+    dev = _require_cuda(("grad_images", grad_images), ("features", features), ("idx", idx), ("dists", dists))
+    lib = _lib.load()
+    C, P = (int(v) for v in features.shape)
+    N, H, W, K = (int(v) for v in idx.shape)
+    feat, fs_c, fs_p = _feature_layout(features)
+    go, ii, dd = grad_images.contiguous(), idx.contiguous(), dists.contiguous()
+    with torch.cuda.device(dev):
+        if fs_c == 1 and C > 1:
+            grad_features = torch.empty((P, C), dtype=torch.float32, device=dev).permute(1, 0)  # point-major, like feat
+        else:
+            grad_features = torch.empty((C, P), dtype=torch.float32, device=dev)
+        grad_dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        if C * P == 0 or grad_dists.numel() == 0:
+            return grad_features.zero_(), grad_dists.zero_()
+        _lib.check(lib.b200r_points_alpha_render_backward(_ptr(go), _ptr(feat), C, P, fs_c, fs_p, _ptr(ii), _ptr(dd),
+                                                          float(radius) * float(radius), N, K, H, W,
+                                                          grad_features.data_ptr(), _ptr(grad_dists), _stream_ptr(dev)))
+    return grad_features, grad_dists
 
 
 def accum_weightedsum(features: torch.Tensor, alphas: torch.Tensor, points_idx: torch.Tensor):

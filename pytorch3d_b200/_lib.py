@@ -44,6 +44,10 @@ SIGNATURES = {
         ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "b200r_alpha_composite_backward": (
         ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "b200r_alpha_composite_forward_strided": (
+        ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "b200r_alpha_composite_backward_strided": (
+        ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b200r_weighted_sum_forward": (
         ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "b200r_weighted_sum_backward": (
@@ -52,6 +56,10 @@ SIGNATURES = {
         ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "b200r_norm_weighted_sum_backward": (
         ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "b200r_points_alpha_render_forward": (
+        ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _f32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "b200r_points_alpha_render_backward": (
+        ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b200r_interp_face_attrs_forward": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "b200r_interp_face_attrs_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "b200r_peer_alloc": (ctypes.c_int, [_sz, ctypes.POINTER(_vp), ctypes.c_char_p]),

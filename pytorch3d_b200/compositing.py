@@ -30,6 +30,41 @@ def alpha_composite(pointsidx, alphas, pt_clds) -> torch.Tensor:
     return _CompositeAlphaPoints.apply(pt_clds, alphas, pointsidx)
 
 
+class _RenderPointsAlpha(torch.autograd.Function):
+    """images = alpha_composite(idx, 1 - dists / radius**2, features) in one kernel per direction, on the rasterizer's
+    (N,H,W,K) layout (see `render_points_alpha`)."""
+
+    @staticmethod
+    def forward(ctx, features, dists, idx, radius):
+        images = _C.points_alpha_render(features, idx, dists, radius)
+        ctx.save_for_backward(features, dists, idx)
+        ctx.radius = radius
+        ctx.mark_non_differentiable(idx)
+        return images
+
+    @staticmethod
+    def backward(ctx, grad_images):
+        features, dists, idx = ctx.saved_tensors
+        grad_features, grad_dists = _C.points_alpha_render_backward(grad_images, features, idx, dists, ctx.radius)
+        return grad_features, grad_dists, None, None
+
+
+def render_points_alpha(fragments, features, radius: float) -> torch.Tensor:
+    """Fused form of what `PointsRenderer.forward` does with an `AlphaCompositor`
+    (pytorch3d/renderer/points/renderer.py:63-73 of the reference):
+
+        weights = 1 - fragments.dists.permute(0, 3, 1, 2) / (radius * radius)
+        images = alpha_composite(fragments.idx.long().permute(0, 3, 1, 2), weights, features)
+
+    `fragments`: PointFragments (or (idx, zbuf, dists)); `features`: (C, P) packed features (the reference passes
+    `features_packed().permute(1, 0)`); scalar `radius`.  Returns (N, C, H, W) like the compositor (the renderer then
+    permutes to (N, H, W, C)).  Forward values are bit-identical to the unfused chain; gradients flow to `features` and
+    to `fragments.dists`."""
+    idx = fragments.idx if hasattr(fragments, "idx") else fragments[0]
+    dists = fragments.dists if hasattr(fragments, "dists") else fragments[2]
+    return _RenderPointsAlpha.apply(features, dists, idx, float(radius))
+
+
 def _make_composite(forward_op, backward_op, doc):
     class _Composite(torch.autograd.Function):
         @staticmethod

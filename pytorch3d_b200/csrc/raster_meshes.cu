@@ -99,9 +99,6 @@ __global__ void __launch_bounds__(SETUP_FACES)
                             float sqrt_blur, int cull_backfaces, uint4* __restrict__ rect,
                             int* __restrict__ tile_count, float4* __restrict__ rec) {
   __shared__ __align__(16) float s_fv[SETUP_FACES * 9];
-#ifndef B200R_EXP_DIRECTREC
-  __shared__ __align__(16) float4 s_rec[SETUP_FACES * 4];
-#endif
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x;
   const int64_t f0 = (int64_t)blockIdx.x * SETUP_FACES;
@@ -151,11 +148,7 @@ __global__ void __launch_bounds__(SETUP_FACES)
     rect[fi] = make_uint4(r.x, r.y, (uint32_t)max(n, 0), 0u);
     // the reference reads the int64 neighbour index into an int (rasterize_meshes.cu:186)
     const int nb = neighbor ? (int)__ldg(neighbor + fi) : -1;
-#ifdef B200R_EXP_DIRECTREC
     float4* out = rec + fi * 4;
-#else
-    float4* out = s_rec + tid * 4;
-#endif
     out[0] = make_float4(f.x0, f.y0, f.x1, f.y1);
     out[1] = make_float4(f.x2, f.y2, bary_denominator(f), __int_as_float((int)fi));
     out[2] = make_float4(f.z0, f.z1, f.z2, __int_as_float(nb));
@@ -164,13 +157,6 @@ __global__ void __launch_bounds__(SETUP_FACES)
                                             __int_as_float(rng.w));
   }
   warp_count_rect(r, n, TY, TX, tile_count, tid & 31);  // all lanes participate
-#ifndef B200R_EXP_DIRECTREC
-  // the CTA's records are one contiguous block of the record array: written out with consecutive lanes on consecutive
-  // 16-byte pieces (whole sectors per instruction; per-thread stores at a 64-byte stride filled half of each sector)
-  __syncthreads();
-  float4* dst = rec + f0 * 4;
-  for (int e = tid; e < nf * 4; e += SETUP_FACES) dst[e] = s_rec[e];
-#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1471,8 +1457,14 @@ __device__ __forceinline__ void warp_scatter(float* __restrict__ grad_face_verts
 
 // GV > 0: K is a multiple of GV (8 or 4) and a pixel's face indices are fetched GV at a time with 16-byte loads
 // (a group without faces costs nothing else); GV == 0: any K, scalar loads.
-template <int GV>
-__global__ void __launch_bounds__(TILE_THREADS, 4) mesh_backward_kernel(const BackwardParams p) {
+// PF (GV == 8, 16-byte aligned gradients): valid slots come first in every pixel, so as soon as the indices are known a
+// pixel with a hit fetches the upstream gradients of its first four slots with five 16-byte loads -- one round trip to
+// DRAM for all of them instead of one per slot (the kernel's stall samples are 50 % long_scoreboard: dependent loads).
+#ifndef B200R_BWD_PF_CTAS
+#define B200R_BWD_PF_CTAS 3
+#endif
+template <int GV, bool PF>
+__global__ void __launch_bounds__(TILE_THREADS, PF ? B200R_BWD_PF_CTAS : 4) mesh_backward_kernel(const BackwardParams p) {
   const int lane = threadIdx.x & 31;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = p.n0 + blockIdx.z;  // grid = (TX, TY, images)
   int xo, yo;
@@ -1484,6 +1476,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_backward_kernel(const Ba
   const int64_t o = in_image ? (((int64_t)n * p.H + yo) * p.W + xo) * K : 0;
   const bool persp = p.persp != 0, clip = p.clip != 0;
   constexpr int G = GV > 0 ? GV : 1;
+  static_assert(!PF || GV == 8, "the prefetching variant is the K % 8 == 0 kernel");
 
   for (int k0 = 0; k0 < K; k0 += G) {
     int fk[G];
@@ -1498,17 +1491,51 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_backward_kernel(const Ba
     } else {
       fk[0] = in_image ? (int)p.pix_to_face[o + k0] : -1;
     }
+    float pz[PF ? 4 : 1], pd[PF ? 4 : 1], pb[PF ? 12 : 1];  // upstream gradients of slots k0 .. k0+3
+    if (PF) {
+      float4 vz = make_float4(0.f, 0.f, 0.f, 0.f), vd = vz, b0 = vz, b1 = vz, b2 = vz;
+      if (fk[0] >= 0) {
+        vz = __ldg(reinterpret_cast<const float4*>(p.grad_zbuf + o + k0));
+        vd = __ldg(reinterpret_cast<const float4*>(p.grad_dists + o + k0));
+        const float4* gb = reinterpret_cast<const float4*>(p.grad_bary + (o + k0) * 3);
+        b0 = __ldg(gb + 0);
+        b1 = __ldg(gb + 1);
+        b2 = __ldg(gb + 2);
+      }
+      pz[0] = vz.x; pz[1] = vz.y; pz[2] = vz.z; pz[3] = vz.w;
+      pd[0] = vd.x; pd[1] = vd.y; pd[2] = vd.z; pd[3] = vd.w;
+      pb[0] = b0.x; pb[1] = b0.y; pb[2] = b0.z; pb[3] = b0.w;
+      pb[4] = b1.x; pb[5] = b1.y; pb[6] = b1.z; pb[7] = b1.w;
+      pb[8] = b2.x; pb[9] = b2.y; pb[10] = b2.z; pb[11] = b2.w;
+    }
 #pragma unroll 1
     for (int j = 0; j < G; ++j) {
       const int face = fk[0];
 #pragma unroll
       for (int u = 0; u + 1 < G; ++u) fk[u] = fk[u + 1];  // rotate: one copy of the gradient code
+      float gz = 0.f, gd = 0.f, gb0 = 0.f, gb1 = 0.f, gb2 = 0.f;
+      if (PF) {  // (rotated like the indices)
+        gz = pz[0]; gd = pd[0]; gb0 = pb[0]; gb1 = pb[1]; gb2 = pb[2];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          pz[u] = pz[u + 1];
+          pd[u] = pd[u + 1];
+        }
+#pragma unroll
+        for (int u = 0; u < 9; ++u) pb[u] = pb[u + 3];
+      }
       if (!__any_sync(0xffffffffu, face >= 0)) continue;  // padded slots (:472-474)
       float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (face >= 0) {
         const int64_t i = o + k0 + j;
-        backward_one(p, px, py, face, __ldg(p.grad_zbuf + i), __ldg(p.grad_dists + i), __ldg(p.grad_bary + i * 3),
-                     __ldg(p.grad_bary + i * 3 + 1), __ldg(p.grad_bary + i * 3 + 2), persp, clip, g);
+        if (!PF || j >= 4) {
+          gz = __ldg(p.grad_zbuf + i);
+          gd = __ldg(p.grad_dists + i);
+          gb0 = __ldg(p.grad_bary + i * 3);
+          gb1 = __ldg(p.grad_bary + i * 3 + 1);
+          gb2 = __ldg(p.grad_bary + i * 3 + 2);
+        }
+        backward_one(p, px, py, face, gz, gd, gb0, gb1, gb2, persp, clip, g);
       }
       warp_scatter(p.grad_face_verts, face, g, lane);
     }
@@ -1746,12 +1773,21 @@ extern "C" int b200r_rasterize_meshes_backward(const float* face_verts, int64_t 
   if (prof) phase_timer().record(3, stream);
   for (p.n0 = 0; p.n0 < N; p.n0 += 65535) {  // grid.z is limited to 65535 images per launch
     const dim3 bgrid((unsigned)TX, (unsigned)TY, (unsigned)min(N - p.n0, 65535));
-    if ((K & 7) == 0)
-      mesh_backward_kernel<8><<<bgrid, TILE_THREADS, 0, stream>>>(p);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(grad_zbuf) | reinterpret_cast<uintptr_t>(grad_bary) |
+                           reinterpret_cast<uintptr_t>(grad_dists)) & 15u) == 0;
+#ifdef B200R_EXP_NOBWDPF
+    const bool prefetch = false;
+#else
+    const bool prefetch = aligned;
+#endif
+    if ((K & 7) == 0 && prefetch)
+      mesh_backward_kernel<8, true><<<bgrid, TILE_THREADS, 0, stream>>>(p);
+    else if ((K & 7) == 0)
+      mesh_backward_kernel<8, false><<<bgrid, TILE_THREADS, 0, stream>>>(p);
     else if ((K & 3) == 0)
-      mesh_backward_kernel<4><<<bgrid, TILE_THREADS, 0, stream>>>(p);
+      mesh_backward_kernel<4, false><<<bgrid, TILE_THREADS, 0, stream>>>(p);
     else
-      mesh_backward_kernel<0><<<bgrid, TILE_THREADS, 0, stream>>>(p);
+      mesh_backward_kernel<0, false><<<bgrid, TILE_THREADS, 0, stream>>>(p);
   }
   B200R_LAUNCHED("mesh_backward_kernel");
   if (prof) {

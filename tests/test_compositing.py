@@ -171,3 +171,43 @@ def test_weighted_sum_cuda_forward_backward(built_lib, norm, N, K, H, W, C, P, p
         bg = (idx[:, 0] < 0).to(dev)
         assert torch.equal(img2.permute(0, 2, 3, 1)[~bg], out.permute(0, 2, 3, 1)[~bg])
         assert (img2.permute(0, 2, 3, 1)[bg] == 0.5).all()
+
+
+# ------------------------------------------------------------------------------------ fused point rendering
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,N,size,K,C,r", [(3000, 2, (40, 56), 6, 4, 0.08), (20000, 3, (64, 64), 10, 3, 0.03),
+                                           (500, 1, (17, 33), 1, 1, 0.2)])
+def test_fused_point_rendering_equals_the_unfused_chain(built_lib, P, N, size, K, C, r):
+    """`render_points_alpha(fragments, features, r)` = what PointsRenderer does with an AlphaCompositor
+    (pytorch3d/renderer/points/renderer.py:63-73): weights = 1 - dists / r^2 (torch), idx.long(), two permutes and
+    alpha_composite -- forward bit for bit, gradients w.r.t. features and dists to rounding (different summation order
+    of the atomics only)."""
+    from pytorch3d_b200 import _C, compositing, synthetic
+    dev = torch.device("cuda:0")
+    pc = synthetic.random_pointclouds(N, P, seed=P)
+    pts = pc.points_packed().to(dev)
+    rad = torch.full((pts.shape[0],), r, device=dev)
+    idx, zbuf, dists = _C.rasterize_points(pts, pc.cloud_to_packed_first_idx().to(dev),
+                                           pc.num_points_per_cloud().to(dev), size, rad, K, 0, 0)
+    g = torch.Generator().manual_seed(7)
+    if K != 6:  # the renderer's layout: features_packed() is (P, C); the compositor gets its (C, P) view
+        feats = torch.rand(pts.shape[0], C, generator=g).to(dev).permute(1, 0)
+    else:       # a plain contiguous (C, P) array
+        feats = torch.rand(C, pts.shape[0], generator=g).to(dev)
+    go = torch.rand((N, C) + tuple(size), generator=g).to(dev)
+    # the unfused chain, as the reference renderer writes it
+    d1 = dists.clone().requires_grad_(True)
+    f1 = feats.clone().requires_grad_(True)
+    weights = 1 - d1.permute(0, 3, 1, 2) / (r * r)
+    img1 = compositing.alpha_composite(idx.long().permute(0, 3, 1, 2), weights, f1)
+    (img1 * go).sum().backward()
+    # fused
+    d2 = dists.clone().requires_grad_(True)
+    f2 = feats.clone().requires_grad_(True)
+    img2 = compositing.render_points_alpha((idx, zbuf, d2), f2, r)
+    (img2 * go).sum().backward()
+    assert torch.equal(img1, img2), "fused forward must be bit-identical to the unfused chain"
+    assert torch.allclose(f1.grad, f2.grad, rtol=1e-4, atol=1e-5 * float(f1.grad.abs().max()))
+    assert torch.allclose(d1.grad, d2.grad, rtol=1e-4, atol=1e-5 * float(d1.grad.abs().max()))
+    assert int((idx >= 0).sum()) > 0

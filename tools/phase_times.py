@@ -16,8 +16,9 @@ from pytorch3d_b200 import _C, _lib, synthetic  # noqa: E402
 args = sys.argv[1:]
 pdl_modes = [1]
 while args and args[0].startswith("--"):
-    if args[0] == "--lib":  # development: time another build of the library
-        _lib.LIB_PATH = os.path.abspath(args[1])
+    if args[0] == "--lib":  # development: time another build of the library (through the ctypes binding: the
+        _lib.LIB_PATH = os.path.abspath(args[1])  # torch extension is linked against the in-tree library)
+        _C.USE_EXT = False
     elif args[0] == "--pdl":
         pdl_modes = [0, 1] if args[1] == "both" else [int(args[1])]
     args = args[2:]
