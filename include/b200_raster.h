@@ -61,6 +61,9 @@ size_t b200r_rasterize_meshes_workspace_bytes(int64_t F, int32_t N, int32_t H, i
  *    call site pytorch3d/renderer/mesh/rasterize_meshes.py:297-310).
  *
  *  face_verts                 float32 (F,3,3)   packed faces in NDC (+X left, +Y up, z = depth)
+ *  (mesh_to_face_first_idx / num_faces_per_mesh must describe ASCENDING, NON-OVERLAPPING ranges of the packed array --
+ *   what Meshes produces: every face belongs to exactly one image.  The reference's kernels loop over each image's
+ *   range and so also accept overlapping ranges; here images other than a face's owner would not see it.)
  *  mesh_to_face_first_idx     int64   (N,)      first packed face of each mesh (ascending)
  *  num_faces_per_mesh         int64   (N,)
  *  clipped_faces_neighbor_idx int64   (F,)      -1 or index of the other half of a clipped face

@@ -393,6 +393,43 @@ __device__ __forceinline__ void cta_sort_segment(int* seg, int n, int* s_keys, i
   __syncthreads();
 }
 
+// A tile list of any length put in ascending order of 64-bit keys built by `make_key(element)`; the keys live in shared
+// memory (`keys`, room for n of them), the list itself is rewritten in that order.  Used by the mesh fine pass to walk a
+// tile's faces front to back (key = (nearest vertex depth, face)).
+template <class MakeKey>
+__device__ __forceinline__ void cta_sort_segment_by_key(int* seg, int n, unsigned long long* keys, MakeKey make_key) {
+  for (int i = threadIdx.x; i < n; i += TILE_THREADS) keys[i] = make_key(seg[i]);
+  __syncthreads();
+  for (int k = 2; (k >> 1) < n; k <<= 1) {
+    for (int i = threadIdx.x; i < n; i += TILE_THREADS) {  // mirror step
+      const int j = i ^ (k - 1);
+      if (j > i && j < n) {
+        const unsigned long long a = keys[i], b = keys[j];
+        if (b < a) {
+          keys[i] = b;
+          keys[j] = a;
+        }
+      }
+    }
+    __syncthreads();
+    for (int d = k >> 2; d > 0; d >>= 1) {
+      for (int i = threadIdx.x; i < n; i += TILE_THREADS) {
+        const int j = i ^ d;
+        if (j > i && j < n) {
+          const unsigned long long a = keys[i], b = keys[j];
+          if (b < a) {
+            keys[i] = b;
+            keys[j] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += TILE_THREADS) seg[i] = (int)(unsigned)(keys[i] & 0xffffffffull);
+  __syncthreads();
+}
+
 // Workspace carving (all int32 / uint2 arrays, 16B-aligned sections).
 struct BinWorkspace {
   int* tile_count;  // [ntiles]   counts, then fill cursors (absolute positions)

@@ -516,16 +516,19 @@ struct FineStage {
     float4 box[CHUNK];                          // blur > 0: blur-expanded boxes (pass A)
     unsigned mask[CHUNK / 32][TILE_THREADS];    // blur = 0: per pixel (thread), one bit per staged face
     int sort_buf[2 * TILE_THREADS];             // exchange buffers of cta_sort256 (before the chunk is staged)
+    unsigned long long sort_buf64[2 * TILE_THREADS];  // ... of cta_sort256_u64
   } u;
   unsigned rng[CHUNK];                          // blur = 0: tile-local pixel rectangle c_lo | c_hi<<8 | r_lo<<16 | r_hi<<24
   float col[TILE], row[TILE];                   // NDC coordinates of the tile's 16 pixel columns / rows
   int tie;                                      // see flag_tie()
+  unsigned char tie_lane[TILE_THREADS];         // ... and which pixels (threads) raised it
 };
 
 __device__ __forceinline__ void flag_tie() {
 #ifndef B200R_EXP_NOWATCH  // (timing experiment of tools/variant_time.py: no tie watching at all)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   reinterpret_cast<FineStage*>(smem_raw)->tie = 1;
+  reinterpret_cast<FineStage*>(smem_raw)->tie_lane[threadIdx.x] = 1;
 #endif
 }
 
@@ -697,18 +700,36 @@ __device__ __forceinline__ float face_depth_lower_bound(const float4 fa, const f
 // triangles of a quad extrapolate to the same depth) and with clipped-face neighbours (whose replace-in-queue rule
 // depends on the order by itself) the list is sorted up front.  Either way the result is the one the sorted walk
 // gives; sorting every list cost 30 % of the kernel's instructions.
+// `order`: ORDER_ARRIVAL (the list as the fill pass left it), ORDER_INDEX (ascending face index: the reference's order)
+// or ORDER_DEPTH (ascending nearest-vertex depth: front to back).  `active`: this thread's pixel takes part in the walk
+// (its queue is updated); inactive threads still help to stage.  `scratch_ints`: how much of the kernel's shared memory,
+// from its start, a long-list sort may use (everything on the first walk of a tile; only the staging area when queue
+// payload of an earlier walk must survive).
+enum { ORDER_ARRIVAL = 0, ORDER_INDEX = 1, ORDER_DEPTH = 2 };
+
 template <class Q, bool NB, bool SCAN>
 __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& sh, Q& q, int tile_x, int tile_y, int n,
-                                               int seg_begin, int count, bool overflow, bool sorted_walk, bool valid,
-                                               int lc, int lr) {
+                                               int seg_begin, int count, bool overflow, int order, bool active,
+                                               int scratch_ints, int lc, int lr) {
   const int tid = threadIdx.x, lane = tid & 31;
   const bool persp = p.persp != 0, clip = p.clip != 0;
   const float blur_radius = p.blur_radius;
+  const bool valid = active;
   // (an overflowed tile walks the mesh's own faces: already in order)
+  const bool sorted_walk = order == ORDER_INDEX;
   const bool sort_staged = sorted_walk && !overflow && count <= CHUNK;
-  // (the long-list sort may use all of the kernel's shared memory: nothing lives there yet / any more)
+  const bool depth_staged = order == ORDER_DEPTH && count <= CHUNK;
+  const float4* rec = p.rec;
+  // nearest vertex depth of a listed face (listed faces are drawable: z > 0, the float's bits are ordered), then its index
+  auto depth_key = [rec](int f) {
+    const float4 c = __ldg(rec + (int64_t)f * 4 + 2);
+    return ((unsigned long long)__float_as_uint(fminf(fminf(c.x, c.y), c.z)) << 32) | (unsigned)f;
+  };
+  // (the long-list sorts use the kernel's shared memory as scratch: nothing lives in that part yet / any more)
   if (sorted_walk && !overflow && count > CHUNK)
-    cta_sort_segment(p.pairs + seg_begin, count, reinterpret_cast<int*>(&sh), p.smem_ints);
+    cta_sort_segment(p.pairs + seg_begin, count, reinterpret_cast<int*>(&sh), scratch_ints);
+  if (order == ORDER_DEPTH && count > CHUNK)
+    cta_sort_segment_by_key(p.pairs + seg_begin, count, reinterpret_cast<unsigned long long*>(&sh), depth_key);
   // NDC coordinates of the tile's 16 pixel columns and rows (two IEEE divisions each): computed once per tile
   // by 32 threads, read by every thread after the barriers of the first chunk
   if (tid < 2 * TILE) {
@@ -718,7 +739,10 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
     else
       sh.row[i] = pix_to_ndc(p.H - 1 - (tile_y * TILE + i), p.H, p.ry);
   }
-  if (tid == 2 * TILE && !sorted_walk) sh.tie = 0;
+  if (!sorted_walk) {
+    if (tid == 2 * TILE) sh.tie = 0;
+    sh.tie_lane[tid] = 0;
+  }
 
   for (int base = 0; base < count; base += CHUNK) {
     const int nc = min(CHUNK, count - base);
@@ -729,6 +753,12 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
     if (sort_staged) {
       f = cta_sort256(f, nc, sh.u.sort_buf);
       if (nc > 32) __syncthreads();  // the exchange buffers alias the masks / boxes written next
+    } else if (depth_staged) {
+      unsigned long long key = ~0ull;
+      if (tid < nc) key = depth_key(f);
+      key = cta_sort256_u64(key, nc, sh.u.sort_buf64);
+      if (nc > 32) __syncthreads();
+      f = (int)(unsigned)(key & 0xffffffffull);
     }
     if (tid < nc) {
       const float4* r = p.rec + (int64_t)f * 4;
@@ -832,11 +862,13 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
     const float px = sh.col[lc], py = sh.row[lr];
     // (worth its ~80 instructions per face and warp only where a pixel has far more candidates than queue slots: long
     // tile lists -- config 5: 2300 faces per tile, 13.0 -> 9.1 ms; north-star batch with blur 1e-4: none culled, +3 %)
-    const bool cull_depth = (clip || !persp) && count >= 512;
+    const bool cull_depth = (clip || !persp) && (order == ORDER_DEPTH || count >= 512);
     // extent of the warp's footprint (pixel centres are monotonic in the pixel index)
     const float fc0 = sh.col[lc & 8], fc1 = sh.col[(lc & 8) + 7], fr0 = sh.row[lr & 12], fr1 = sh.row[(lr & 12) + 3];
     const float cmin = fminf(fc0, fc1), cmax = fmaxf(fc0, fc1), rmin = fminf(fr0, fr1), rmax = fmaxf(fr0, fr1);
+    const bool warp_active = __any_sync(0xffffffffu, valid);  // (a redo of flagged pixels leaves most warps idle)
     for (int sub = 0; sub < nc; sub += ROUND) {
+      if (!warp_active) break;
       // ---- pass A: 64-bit mask of the faces of this round whose box contains my pixel
       unsigned m0 = 0, m1 = 0;
       {
@@ -939,6 +971,26 @@ __device__ __forceinline__ TileWork tile_work(const FineParams& p) {
   return t;
 }
 
+// Which walk a tile starts with (see fine_tile_body and DESIGN.md 5).  Without a blur band: arrival order, watched for depth
+// ties.  With one: FRONT TO BACK (ascending nearest-vertex depth) when the depth bound of the warp-level culling exists
+// (clip_barycentric_coords, or no perspective correction) and the list's keys fit the kernel's shared memory -- the queues
+// then fill with near hits first and most of the band's far candidates are culled for whole warps -- again watched for
+// depth ties; the pixels that saw one (only those) are redone in index order before anything is written.  Clipped-face
+// neighbours (order-dependent by themselves) and overflowed tiles: index order.
+template <bool NB, bool SCAN>
+__device__ __forceinline__ int first_walk_order(const FineParams& p, const TileWork& t) {
+  if (t.overflow || NB) return ORDER_INDEX;
+  if (SCAN) return ORDER_ARRIVAL;
+#ifndef B200R_EXP_DEPTHORDER
+  // (measured, round 2: structured meshes tie so often in the blur band that too many pixels are redone -- north-star
+  // batch with blur 1e-4: fine 917 -> 1306 us, config 2: 139 -> 198 us, config 5: 9.3 -> 14.9 ms; kept as an experiment)
+  return ORDER_INDEX;
+#else
+  const bool bound = p.clip != 0 || p.persp == 0;
+  return (bound && 2 * t.count <= p.smem_ints) ? ORDER_DEPTH : ORDER_INDEX;
+#endif
+}
+
 template <int KMAX, bool NB, bool SCAN>
 __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FineParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -963,10 +1015,24 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
   float4* pay = rq.pay;
   const int K = p.K;
   // (see fine_tile_body: arrival-order walk first where ties are rare, sorted walk only if one was seen)
-  bool sorted_walk = t.overflow || !(SCAN && !NB);
+  int order = first_walk_order<NB, SCAN>(p, t);
+  bool active = valid;
+  int scratch_ints = p.smem_ints;
   for (;;) {
-  fine_tile_body<RegQueue<KMAX>, NB, SCAN>(p, sh, rq, tile_x, tile_y, n, t.seg_begin, t.count, t.overflow, sorted_walk,
-                                           valid, lc, lr);
+  fine_tile_body<RegQueue<KMAX>, NB, SCAN>(p, sh, rq, tile_x, tile_y, n, t.seg_begin, t.count, t.overflow, order,
+                                           active, scratch_ints, lc, lr);
+  if (order == ORDER_DEPTH) {
+    // front-to-back walk done: did any pixel see a depth tie?  Those pixels -- and only those -- walk again in index
+    // order (the queue payload of the others stays where it is: the long-list sort may only use the staging area)
+    if (tile_saw_tie(sh)) {
+      active = valid && sh.tie_lane[tid] != 0;
+      if (active) rq.reset();
+      order = ORDER_INDEX;
+      scratch_ints = (int)(sizeof(FineStage) / sizeof(int));
+      __syncthreads();  // every thread has read its flag before the next walk clears / reuses the staging area
+      continue;
+    }
+  }
   bool stored = false;
   int slot[KMAX];
   q.sort(slot);
@@ -1042,8 +1108,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
       }
     }
   }
-  if (sorted_walk || !tile_saw_tie(sh)) return;
-  sorted_walk = true;
+  if (order != ORDER_ARRIVAL || !tile_saw_tie(sh)) return;
+  order = ORDER_INDEX;
   rq.reset();
   }
 }
@@ -1080,10 +1146,22 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) mesh_fine_smemq_kernel(const 
 
   SmemQueue<NB> q;
   q.init(smem_raw + sizeof(FineStage), K, tid);
-  bool sorted_walk = t.overflow || !(SCAN && !NB);
+  int order = first_walk_order<NB, SCAN>(p, t);
+  bool active = valid;
+  int scratch_ints = p.smem_ints;
   for (;;) {
-  fine_tile_body<SmemQueue<NB>, NB, SCAN>(p, sh, q, tile_x, tile_y, n, t.seg_begin, t.count, t.overflow, sorted_walk,
-                                          valid, lc, lr);
+  fine_tile_body<SmemQueue<NB>, NB, SCAN>(p, sh, q, tile_x, tile_y, n, t.seg_begin, t.count, t.overflow, order, active,
+                                          scratch_ints, lc, lr);
+  if (order == ORDER_DEPTH) {  // (see mesh_fine_kernel)
+    if (tile_saw_tie(sh)) {
+      active = valid && sh.tie_lane[tid] != 0;
+      if (active) q.reset();
+      order = ORDER_INDEX;
+      scratch_ints = (int)(sizeof(FineStage) / sizeof(int));
+      __syncthreads();
+      continue;
+    }
+  }
   q.sort();
   const float px = sh.col[lc], py = sh.row[lr];
   const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
@@ -1149,8 +1227,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) mesh_fine_smemq_kernel(const 
     p.bary[(o + k) * 3 + 2] = h.b2;
   }
   }
-  if (sorted_walk || !tile_saw_tie(sh)) return;
-  sorted_walk = true;
+  if (order != ORDER_ARRIVAL || !tile_saw_tie(sh)) return;
+  order = ORDER_INDEX;
   q.reset();
   }
 }
@@ -1775,10 +1853,10 @@ extern "C" int b200r_rasterize_meshes_backward(const float* face_verts, int64_t 
     const dim3 bgrid((unsigned)TX, (unsigned)TY, (unsigned)min(N - p.n0, 65535));
     const bool aligned = ((reinterpret_cast<uintptr_t>(grad_zbuf) | reinterpret_cast<uintptr_t>(grad_bary) |
                            reinterpret_cast<uintptr_t>(grad_dists)) & 15u) == 0;
-#ifdef B200R_EXP_NOBWDPF
-    const bool prefetch = false;
+#ifdef B200R_EXP_BWDPF  // (measured, round 2: 96 -> 113 us at three CTAs per SM: the occupancy it costs outweighs the
+    const bool prefetch = aligned;  // round trips it saves; kept as an experiment)
 #else
-    const bool prefetch = aligned;
+    const bool prefetch = false && aligned;
 #endif
     if ((K & 7) == 0 && prefetch)
       mesh_backward_kernel<8, true><<<bgrid, TILE_THREADS, 0, stream>>>(p);

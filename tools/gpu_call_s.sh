@@ -3,9 +3,9 @@
 set -u
 mkdir -p gpurun_out
 echo "== phase times (bwd prefetch: in-tree = 3 CTAs/SM; variants: 4 CTAs/SM, no prefetch)"
-timeout 600 python tools/phase_times.py ns c2 ns_blur ns_k16 > gpurun_out/s_phase.log 2>&1; tail -4 gpurun_out/s_phase.log
-for v in bwdpf4 nobwdpf; do
-  timeout 300 python tools/phase_times.py --lib tools/_variants/lib_$v.so ns c2 ns_blur > gpurun_out/s_phase_$v.log 2>&1; tail -3 gpurun_out/s_phase_$v.log
+timeout 600 python tools/phase_times.py ns c2 ns_blur ns_k16 c5 > gpurun_out/s_phase.log 2>&1; tail -5 gpurun_out/s_phase.log
+for v in bwdpf4 nobwdpf nodepth; do
+  timeout 300 python tools/phase_times.py --lib tools/_variants/lib_$v.so ns c2 ns_blur c5 > gpurun_out/s_phase_$v.log 2>&1; tail -4 gpurun_out/s_phase_$v.log
 done
 echo "== pytest gpu"
 timeout 900 python -m pytest tests -m gpu -q -rs -p no:cacheprovider > gpurun_out/s_pytest.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/s_pytest.log

@@ -36,6 +36,17 @@ for (size, K) in [((64, 64), 10), ((33, 47), 7), ((16, 16), 4), ((24, 24), 40)]:
     o = _C.rasterize_points(pts, pf, pn, size, rad, K, 0, 0)
     _C.rasterize_points_backward(pts, o[0], torch.randn_like(o[1]), torch.randn_like(o[2]))
     print("points", size, K, int((o[0] >= 0).sum()), flush=True)
+# compositing: drop-in alpha composite (strided point-major features) and the fused point renderer op
+o = _C.rasterize_points(pts, pf, pn, (33, 47), rad, 6, 0, 0)
+feats = torch.rand(pts.shape[0], 4, device=dev).permute(1, 0)
+w = (1 - o[2] / (0.05 * 0.05)).permute(0, 3, 1, 2)
+il = o[0].long().permute(0, 3, 1, 2)
+img = _C.accum_alphacomposite(feats, w, il)
+_C.accum_alphacomposite_backward(torch.randn_like(img), feats, w, il)
+img2 = _C.points_alpha_render(feats, o[0], o[2], 0.05)
+_C.points_alpha_render_backward(torch.randn_like(img2), feats, o[0], o[2], 0.05)
+assert torch.equal(img, img2)
+print("compositing", tuple(img.shape), flush=True)
 # packed frame exchange kernels (one GPU: the region is local memory)
 lib = _lib.load()
 out = _C.rasterize_meshes(fv, first, num, nb, (64, 64), 0.0, 8, 0, 0, False, False, False)
