@@ -25,6 +25,11 @@ struct Strides4 {
 
 constexpr float kCompEps = 1e-9f;  // alpha_composite.cu:20
 
+// One 16-byte reduction for the four channels of a point (point-major features, C = 4): sm_90+ vector atomics.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // Feature (c, point) lives at features[c * fs_c + point * fs_p] (the renderer passes `features_packed().permute(1, 0)`,
 // a (C, P) view of point-major memory: all channels of a point in one sector, no contiguous copy).  CMAX > 0: C <= CMAX,
 // the slots are walked once with one accumulator per channel -- per channel the reference's operations in its order;
@@ -91,6 +96,8 @@ __global__ void __launch_bounds__(256)
     const int64_t* ip = points_idx + n * si.n + y * si.y + x * si.x;
     const float* go = grad_out + (int64_t)n * C * plane + (int64_t)y * W + x;  // + c * plane
     float* ga = grad_alphas + (int64_t)n * K * plane + (int64_t)y * W + x;     // + k * plane (contiguous N,K,H,W)
+    const bool pm4 = C == 4 && fs_c == 1 && fs_p == 4 &&
+                     ((reinterpret_cast<uintptr_t>(features) | reinterpret_cast<uintptr_t>(grad_features)) & 15u) == 0;
     // transmittance before the last valid slot, then walk the slots backwards keeping the suffix sum
     //   S_k = sum_{t>k} cum_t * alpha_t * A_t,   A_t = sum_c grad_out_c * feat[c, idx_t]
     // grad_alpha_k = cum_k * A_k - S_k / (1 - alpha_k + eps)          (alpha_composite.cu:112-134, summed over c)
@@ -119,10 +126,17 @@ __global__ void __launch_bounds__(256)
       }
       float A = 0.0f;
       const float w = cum_k * a;
-      for (int64_t c = 0; c < C; ++c) {  // (grad_features has the layout of features)
-        const float g = go[c * plane];
-        A += g * __ldg(features + c * fs_c + id * fs_p);
-        atomicAdd(grad_features + c * fs_c + id * fs_p, g * w);  // (:115-117)
+      if (pm4) {  // point-major features, four channels: one 16-byte load and one 16-byte reduction per hit
+        const float4 f = __ldg(reinterpret_cast<const float4*>(features) + id);
+        const float g0 = go[0], g1 = go[plane], g2 = go[2 * plane], g3 = go[3 * plane];
+        A = ((g0 * f.x + g1 * f.y) + g2 * f.z) + g3 * f.w;
+        red_add_v4(grad_features + id * 4, g0 * w, g1 * w, g2 * w, g3 * w);
+      } else {
+        for (int64_t c = 0; c < C; ++c) {  // (grad_features has the layout of features)
+          const float g = go[c * plane];
+          A += g * __ldg(features + c * fs_c + id * fs_p);
+          atomicAdd(grad_features + c * fs_c + id * fs_p, g * w);  // (:115-117)
+        }
       }
       ga[k * plane] = cum_k * A - suffix / (one_minus + kCompEps);
       suffix += w * A;
@@ -309,6 +323,7 @@ __global__ void __launch_bounds__(256)
   const int64_t plane = (int64_t)H * W;
   const float inv = fdiv(1.0f, r2);
   const bool vec4 = CMAX == 4 && C == 4 && fs_c == 1 && fs_p == 4 && (reinterpret_cast<uintptr_t>(features) & 15u) == 0;
+  const bool gvec4 = (reinterpret_cast<uintptr_t>(grad_features) & 15u) == 0;
   for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += stride) {
     const int64_t n = pix / plane, yx = pix - n * plane;
     const int32_t* ip = idx + pix * K;
@@ -353,9 +368,13 @@ __global__ void __launch_bounds__(256)
           for (int c = 0; c < CMAX; ++c) f[c] = c < C ? __ldg(features + c * fs_c + id * fs_p) : 0.0f;
         }
 #pragma unroll
-        for (int c = 0; c < CMAX; ++c) {
-          A += g[c] * f[c];
-          if (c < C) atomicAdd(grad_features + c * fs_c + id * fs_p, g[c] * w);
+        for (int c = 0; c < CMAX; ++c) A += g[c] * f[c];
+        if (vec4 && gvec4) {
+          red_add_v4(grad_features + (int64_t)id * 4, g[0] * w, g[1 % CMAX] * w, g[2 % CMAX] * w, g[3 % CMAX] * w);
+        } else {
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c)
+            if (c < C) atomicAdd(grad_features + c * fs_c + id * fs_p, g[c] * w);
         }
       } else {
         for (int64_t c = 0; c < C; ++c) {
