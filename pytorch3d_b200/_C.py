@@ -30,7 +30,7 @@ PAIR_CAPACITY = 0
 # Without it (library built alone) they call the C ABI through ctypes; both run the same kernels of the same library.
 _EXT = None
 _EXT_TRIED = False
-USE_EXT = True  # tests switch it off to exercise the ctypes binding of the same entry points
+USE_EXT = not _lib.DEV_OVERRIDE  # tests switch it off to exercise the ctypes binding of the same entry points
 
 
 def _ext():

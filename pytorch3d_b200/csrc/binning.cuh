@@ -89,11 +89,29 @@ __device__ __forceinline__ void warp_count_rect(uint2 r, int n, int TY, int TX, 
 // Exclusive scan of `counts[0..n)` into `offsets[0..n]` by one CTA of 1024 threads, 8192 elements per sweep
 // (eight coalesced loads in flight per thread, then eight block-wide shuffle scans).  `counts` is overwritten
 // with the segment starts as well: it becomes the array of fill cursors.
-static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict__ counts, int* __restrict__ offsets, int n) {
+// `order` (optional, n entries): a permutation of the tiles -- long lists first, then short ones, empty tiles last,
+// raster order inside each class.  The fine pass runs one CTA per tile and the hardware starts CTAs in index order, so
+// its last wave then consists of tiles that finish at once instead of a few heavy ones that leave most SMs idle (a
+// blur-band tile of the north-star batch runs for ~120 us of a 920 us kernel).  Keeping the raster order inside a class
+// keeps neighbouring tiles -- which share most of their faces' records -- in flight together (an arbitrary order inside
+// the classes cost config 5 11 %).  Three classes: longer than the mean non-empty list, shorter, empty; the per-class
+// ranks of all tiles come from ONE block scan of a packed 3 x 21-bit counter.
+__device__ __forceinline__ unsigned long long order_key(int count, int mean) {
+  return count <= 0 ? (1ull << 42) : (count > mean ? 1ull : (1ull << 21));
+}
+
+static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict__ counts, int* __restrict__ offsets, int n,
+                                                                int* __restrict__ order) {
   __shared__ long long warp_sums[32];
   __shared__ long long carry_s;
+  __shared__ unsigned long long order_sums[32];
+  __shared__ unsigned long long order_total, order_carry;
+  __shared__ int nonempty_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) carry_s = 0;
+  if (tid == 0) {
+    carry_s = 0;
+    nonempty_s = 0;
+  }
   pdl_trigger();  // (see common.cuh: the fill kernel may become resident now)
   pdl_wait();     // the counters are complete
   __syncthreads();
@@ -118,6 +136,13 @@ static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict_
     long long total = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) total += v[j];
+    if (order != nullptr) {
+      int ne = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ne += v[j] > 0 ? 1 : 0;
+      ne = __reduce_add_sync(0xffffffffu, ne);
+      if (lane == 0 && ne > 0) atomicAdd(&nonempty_s, ne);
+    }
     long long inc = total;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -163,6 +188,73 @@ static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict_
     __syncthreads();
   }
   if (tid == 0) offsets[n] = (int)min(carry_s, (long long)INT_MAX);
+  if (order == nullptr) return;
+  __syncthreads();  // the offsets written above are visible to the whole CTA; the non-empty count is complete
+  const long long total_pairs = carry_s;
+  const int mean = (int)min(total_pairs / max(nonempty_s, 1), (long long)INT_MAX);
+  // pass 1: how many tiles per class (block reduction of the packed counters)
+  unsigned long long mine = 0;
+  for (int i = tid; i < n; i += 1024) mine += order_key(offsets[i + 1] - offsets[i], mean);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+  if (lane == 0) order_sums[wid] = mine;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 32; ++w) t += order_sums[w];
+    order_total = t;
+    order_carry = 0;
+  }
+  __syncthreads();
+  const unsigned long long total = order_total;
+  const unsigned long long mask21 = (1ull << 21) - 1;
+  const long long n_long = (long long)(total & mask21), n_short = (long long)((total >> 21) & mask21);
+  // pass 2: ranks inside the classes, in raster order: every thread owns 8 consecutive tiles per sweep
+  for (int base = 0; base < n; base += 8192) {
+    const int i0 = base + tid * 8;
+    unsigned long long k[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      k[j] = i0 + j < n ? order_key(offsets[i0 + j + 1] - offsets[i0 + j], mean) : 0ull;
+      tot += k[j];
+    }
+    unsigned long long inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (lane == 31) order_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned long long w = order_sums[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += t;
+      }
+      order_sums[lane] = w;
+    }
+    __syncthreads();
+    unsigned long long excl = order_carry + inc - tot + (wid > 0 ? order_sums[wid - 1] : 0ull);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (i0 + j < n) {
+        long long pos;
+        if (k[j] == 1ull)
+          pos = (long long)(excl & mask21);
+        else if (k[j] == (1ull << 21))
+          pos = n_long + (long long)((excl >> 21) & mask21);
+        else
+          pos = n_long + n_short + (long long)((excl >> 42) & mask21);
+        order[pos] = i0 + j;
+      }
+      excl += k[j];
+    }
+    __syncthreads();
+    if (tid == 0) order_carry += order_sums[31];
+    __syncthreads();
+  }
 }
 
 // Pass 3: scatter element ids into the tile segments (`cursor` starts at each segment's begin).  Same warp
@@ -278,12 +370,12 @@ static __global__ void __launch_bounds__(256)
 // rasterize_points.cu:128), which is what pins tie-breaking and makes the output deterministic.
 // "Normalised" bitonic network (every compare-exchange ascending), valid for any segment length:
 // partners beyond the end are treated as +inf and skipped.
-constexpr int SORT_THREADS = TILE_THREADS;
+// (all CTA-wide sorts below are templated on NT, the number of threads of the calling CTA)
 
 // One compare-exchange sweep of the bitonic network over keys[0..n) by the whole CTA.
-template <bool MIRROR>
+template <bool MIRROR, int NT>
 __device__ __forceinline__ void sort_sweep(int* keys, int n, int d) {
-  for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+  for (int i = threadIdx.x; i < n; i += NT) {
     const int j = MIRROR ? (i ^ (d - 1)) : (i ^ d);  // MIRROR: d is the block size k
     if (j > i && j < n) {
       const int a = keys[i], b = keys[j];
@@ -300,6 +392,7 @@ __device__ __forceinline__ void sort_sweep(int* keys, int n, int d) {
 // thread, bitonic network ("normalised": every compare-exchange ascending, each merge = a mirror step i ^ (k-1)
 // followed by half-cleaners i ^ d), partners closer than 32 by shuffle, the others through shared memory
 // (double-buffered: one barrier per step; at most 6 such steps).  Unused threads hold INT_MAX.
+template <int NT = TILE_THREADS>
 __device__ __forceinline__ int cta_sort256(int key, int n, int* buf) {
   const int i = threadIdx.x;
   int phase = 0;
@@ -310,9 +403,9 @@ __device__ __forceinline__ int cta_sort256(int key, int n, int* buf) {
       if (k <= 32) {
         other = __shfl_xor_sync(0xffffffffu, key, m);
       } else {
-        buf[phase * TILE_THREADS + i] = key;
+        buf[phase * NT + i] = key;
         __syncthreads();
-        other = buf[phase * TILE_THREADS + (i ^ m)];
+        other = buf[phase * NT + (i ^ m)];
         phase ^= 1;
       }
       key = (i & (k >> 1)) == 0 ? min(key, other) : max(key, other);
@@ -322,9 +415,9 @@ __device__ __forceinline__ int cta_sort256(int key, int n, int* buf) {
       if (d < 32) {
         other = __shfl_xor_sync(0xffffffffu, key, d);
       } else {
-        buf[phase * TILE_THREADS + i] = key;
+        buf[phase * NT + i] = key;
         __syncthreads();
-        other = buf[phase * TILE_THREADS + (i ^ d)];
+        other = buf[phase * NT + (i ^ d)];
         phase ^= 1;
       }
       key = (i & d) == 0 ? min(key, other) : max(key, other);
@@ -335,6 +428,7 @@ __device__ __forceinline__ int cta_sort256(int key, int n, int* buf) {
 
 // The same network on 64-bit keys (the point rasterizer sorts a tile's points by (depth, index)): partners closer than
 // 32 by two shuffles, the others through shared memory (`buf`: 2 * TILE_THREADS keys).
+template <int NT = TILE_THREADS>
 __device__ __forceinline__ unsigned long long cta_sort256_u64(unsigned long long key, int n, unsigned long long* buf) {
   const int i = threadIdx.x;
   int phase = 0;
@@ -348,9 +442,9 @@ __device__ __forceinline__ unsigned long long cta_sort256_u64(unsigned long long
       if (k <= 32) {
         other = __shfl_xor_sync(0xffffffffu, key, m);
       } else {
-        buf[phase * TILE_THREADS + i] = key;
+        buf[phase * NT + i] = key;
         __syncthreads();
-        other = buf[phase * TILE_THREADS + (i ^ m)];
+        other = buf[phase * NT + (i ^ m)];
         phase ^= 1;
       }
       B200R_CE64(other, (i & (k >> 1)) == 0);
@@ -360,9 +454,9 @@ __device__ __forceinline__ unsigned long long cta_sort256_u64(unsigned long long
       if (d < 32) {
         other = __shfl_xor_sync(0xffffffffu, key, d);
       } else {
-        buf[phase * TILE_THREADS + i] = key;
+        buf[phase * NT + i] = key;
         __syncthreads();
-        other = buf[phase * TILE_THREADS + (i ^ d)];
+        other = buf[phase * NT + (i ^ d)];
         phase ^= 1;
       }
       B200R_CE64(other, (i & d) == 0);
@@ -374,34 +468,35 @@ __device__ __forceinline__ unsigned long long cta_sort256_u64(unsigned long long
 
 // Longer lists: the same network swept by the whole CTA over the list in shared memory (when it fits the
 // kernel's dynamic shared memory, which is not in use yet) or in place in global memory.
+template <int NT = TILE_THREADS>
 __device__ __forceinline__ void cta_sort_segment(int* seg, int n, int* s_keys, int cap) {
   const bool in_smem = n <= cap;
   int* keys = in_smem ? s_keys : seg;
   if (in_smem)
-    for (int i = threadIdx.x; i < n; i += TILE_THREADS) s_keys[i] = seg[i];
+    for (int i = threadIdx.x; i < n; i += NT) s_keys[i] = seg[i];
   __syncthreads();
   for (int k = 2; (k >> 1) < n; k <<= 1) {
-    sort_sweep<true>(keys, n, k);
+    sort_sweep<true, NT>(keys, n, k);
     __syncthreads();
     for (int d = k >> 2; d > 0; d >>= 1) {
-      sort_sweep<false>(keys, n, d);
+      sort_sweep<false, NT>(keys, n, d);
       __syncthreads();
     }
   }
   if (in_smem)
-    for (int i = threadIdx.x; i < n; i += TILE_THREADS) seg[i] = s_keys[i];
+    for (int i = threadIdx.x; i < n; i += NT) seg[i] = s_keys[i];
   __syncthreads();
 }
 
 // A tile list of any length put in ascending order of 64-bit keys built by `make_key(element)`; the keys live in shared
 // memory (`keys`, room for n of them), the list itself is rewritten in that order.  Used by the mesh fine pass to walk a
 // tile's faces front to back (key = (nearest vertex depth, face)).
-template <class MakeKey>
+template <int NT, class MakeKey>
 __device__ __forceinline__ void cta_sort_segment_by_key(int* seg, int n, unsigned long long* keys, MakeKey make_key) {
-  for (int i = threadIdx.x; i < n; i += TILE_THREADS) keys[i] = make_key(seg[i]);
+  for (int i = threadIdx.x; i < n; i += NT) keys[i] = make_key(seg[i]);
   __syncthreads();
   for (int k = 2; (k >> 1) < n; k <<= 1) {
-    for (int i = threadIdx.x; i < n; i += TILE_THREADS) {  // mirror step
+    for (int i = threadIdx.x; i < n; i += NT) {  // mirror step
       const int j = i ^ (k - 1);
       if (j > i && j < n) {
         const unsigned long long a = keys[i], b = keys[j];
@@ -413,7 +508,7 @@ __device__ __forceinline__ void cta_sort_segment_by_key(int* seg, int n, unsigne
     }
     __syncthreads();
     for (int d = k >> 2; d > 0; d >>= 1) {
-      for (int i = threadIdx.x; i < n; i += TILE_THREADS) {
+      for (int i = threadIdx.x; i < n; i += NT) {
         const int j = i ^ d;
         if (j > i && j < n) {
           const unsigned long long a = keys[i], b = keys[j];
@@ -426,7 +521,7 @@ __device__ __forceinline__ void cta_sort_segment_by_key(int* seg, int n, unsigne
       __syncthreads();
     }
   }
-  for (int i = threadIdx.x; i < n; i += TILE_THREADS) seg[i] = (int)(unsigned)(keys[i] & 0xffffffffull);
+  for (int i = threadIdx.x; i < n; i += NT) seg[i] = (int)(unsigned)(keys[i] & 0xffffffffull);
   __syncthreads();
 }
 
@@ -434,6 +529,7 @@ __device__ __forceinline__ void cta_sort_segment_by_key(int* seg, int n, unsigne
 struct BinWorkspace {
   int* tile_count;  // [ntiles]   counts, then fill cursors (absolute positions)
   int* tile_offset; // [ntiles+1] exclusive offsets; [ntiles] = total pairs
+  int* tile_order;  // [ntiles]   tiles by decreasing list length (schedule of the fine pass)
   uint4* rect;      // [E] tile rectangle (x: tx0|tx1<<16, y: ty0|ty1<<16), z: owning mesh / cloud
   int* pairs;       // [capacity]
   int64_t capacity;
@@ -444,8 +540,8 @@ struct BinWorkspace {
 // element.  (A blur band of 16 pixels puts every sub-pixel face of a 10^6-face mesh into ~9.4 tiles: with the former
 // 8 pairs per element the last 12 % of the tiles overflowed and walked the whole mesh -- 64 ms instead of ~10.)
 // The buffer is scratch that only the used part of is ever touched.
-inline int64_t default_pair_capacity(int64_t E, int N, int H, int W) {
-  const int64_t tiles = (int64_t)div_up(H, TILE) * div_up(W, TILE);
+inline int64_t default_pair_capacity(int64_t E, int N, int H, int W, int tile_h = TILE, int tile_w = TILE) {
+  const int64_t tiles = (int64_t)div_up(H, tile_h) * div_up(W, tile_w);
   const int64_t exact = E * tiles;
   const int64_t heur = 32 * E + 64 * (int64_t)N * tiles;
   int64_t c = exact < heur ? exact : heur;
@@ -454,10 +550,11 @@ inline int64_t default_pair_capacity(int64_t E, int N, int H, int W) {
   return c;
 }
 
-inline BinWorkspace carve_workspace(void* base, int64_t E, int N, int H, int W, int64_t capacity) {
+inline BinWorkspace carve_workspace(void* base, int64_t E, int N, int H, int W, int64_t capacity, int tile_h = TILE,
+                                    int tile_w = TILE) {
   BinWorkspace ws;
-  const int64_t ntiles = (int64_t)N * div_up(H, TILE) * div_up(W, TILE);
-  if (capacity <= 0) capacity = default_pair_capacity(E, N, H, W);
+  const int64_t ntiles = (int64_t)N * div_up(H, tile_h) * div_up(W, tile_w);
+  if (capacity <= 0) capacity = default_pair_capacity(E, N, H, W, tile_h, tile_w);
   ws.capacity = capacity;
   size_t off = 0;
   char* p = static_cast<char*>(base);
@@ -465,6 +562,8 @@ inline BinWorkspace carve_workspace(void* base, int64_t E, int N, int H, int W, 
   off = align_up(off + sizeof(int) * (size_t)ntiles, 16);
   ws.tile_offset = reinterpret_cast<int*>(p + off);
   off = align_up(off + sizeof(int) * (size_t)(ntiles + 1), 16);
+  ws.tile_order = reinterpret_cast<int*>(p + off);
+  off = align_up(off + sizeof(int) * (size_t)ntiles, 16);
   ws.rect = reinterpret_cast<uint4*>(p + off);
   off = align_up(off + sizeof(uint4) * (size_t)(E > 0 ? E : 1), 16);
   ws.pairs = reinterpret_cast<int*>(p + off);

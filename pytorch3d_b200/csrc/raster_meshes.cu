@@ -22,7 +22,14 @@
 namespace b200r {
 
 constexpr int SETUP_FACES = 256;  // faces per CTA in the setup pass (one per thread)
-constexpr int CHUNK = 256;        // faces staged per round in the fine pass
+// Tile of the mesh FORWARD pass (binning + fine kernels): FTW x FTH pixels, one thread per pixel, warps own 8x4
+// footprints.  (The backward kernels and the point rasterizer keep TILE x TILE = 16 x 16.)
+#ifndef B200R_MESH_TILE_H
+#define B200R_MESH_TILE_H 16
+#endif
+constexpr int FTW = 16, FTH = B200R_MESH_TILE_H, FTHREADS = FTW * FTH;
+static_assert(FTH == 16 || FTH == 8, "16x16 or 16x8 tiles");
+constexpr int CHUNK = FTHREADS;   // faces staged per round in the fine pass (one per thread)
 constexpr int SMEMQ_MAX_K = 32;   // largest K served by the shared-memory queue kernel (mesh_fine_smemq_kernel)
 
 // ------------------------------------------------------------------------------------------------
@@ -90,8 +97,11 @@ __device__ __forceinline__ void exact_pixel_range(float vmin, float vmax, int S,
 // INDEXED (the fused entry point): the faces are given as (verts, faces); the kernel gathers the three vertices
 // of each face itself -- what `verts_packed[faces_packed]` does in the reference's wrapper
 // (rasterize_meshes.py:144-148) -- and also writes the gathered (F,3,3) array for the backward pass.
+#ifndef B200R_SETUP_CTAS
+#define B200R_SETUP_CTAS 1
+#endif
 template <bool INDEXED>
-__global__ void __launch_bounds__(SETUP_FACES)
+__global__ void __launch_bounds__(SETUP_FACES, B200R_SETUP_CTAS)
     mesh_setup_count_kernel(const float* __restrict__ face_verts, const float* __restrict__ verts, int64_t V,
                             const int64_t* __restrict__ faces, float* __restrict__ face_verts_out,
                             const int64_t* __restrict__ neighbor, int64_t F, const int64_t* __restrict__ first,
@@ -141,8 +151,8 @@ __global__ void __launch_bounds__(SETUP_FACES)
       exact_pixel_range(box.z, box.w, H, ry, iy_lo, iy_hi);
       if (ix_lo <= ix_hi && iy_lo <= iy_hi) {
         rng = make_int4(W - 1 - ix_hi, W - 1 - ix_lo, H - 1 - iy_hi, H - 1 - iy_lo);
-        r = make_uint2((uint32_t)(rng.x / TILE) | ((uint32_t)(rng.y / TILE) << 16),
-                       (uint32_t)(rng.z / TILE) | ((uint32_t)(rng.w / TILE) << 16));
+        r = make_uint2((uint32_t)(rng.x / FTW) | ((uint32_t)(rng.y / FTW) << 16),
+                       (uint32_t)(rng.z / FTH) | ((uint32_t)(rng.w / FTH) << 16));
       }
     }
     rect[fi] = make_uint4(r.x, r.y, (uint32_t)max(n, 0), 0u);
@@ -217,7 +227,7 @@ __device__ __forceinline__ bool key_less(float za, int ia, float zb, int ib) {
 // maximum is searched again (first slot with a strictly larger z wins).  Faces reach the queue in ascending
 // index order (sorted tile lists), so ties are resolved exactly as by the reference's naive kernel.
 // The keys (z, face) live in registers with compile-time indices only (predicated updates); the payload
-// (signed distance + barycentrics) of slot k lives in shared memory at pay[k * TILE_THREADS + thread], where
+// (signed distance + barycentrics) of slot k lives in shared memory at pay[k * FTHREADS + thread], where
 // a dynamic slot index costs nothing.
 template <int KMAX>
 struct TopK {
@@ -244,7 +254,7 @@ struct TopK {
       z[i] = w ? h.z : z[i];
       id[i] = w ? f : id[i];
     }
-    pay[slot * TILE_THREADS] = make_float4(h.dist, h.b0, h.b1, h.b2);
+    pay[slot * FTHREADS] = make_float4(h.dist, h.b0, h.b1, h.b2);
   }
   // Handle a face that covers the pixel (the `else` branch at :216-236).
   __device__ __forceinline__ void offer(const Hit& h, int f, int K, float4* pay) {
@@ -279,7 +289,7 @@ struct TopK {
     for (int i = KMAX - 1; i >= 0; --i)
       if (i < size && id[i] == neighbor) at = i;  // first match
     if (at < 0) return false;
-    if (fabsf(h.dist) < fabsf(pay[at * TILE_THREADS].x)) {
+    if (fabsf(h.dist) < fabsf(pay[at * FTHREADS].x)) {
       put(at, h, f, pay);
       if (h.z > max_z) {
         max_z = h.z;
@@ -340,7 +350,7 @@ struct RegQueue {
 };
 
 // Queue policy of the 8 < K <= 32 kernel: the same queue with its keys in dynamic shared memory, slot-major with
-// one column per thread (element k of this thread at [k * TILE_THREADS]) -- a dynamic slot index is free there, and
+// one column per thread (element k of this thread at [k * FTHREADS]) -- a dynamic slot index is free there, and
 // a 32-slot queue in registers would cost 64 registers plus 2 * KMAX predicated moves per insertion.  Only
 // (z, face) are kept (plus the signed distance when the clipped-face neighbour rule needs it); the barycentrics
 // of the K winners are recomputed in the epilogue with the same arithmetic, hence the same bits.
@@ -354,8 +364,8 @@ struct SmemQueue {
   __device__ __forceinline__ void init(unsigned char* base, int K_, int tid) {
     K = K_;
     qz = reinterpret_cast<float*>(base) + tid;
-    qi = reinterpret_cast<int*>(base) + K_ * TILE_THREADS + tid;
-    qd = NB ? reinterpret_cast<float*>(base) + 2 * K_ * TILE_THREADS + tid : nullptr;
+    qi = reinterpret_cast<int*>(base) + K_ * FTHREADS + tid;
+    qd = NB ? reinterpret_cast<float*>(base) + 2 * K_ * FTHREADS + tid : nullptr;
     reset();
   }
   __device__ __forceinline__ void reset() {
@@ -366,9 +376,9 @@ struct SmemQueue {
   __device__ __forceinline__ bool full() const { return size >= K; }
   __device__ __forceinline__ float max_z() const { return max_zv; }
   __device__ __forceinline__ void put(int slot, const Hit& h, int f) {
-    qz[slot * TILE_THREADS] = h.z;
-    qi[slot * TILE_THREADS] = f;
-    if (NB) qd[slot * TILE_THREADS] = h.dist;
+    qz[slot * FTHREADS] = h.z;
+    qi[slot * FTHREADS] = f;
+    if (NB) qd[slot * FTHREADS] = h.dist;
   }
   __device__ __forceinline__ void offer(const Hit& h, int f) {  // (:216-236)
     if (size < K) {
@@ -383,7 +393,7 @@ struct SmemQueue {
       put(max_idx, h, f);
       max_zv = h.z;
       for (int i = 0; i < K; ++i) {
-        const float v = qz[i * TILE_THREADS];
+        const float v = qz[i * FTHREADS];
         if (v > max_zv) {
           max_zv = v;
           max_idx = i;
@@ -397,12 +407,12 @@ struct SmemQueue {
   __device__ __forceinline__ bool offer_neighbor(const Hit& h, int f, int nb) {  // (:186-215)
     int at = -1;
     for (int i = 0; i < size; ++i)
-      if (qi[i * TILE_THREADS] == nb) {
+      if (qi[i * FTHREADS] == nb) {
         at = i;
         break;
       }
     if (at < 0) return false;
-    if (NB && fabsf(h.dist) < fabsf(qd[at * TILE_THREADS])) {
+    if (NB && fabsf(h.dist) < fabsf(qd[at * FTHREADS])) {
       put(at, h, f);
       if (h.z > max_zv) {
         max_zv = h.z;
@@ -414,16 +424,16 @@ struct SmemQueue {
   // BubbleSort on (z, idx) (:322): keys are unique -> an insertion sort over the thread's own column
   __device__ __forceinline__ void sort() {
     for (int i = 1; i < size; ++i) {
-      const float tz = qz[i * TILE_THREADS];
-      const int ti = qi[i * TILE_THREADS];
+      const float tz = qz[i * FTHREADS];
+      const int ti = qi[i * FTHREADS];
       int j = i - 1;
-      while (j >= 0 && key_less(tz, ti, qz[j * TILE_THREADS], qi[j * TILE_THREADS])) {
-        qz[(j + 1) * TILE_THREADS] = qz[j * TILE_THREADS];
-        qi[(j + 1) * TILE_THREADS] = qi[j * TILE_THREADS];
+      while (j >= 0 && key_less(tz, ti, qz[j * FTHREADS], qi[j * FTHREADS])) {
+        qz[(j + 1) * FTHREADS] = qz[j * FTHREADS];
+        qi[(j + 1) * FTHREADS] = qi[j * FTHREADS];
         --j;
       }
-      qz[(j + 1) * TILE_THREADS] = tz;
-      qi[(j + 1) * TILE_THREADS] = ti;
+      qz[(j + 1) * FTHREADS] = tz;
+      qi[(j + 1) * FTHREADS] = ti;
     }
   }
 };
@@ -467,6 +477,7 @@ struct FineParams {
   const int64_t* first;
   const int64_t* num;
   const int* tile_offset;
+  const int* tile_order;  // schedule: the CTA with linear index b takes tile tile_order[b] (nullptr: tile b)
   int* pairs;  // tile lists; each CTA puts its own segment in ascending face order before reading it
   int64_t capacity;
   int n0;  // first image of this launch (grid.z is limited to 65535 images)
@@ -485,6 +496,12 @@ __device__ __forceinline__ void thread_pixel(int tile_x, int tile_y, int& xo, in
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   xo = tile_x * TILE + (w & 1) * 8 + (lane & 7);
   yo = tile_y * TILE + (w >> 1) * 4 + (lane >> 3);
+}
+// ... of the forward pass's FTW x FTH tiles
+__device__ __forceinline__ void fthread_pixel(int tile_x, int tile_y, int& xo, int& yo) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  xo = tile_x * FTW + (w & 1) * 8 + (lane & 7);
+  yo = tile_y * FTH + (w >> 1) * 4 + (lane >> 3);
 }
 
 __device__ __forceinline__ float warp_min(float v) {
@@ -514,14 +531,14 @@ struct FineStage {
   float4 c[CHUNK];  // z0, z1, z2, neighbour     }
   union {
     float4 box[CHUNK];                          // blur > 0: blur-expanded boxes (pass A)
-    unsigned mask[CHUNK / 32][TILE_THREADS];    // blur = 0: per pixel (thread), one bit per staged face
-    int sort_buf[2 * TILE_THREADS];             // exchange buffers of cta_sort256 (before the chunk is staged)
-    unsigned long long sort_buf64[2 * TILE_THREADS];  // ... of cta_sort256_u64
+    unsigned mask[CHUNK / 32][FTHREADS];        // blur = 0: per pixel (thread), one bit per staged face
+    int sort_buf[2 * FTHREADS];                 // exchange buffers of cta_sort256 (before the chunk is staged)
+    unsigned long long sort_buf64[2 * FTHREADS];  // ... of cta_sort256_u64
   } u;
   unsigned rng[CHUNK];                          // blur = 0: tile-local pixel rectangle c_lo | c_hi<<8 | r_lo<<16 | r_hi<<24
-  float col[TILE], row[TILE];                   // NDC coordinates of the tile's 16 pixel columns / rows
+  float col[FTW], row[FTH];                     // NDC coordinates of the tile's pixel columns / rows
   int tie;                                      // see flag_tie()
-  unsigned char tie_lane[TILE_THREADS];         // ... and which pixels (threads) raised it
+  unsigned char tie_lane[FTHREADS];             // ... and which pixels (threads) raised it
 };
 
 __device__ __forceinline__ void flag_tie() {
@@ -594,33 +611,33 @@ __device__ __forceinline__ void store_pair_split(float4* runA, float4* runB, con
 template <int KMAX>
 __device__ __forceinline__ void write_empty_tile(const FineParams& p, int n, int tile_x, int tile_y) {
   const int tid = threadIdx.x;
-  const int x0 = tile_x * TILE, y0 = tile_y * TILE;
+  const int x0 = tile_x * FTW, y0 = tile_y * FTH;
   const int K = p.K;
-  if ((KMAX == 0 || K == KMAX) && (K % 4) == 0 && x0 + TILE <= p.W && y0 + TILE <= p.H) {
+  if ((KMAX == 0 || K == KMAX) && (K % 4) == 0 && x0 + FTW <= p.W && y0 + FTH <= p.H) {
     const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
     const int KK = KMAX > 0 ? KMAX : K;
-    const int SEG_I = TILE * KK / 2;  // longlong2 per row segment of pix_to_face
-    const int SEG_F = TILE * KK / 4;  // float4 per row segment of zbuf / dists (x3 for bary)
+    const int SEG_I = FTW * KK / 2;  // longlong2 per row segment of pix_to_face
+    const int SEG_F = FTW * KK / 4;  // float4 per row segment of zbuf / dists (x3 for bary)
 #pragma unroll
-    for (int e = tid; e < TILE * SEG_I; e += TILE_THREADS) {
+    for (int e = tid; e < FTH * SEG_I; e += FTHREADS) {
       const int64_t o = (((int64_t)n * p.H + y0 + e / SEG_I) * p.W + x0) * KK;
       out_store(reinterpret_cast<longlong2*>(p.pix_to_face + o) + e % SEG_I, make_longlong2(-1ll, -1ll));
     }
 #pragma unroll
-    for (int e = tid; e < TILE * SEG_F; e += TILE_THREADS) {
+    for (int e = tid; e < FTH * SEG_F; e += FTHREADS) {
       const int64_t o = (((int64_t)n * p.H + y0 + e / SEG_F) * p.W + x0) * KK;
       out_store(reinterpret_cast<float4*>(p.zbuf + o) + e % SEG_F, m1);
       out_store(reinterpret_cast<float4*>(p.dists + o) + e % SEG_F, m1);
     }
 #pragma unroll
-    for (int e = tid; e < TILE * SEG_F * 3; e += TILE_THREADS) {
+    for (int e = tid; e < FTH * SEG_F * 3; e += FTHREADS) {
       const int64_t o = (((int64_t)n * p.H + y0 + e / (SEG_F * 3)) * p.W + x0) * KK;
       out_store(reinterpret_cast<float4*>(p.bary + o * 3) + e % (SEG_F * 3), m1);
     }
     return;
   }
   int xo, yo;
-  thread_pixel(tile_x, tile_y, xo, yo);
+  fthread_pixel(tile_x, tile_y, xo, yo);
   if (xo >= p.W || yo >= p.H) return;
   const int64_t o = (((int64_t)n * p.H + yo) * p.W + xo) * K;
   for (int k = 0; k < K; ++k) {
@@ -727,20 +744,19 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
   };
   // (the long-list sorts use the kernel's shared memory as scratch: nothing lives in that part yet / any more)
   if (sorted_walk && !overflow && count > CHUNK)
-    cta_sort_segment(p.pairs + seg_begin, count, reinterpret_cast<int*>(&sh), scratch_ints);
+    cta_sort_segment<FTHREADS>(p.pairs + seg_begin, count, reinterpret_cast<int*>(&sh), scratch_ints);
   if (order == ORDER_DEPTH && count > CHUNK)
-    cta_sort_segment_by_key(p.pairs + seg_begin, count, reinterpret_cast<unsigned long long*>(&sh), depth_key);
+    cta_sort_segment_by_key<FTHREADS>(p.pairs + seg_begin, count, reinterpret_cast<unsigned long long*>(&sh), depth_key);
   // NDC coordinates of the tile's 16 pixel columns and rows (two IEEE divisions each): computed once per tile
   // by 32 threads, read by every thread after the barriers of the first chunk
-  if (tid < 2 * TILE) {
-    const int i = tid & (TILE - 1);
-    if (tid < TILE)
-      sh.col[i] = pix_to_ndc(p.W - 1 - (tile_x * TILE + i), p.W, p.rx);
+  if (tid < FTW + FTH) {
+    if (tid < FTW)
+      sh.col[tid] = pix_to_ndc(p.W - 1 - (tile_x * FTW + tid), p.W, p.rx);
     else
-      sh.row[i] = pix_to_ndc(p.H - 1 - (tile_y * TILE + i), p.H, p.ry);
+      sh.row[tid - FTW] = pix_to_ndc(p.H - 1 - (tile_y * FTH + tid - FTW), p.H, p.ry);
   }
   if (!sorted_walk) {
-    if (tid == 2 * TILE) sh.tie = 0;
+    if (tid == FTW + FTH) sh.tie = 0;
     sh.tie_lane[tid] = 0;
   }
 
@@ -751,12 +767,12 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
     int f = INT_MAX;
     if (tid < nc) f = overflow ? (int)(p.first[n] + base + tid) : p.pairs[seg_begin + base + tid];
     if (sort_staged) {
-      f = cta_sort256(f, nc, sh.u.sort_buf);
+      f = cta_sort256<FTHREADS>(f, nc, sh.u.sort_buf);
       if (nc > 32) __syncthreads();  // the exchange buffers alias the masks / boxes written next
     } else if (depth_staged) {
       unsigned long long key = ~0ull;
       if (tid < nc) key = depth_key(f);
-      key = cta_sort256_u64(key, nc, sh.u.sort_buf64);
+      key = cta_sort256_u64<FTHREADS>(key, nc, sh.u.sort_buf64);
       if (nc > 32) __syncthreads();
       f = (int)(unsigned)(key & 0xffffffffull);
     }
@@ -769,8 +785,8 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
       if (SCAN) {
         const int gx = __float_as_int(rd.x), gy = __float_as_int(rd.y), gz = __float_as_int(rd.z),
                   gw = __float_as_int(rd.w);
-        const int c_lo = max(gx - tile_x * TILE, 0), c_hi = min(gy - tile_x * TILE, TILE - 1);
-        const int r_lo = max(gz - tile_y * TILE, 0), r_hi = min(gw - tile_y * TILE, TILE - 1);
+        const int c_lo = max(gx - tile_x * FTW, 0), c_hi = min(gy - tile_x * FTW, FTW - 1);
+        const int r_lo = max(gz - tile_y * FTH, 0), r_hi = min(gw - tile_y * FTH, FTH - 1);
         sh.rng[tid] = (c_lo > c_hi || r_lo > r_hi) ? 1u  // empty: c_lo = 1 > c_hi = 0
                                                    : (unsigned)(c_lo | (c_hi << 8) | (r_lo << 16) | (r_hi << 24));
       } else {
@@ -796,7 +812,7 @@ __device__ __forceinline__ void fine_tile_body(const FineParams& p, FineStage& s
 #endif
       constexpr int SL = B200R_SCAN_LANES;
       const int dr = tid & (SL - 1);
-      for (int fslot = tid / SL; fslot < nc; fslot += TILE_THREADS / SL) {
+      for (int fslot = tid / SL; fslot < nc; fslot += FTHREADS / SL) {
         const unsigned rg = sh.rng[fslot];
         const int c_lo = rg & 255, c_hi = (rg >> 8) & 255, r_lo = (rg >> 16) & 255, r_hi = rg >> 24;
         if (c_lo > c_hi) continue;
@@ -959,10 +975,18 @@ struct TileWork {
 __device__ __forceinline__ TileWork tile_work(const FineParams& p) {
   pdl_wait();  // the tile lists (fill kernel) and, transitively, the face records are complete (see common.cuh)
   TileWork t;
-  t.tile_x = blockIdx.x;
-  t.tile_y = blockIdx.y;
-  t.n = p.n0 + blockIdx.z;
-  const int i = (t.n * p.TY + t.tile_y) * p.TX + t.tile_x;
+  int i = ((p.n0 + blockIdx.z) * p.TY + blockIdx.y) * p.TX + blockIdx.x;  // linear index of this CTA
+  if (p.tile_order != nullptr) {
+    i = p.tile_order[i];  // heavy tiles first, empty tiles last (see tile_scan_kernel)
+    t.tile_x = i % p.TX;
+    const int r = i / p.TX;
+    t.tile_y = r % p.TY;
+    t.n = r / p.TY;
+  } else {
+    t.tile_x = blockIdx.x;
+    t.tile_y = blockIdx.y;
+    t.n = p.n0 + blockIdx.z;
+  }
   // the tile's face list; tiles whose segment did not fit the pair buffer test every face of the mesh
   t.seg_begin = p.tile_offset[i];
   const int seg_end = p.tile_offset[i + 1];
@@ -992,7 +1016,7 @@ __device__ __forceinline__ int first_walk_order(const FineParams& p, const TileW
 }
 
 template <int KMAX, bool NB, bool SCAN>
-__global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FineParams p) {
+__global__ void __launch_bounds__(FTHREADS, 1024 / FTHREADS) mesh_fine_kernel(const FineParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FineStage& sh = *reinterpret_cast<FineStage*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -1003,9 +1027,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
     return;
   }
   int xo, yo;
-  thread_pixel(tile_x, tile_y, xo, yo);
+  fthread_pixel(tile_x, tile_y, xo, yo);
   const bool valid = xo < p.W && yo < p.H;
-  const int lc = xo - tile_x * TILE, lr = yo - tile_y * TILE;  // local column / row of my pixel
+  const int lc = xo - tile_x * FTW, lr = yo - tile_y * FTH;  // local column / row of my pixel
 
   RegQueue<KMAX> rq;
   rq.q.init();
@@ -1071,7 +1095,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
       for (int k0 = 0; k0 < KMAX; k0 += 4) {
         float d[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) d[u] = k0 + u >= q.size ? -1.0f : pay[slot[k0 + u] * TILE_THREADS].x;
+        for (int u = 0; u < 4; ++u) d[u] = k0 + u >= q.size ? -1.0f : pay[slot[k0 + u] * FTHREADS].x;
         piece[k0 / 4] = make_float4(d[0], d[1], d[2], d[3]);
       }
       store_pair_run<KMAX / 4>(reinterpret_cast<float4*>(p.dists + oa), piece, odd, vA, vB);
@@ -1083,7 +1107,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
         float4 w[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          w[u] = k0 + u >= q.size ? make_float4(-1.f, -1.f, -1.f, -1.f) : pay[slot[k0 + u] * TILE_THREADS];
+          w[u] = k0 + u >= q.size ? make_float4(-1.f, -1.f, -1.f, -1.f) : pay[slot[k0 + u] * FTHREADS];
         piece[3 * (k0 / 4) + 0] = make_float4(w[0].y, w[0].z, w[0].w, w[1].y);
         piece[3 * (k0 / 4) + 1] = make_float4(w[1].z, w[1].w, w[2].y, w[2].z);
         piece[3 * (k0 / 4) + 2] = make_float4(w[2].w, w[3].y, w[3].z, w[3].w);
@@ -1098,7 +1122,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) mesh_fine_kernel(const FinePa
     for (int k = 0; k < KMAX; ++k) {
       if (k < K) {
         const bool e = k >= q.size;
-        const float4 w = e ? make_float4(-1.f, -1.f, -1.f, -1.f) : pay[slot[k] * TILE_THREADS];
+        const float4 w = e ? make_float4(-1.f, -1.f, -1.f, -1.f) : pay[slot[k] * FTHREADS];
         p.pix_to_face[o + k] = e ? -1ll : (long long)q.id[k];
         p.zbuf[o + k] = e ? -1.0f : q.z[k];
         p.dists[o + k] = w.x;
@@ -1128,7 +1152,7 @@ __device__ __forceinline__ void recompute_hit(const FineParams& p, int fi, float
 }
 
 template <bool NB, bool SCAN>
-__global__ void __launch_bounds__(TILE_THREADS, 3) mesh_fine_smemq_kernel(const FineParams p) {
+__global__ void __launch_bounds__(FTHREADS, 768 / FTHREADS) mesh_fine_smemq_kernel(const FineParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FineStage& sh = *reinterpret_cast<FineStage*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -1139,9 +1163,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) mesh_fine_smemq_kernel(const 
     return;
   }
   int xo, yo;
-  thread_pixel(tile_x, tile_y, xo, yo);
+  fthread_pixel(tile_x, tile_y, xo, yo);
   const bool valid = xo < p.W && yo < p.H;
-  const int lc = xo - tile_x * TILE, lr = yo - tile_y * TILE;
+  const int lc = xo - tile_x * FTW, lr = yo - tile_y * FTH;
   const int K = p.K;
 
   SmemQueue<NB> q;
@@ -1181,7 +1205,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) mesh_fine_smemq_kernel(const 
         Hit h = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
         id[u] = -1;
         if (g + u < q.size) {
-          id[u] = q.qi[(g + u) * TILE_THREADS];
+          id[u] = q.qi[(g + u) * FTHREADS];
           recompute_hit(p, id[u], px, py, h);
         }
         z[u] = h.z;
@@ -1215,7 +1239,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) mesh_fine_smemq_kernel(const 
     Hit h = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
     long long id = -1;
     if (k < q.size) {
-      const int fi = q.qi[k * TILE_THREADS];
+      const int fi = q.qi[k * FTHREADS];
       recompute_hit(p, fi, px, py, h);
       id = fi;
     }
@@ -1237,14 +1261,14 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) mesh_fine_smemq_kernel(const 
 // Large-K path (32 < K <= 150): the same queue in thread-local arrays holding only (z, face, dist); the
 // barycentrics of the final winners are recomputed (same arithmetic, so identical values).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const FineParams p) {
+__global__ void __launch_bounds__(FTHREADS) mesh_fine_bigk_kernel(const FineParams p) {
   __shared__ FaceChunk s;
   const int tid = threadIdx.x, lane = tid & 31;
   const int t = blockIdx.x;
   const int n = t / (p.TY * p.TX);
   const int tile_y = (t / p.TX) % p.TY, tile_x = t % p.TX;
   int xo, yo;
-  thread_pixel(tile_x, tile_y, xo, yo);
+  fthread_pixel(tile_x, tile_y, xo, yo);
   const bool valid = xo < p.W && yo < p.H;
   const float px = pix_to_ndc(p.W - 1 - xo, p.W, p.rx);
   const float py = pix_to_ndc(p.H - 1 - yo, p.H, p.ry);
@@ -1260,7 +1284,8 @@ __global__ void __launch_bounds__(TILE_THREADS) mesh_fine_bigk_kernel(const Fine
 
   // ascending face order (see cta_sort256); the staging area doubles as the sort's scratch
   if (!overflow && count > 1)
-    cta_sort_segment(p.pairs + seg_begin, count, reinterpret_cast<int*>(&s), (int)(sizeof(FaceChunk) / sizeof(int)));
+    cta_sort_segment<FTHREADS>(p.pairs + seg_begin, count, reinterpret_cast<int*>(&s),
+                               (int)(sizeof(FaceChunk) / sizeof(int)));
 
   float qz[B200R_MAX_K], qd[B200R_MAX_K];
   int qi[B200R_MAX_K];
@@ -1657,7 +1682,8 @@ using namespace b200r;
 extern "C" size_t b200r_rasterize_meshes_workspace_bytes(int64_t F, int32_t N, int32_t H, int32_t W,
                                                          int64_t pair_capacity) {
   if (F < 0 || N < 0 || H < 0 || W < 0) return 0;
-  return carve_workspace(nullptr, F, N, H, W, pair_capacity).bytes + FACE_RECORD_BYTES * (size_t)(F > 0 ? F : 1);
+  return carve_workspace(nullptr, F, N, H, W, pair_capacity, FTH, FTW).bytes +
+         FACE_RECORD_BYTES * (size_t)(F > 0 ? F : 1);
 }
 
 static int forward_impl(const float* face_verts, const float* verts, int64_t V, const int64_t* faces,
@@ -1671,11 +1697,11 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
   if (F < 0 || N < 0 || H < 0 || W < 0 || K < 0) return fail(B200R_ERR_INVALID_ARGUMENT, "negative size");
   if (F > INT_MAX) return fail(B200R_ERR_INVALID_ARGUMENT, "more than 2^31-1 packed faces are not supported");
   if ((int64_t)N * H * W * K == 0) return B200R_OK;  // empty outputs (rasterize_meshes.cu:793-796)
-  const int TY = div_up(H, TILE), TX = div_up(W, TILE);
+  const int TY = div_up(H, FTH), TX = div_up(W, FTW);
   if (TY > 0xFFFE || TX > 0xFFFE) return fail(B200R_ERR_INVALID_ARGUMENT, "image too large");
   const int64_t ntiles = (int64_t)N * TY * TX;
   if (ntiles > INT_MAX) return fail(B200R_ERR_INVALID_ARGUMENT, "too many tiles");
-  BinWorkspace ws = carve_workspace(workspace, F, N, H, W, pair_capacity);
+  BinWorkspace ws = carve_workspace(workspace, F, N, H, W, pair_capacity, FTH, FTW);
   const size_t nrec = (size_t)(F > 0 ? F : 1);
   if (workspace == nullptr || workspace_bytes < ws.bytes + FACE_RECORD_BYTES * nrec)
     return fail(B200R_ERR_WORKSPACE, "workspace too small for rasterize_meshes_forward");
@@ -1701,8 +1727,16 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
     }
     B200R_LAUNCHED("mesh_setup_count_kernel");
   }
+  // Schedule of the fine pass (see tile_scan_kernel): worth the extra pass of the scan kernel and one more dependent load
+  // per CTA where tiles run long -- with a blur band (north-star batch + blur 1e-4: fine 918 -> 749 us, config 2: 137 ->
+  // 109 us); without one the north-star batch loses 6 us.  The packed class counters hold 2^21 tiles.
+#ifdef B200R_EXP_NOTILEORDER
+  int* const tile_order = nullptr;
+#else
+  int* const tile_order = (blur_radius > 0.0f && ntiles < (1 << 21)) ? ws.tile_order : nullptr;
+#endif
   B200R_CUDA_OK(launch_chained(tile_scan_kernel, dim3(1), dim3(1024), 0, stream, ws.tile_count, ws.tile_offset,
-                               (int)ntiles));
+                               (int)ntiles, tile_order));
   B200R_LAUNCHED("tile_scan_kernel");
   if (F > 0) {
     B200R_CUDA_OK(launch_chained(tile_fill_kernel<true>, dim3((unsigned)((F + 255) / 256)), dim3(256), 0, stream,
@@ -1719,6 +1753,7 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
   p.first = first;
   p.num = num;
   p.tile_offset = ws.tile_offset;
+  p.tile_order = tile_order;
   p.pairs = ws.pairs;
   p.capacity = ws.capacity;
   p.N = N; p.H = H; p.W = W; p.K = K; p.TY = TY; p.TX = TX;
@@ -1741,12 +1776,12 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
     p.smem_ints = (int)((SMEM) / sizeof(int));                                                           \
     for (p.n0 = 0; p.n0 < N; p.n0 += 65535) {                                                            \
       const dim3 grid3((unsigned)TX, (unsigned)TY, (unsigned)min(N - p.n0, 65535));                      \
-      B200R_CUDA_OK(launch_chained(KERNEL, grid3, dim3(TILE_THREADS), (SMEM), stream, p));               \
+      B200R_CUDA_OK(launch_chained(KERNEL, grid3, dim3(FTHREADS), (SMEM), stream, p));                   \
     }                                                                                                    \
   } while (0)
 #define B200R_FINE(KM)                                                                                    \
   do {                                                                                                   \
-    constexpr size_t smem_ = sizeof(FineStage) + sizeof(float4) * KM * TILE_THREADS;                     \
+    constexpr size_t smem_ = sizeof(FineStage) + sizeof(float4) * KM * FTHREADS;                         \
     if (neighbor && no_blur)                                                                             \
       B200R_FINE_LAUNCH((mesh_fine_kernel<KM, true, true>), smem_, smem_);                               \
     else if (neighbor)                                                                                   \
@@ -1766,10 +1801,10 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
     B200R_FINE(8);
   else if (K <= SMEMQ_MAX_K) {
     // queue keys in shared memory: (z, face) per slot, plus the signed distance for the neighbour rule
-    const size_t smem_max_nb = sizeof(FineStage) + (size_t)SMEMQ_MAX_K * TILE_THREADS * 12;
-    const size_t smem_max = sizeof(FineStage) + (size_t)SMEMQ_MAX_K * TILE_THREADS * 8;
-    const size_t smem_nb = sizeof(FineStage) + (size_t)K * TILE_THREADS * 12;
-    const size_t smem = sizeof(FineStage) + (size_t)K * TILE_THREADS * 8;
+    const size_t smem_max_nb = sizeof(FineStage) + (size_t)SMEMQ_MAX_K * FTHREADS * 12;
+    const size_t smem_max = sizeof(FineStage) + (size_t)SMEMQ_MAX_K * FTHREADS * 8;
+    const size_t smem_nb = sizeof(FineStage) + (size_t)K * FTHREADS * 12;
+    const size_t smem = sizeof(FineStage) + (size_t)K * FTHREADS * 8;
     if (neighbor && no_blur)
       B200R_FINE_LAUNCH((mesh_fine_smemq_kernel<true, true>), smem_max_nb, smem_nb);
     else if (neighbor)
@@ -1779,7 +1814,7 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
     else
       B200R_FINE_LAUNCH((mesh_fine_smemq_kernel<false, false>), smem_max, smem);
   } else
-    B200R_CUDA_OK(launch_chained(mesh_fine_bigk_kernel, dim3(grid), dim3(TILE_THREADS), 0, stream, p));
+    B200R_CUDA_OK(launch_chained(mesh_fine_bigk_kernel, dim3(grid), dim3(FTHREADS), 0, stream, p));
 #undef B200R_FINE
 #undef B200R_FINE_LAUNCH
   B200R_LAUNCHED("mesh_fine_kernel");

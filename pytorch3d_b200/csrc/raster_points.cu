@@ -662,7 +662,7 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
     B200R_LAUNCHED("points_setup_count_kernel");
   }
   B200R_CUDA_OK(launch_chained(tile_scan_kernel, dim3(1), dim3(1024), 0, stream, ws.tile_count, ws.tile_offset,
-                               (int)ntiles));
+                               (int)ntiles, (int*)nullptr));
   B200R_LAUNCHED("tile_scan_kernel");
   if (P > 0) {
     if (private_hist)

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "tools", "_variants")
 VARIANTS = {"oldwalk": ["-DB200R_EXP_OLDWALK"]}
 if len(sys.argv) > 2:  # python tools/variant_time.py build name=-DFLAG,-DFLAG2 ...
-    VARIANTS = {a.split("=")[0]: [f for f in a.split("=")[1].split(",") if f] for a in sys.argv[2:]}
+    VARIANTS = {a.split("=", 1)[0]: [f for f in a.split("=", 1)[1].split(",") if f] for a in sys.argv[2:]}
 
 if len(sys.argv) > 1 and sys.argv[1] == "build":
     from pytorch3d_b200 import build as b
