@@ -59,7 +59,7 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-NCU_SUMMARIES = ["ncu_r02_ns_metrics.json", "ncu_r01_ns_metrics.json"]  # newest first
+NCU_SUMMARIES = ["ncu_r02_final_ns_metrics.json", "ncu_r02_ns_metrics.json", "ncu_r01_ns_metrics.json"]  # newest first
 
 
 def ncu_traffic_bytes(kernel):

@@ -246,6 +246,15 @@ def test_mesh_backward(ops, dev, ref_cuda, persp, clip, blur):
         # arithmetics (FMA / no FMA) disagree by 100% on a few faces.  Require agreement on >= 98% of faces.
         ok = err <= 2e-3 * np.maximum(mag, 1e-3 * np.median(mag))
         assert ok.mean() >= 0.98
+        # second witness: the reference's own C++ CPU backward (rasterize_meshes_cpu.cpp:391-532), which applies the clip
+        # backward to the corrected barycentrics like this build (its CUDA kernel does not: DESIGN.md 5)
+        ref_cpu = oracle.load_reference(cuda=False)
+        if ref_cpu is not None:
+            rc = ref_cpu.rasterize_meshes_backward(fv, frag[0].cpu(), gz, gb, gd, True, True).numpy()
+            err_c = np.abs(mine - rc).reshape(nf, -1).max(1)
+            mag_c = np.abs(rc).reshape(nf, -1).max(1)
+            ok_c = err_c <= 2e-3 * np.maximum(mag_c, 1e-3 * np.median(mag_c))
+            assert ok_c.mean() >= 0.98
         return
     scale = mag.max()
     assert err.max() <= 2e-3 * scale
