@@ -109,7 +109,8 @@ int b200r_rasterize_meshes_backward(const float* face_verts, int64_t F, const in
  *  face_verts_out  float32 (F,3,3), written by the forward call: the gathered faces, to be passed to the
  *         backward call (what the reference's autograd saves)
  *  grad_verts      float32 (V,3), zeroed and accumulated by the backward call
- *  grad_face_verts_scratch float32 (F,3,3) scratch of the backward call
+ *  grad_face_verts_scratch unused since the backward kernel adds every contribution straight to the vertices of its
+ *         face (kept in the signature; may be NULL)
  * All other arguments as in b200r_rasterize_meshes_forward / _backward (same workspace size).
  */
 int b200r_rasterize_meshes_forward_indexed(const float* verts, int64_t V, const int64_t* faces, int64_t F,

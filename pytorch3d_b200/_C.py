@@ -287,12 +287,10 @@ def rasterize_meshes_backward_indexed(
     gz, gb, gd = grad_zbuf.contiguous(), grad_bary.contiguous(), grad_dists.contiguous()
     with torch.cuda.device(dev):
         grad_verts = torch.empty((V, 3), dtype=torch.float32, device=dev)
-        scratch = torch.empty((F, 3, 3), dtype=torch.float32, device=dev)
         _lib.check(lib.b200r_rasterize_meshes_backward_indexed(
             _ptr(fv), _ptr(faces), F, V, _ptr(p2f), _ptr(gz), _ptr(gb), _ptr(gd), N, H, W, K,
-            int(bool(perspective_correct)), int(bool(clip_barycentric_coords)), _ptr(grad_verts), _ptr(scratch),
+            int(bool(perspective_correct)), int(bool(clip_barycentric_coords)), _ptr(grad_verts), None,
             _stream_ptr(dev)))
-        scratch.record_stream(torch.cuda.current_stream(dev))
     return grad_verts
 
 

@@ -95,9 +95,18 @@ __device__ __forceinline__ void warp_count_rect(uint2 r, int n, int TY, int TX, 
 // blur-band tile of the north-star batch runs for ~120 us of a 920 us kernel).  Keeping the raster order inside a class
 // keeps neighbouring tiles -- which share most of their faces' records -- in flight together (an arbitrary order inside
 // the classes cost config 5 11 %).  Three classes: longer than the mean non-empty list, shorter, empty; the per-class
-// ranks of all tiles come from ONE block scan of a packed 3 x 21-bit counter.
+// ranks of all tiles come from ONE block scan of a packed counter (3 x 21 bits).
+#ifdef B200R_EXP_ORDER4  // (experiment: four classes -- > 2 x mean, > mean, shorter, empty -- of 16-bit counters)
+constexpr int ORDER_BITS = 16, ORDER_CLASSES = 4;
+__device__ __forceinline__ int order_class(int count, int mean) {
+  return count <= 0 ? 3 : (count > 2 * mean ? 0 : (count > mean ? 1 : 2));
+}
+#else
+constexpr int ORDER_BITS = 21, ORDER_CLASSES = 3;
+__device__ __forceinline__ int order_class(int count, int mean) { return count <= 0 ? 2 : (count > mean ? 0 : 1); }
+#endif
 __device__ __forceinline__ unsigned long long order_key(int count, int mean) {
-  return count <= 0 ? (1ull << 42) : (count > mean ? 1ull : (1ull << 21));
+  return 1ull << (ORDER_BITS * order_class(count, mean));
 }
 
 static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict__ counts, int* __restrict__ offsets, int n,
@@ -207,8 +216,16 @@ static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict_
   }
   __syncthreads();
   const unsigned long long total = order_total;
-  const unsigned long long mask21 = (1ull << 21) - 1;
-  const long long n_long = (long long)(total & mask21), n_short = (long long)((total >> 21) & mask21);
+  const unsigned long long fmask = (1ull << ORDER_BITS) - 1;
+  long long class_base[ORDER_CLASSES];  // tiles in the classes before this one
+  {
+    long long at = 0;
+#pragma unroll
+    for (int c = 0; c < ORDER_CLASSES; ++c) {
+      class_base[c] = at;
+      at += (long long)((total >> (ORDER_BITS * c)) & fmask);
+    }
+  }
   // pass 2: ranks inside the classes, in raster order: every thread owns 8 consecutive tiles per sweep
   for (int base = 0; base < n; base += 8192) {
     const int i0 = base + tid * 8;
@@ -240,13 +257,10 @@ static __global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict_
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (i0 + j < n) {
-        long long pos;
-        if (k[j] == 1ull)
-          pos = (long long)(excl & mask21);
-        else if (k[j] == (1ull << 21))
-          pos = n_long + (long long)((excl >> 21) & mask21);
-        else
-          pos = n_long + n_short + (long long)((excl >> 42) & mask21);
+        long long pos = 0;
+#pragma unroll
+        for (int c = 0; c < ORDER_CLASSES; ++c)
+          if (k[j] == (1ull << (ORDER_BITS * c))) pos = class_base[c] + (long long)((excl >> (ORDER_BITS * c)) & fmask);
         order[pos] = i0 + j;
       }
       excl += k[j];
