@@ -338,7 +338,11 @@ __global__ void __launch_bounds__(TILE_THREADS) points_fine_smem_kernel(const Po
   int size, max_idx;
   float max_z;
   const int seg_begin0 = p.tile_offset[tile], seg_end0 = p.tile_offset[tile + 1];
+#ifdef B200R_EXP_NOBYDEPTH  // (timing experiment: arrival-order walk with the literal queue first)
+  const bool by_depth_ok = false;
+#else
   const bool by_depth_ok = !((int64_t)seg_end0 > p.capacity || seg_end0 == INT_MAX) && seg_end0 - seg_begin0 <= PCHUNK;
+#endif
   for (int attempt = by_depth_ok ? 0 : 1;; attempt = 2) {  // 0: depth order, 1: arrival order, 2: index order (exact)
     const bool sort_list = attempt == 2;
     size = 0;
