@@ -177,7 +177,8 @@ def test_weighted_sum_cuda_forward_backward(built_lib, norm, N, K, H, W, C, P, p
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("P,N,size,K,C,r", [(3000, 2, (40, 56), 6, 4, 0.08), (20000, 3, (64, 64), 10, 3, 0.03),
-                                           (500, 1, (17, 33), 1, 1, 0.2)])
+                                           (500, 1, (17, 33), 1, 1, 0.2), (2000, 2, (32, 48), 5, 7, 0.1),
+                                           (1500, 1, (24, 24), 4, 12, 0.1)])
 def test_fused_point_rendering_equals_the_unfused_chain(built_lib, P, N, size, K, C, r):
     """`render_points_alpha(fragments, features, r)` = what PointsRenderer does with an AlphaCompositor
     (pytorch3d/renderer/points/renderer.py:63-73): weights = 1 - dists / r^2 (torch), idx.long(), two permutes and

@@ -455,3 +455,21 @@ def test_side_stream_and_noncontiguous(ops, dev):
         other = run_mesh(ops, dev, big.to(dev)[..., ::2], first, num, (32, 32), 1e-3, 4)
     s.synchronize()
     assert_frag_equal(base, other)
+
+
+def test_ranges_with_gaps(ops, dev):
+    """`first` / `num` that do not cover the packed array (unowned elements before, between and after the ranges):
+    unowned elements are never drawn; the private-histogram binning of the point path starts a chunk in a gap."""
+    pts, _, _, rad = rand_points(6000, 1, seed=11)
+    pfirst = torch.tensor([100, 2600], dtype=torch.int64)
+    pnum = torch.tensor([2000, 2500], dtype=torch.int64)
+    mine = ops.rasterize_points(pts.to(dev), pfirst.to(dev), pnum.to(dev), (40, 56), rad.to(dev), 6, 0, 0)
+    o = oracle.rasterize_points(pts.numpy(), pfirst.numpy(), pnum.numpy(), (40, 56), rad.numpy(), 6, **CUDA)
+    assert_frag_equal(mine, o, "points with gaps vs oracle")
+    fv, _, _ = rand_faces(3000, 1, seed=12)
+    ffirst = torch.tensor([50, 1500], dtype=torch.int64)
+    fnum = torch.tensor([1000, 1200], dtype=torch.int64)
+    for blur, K in ((0.0, 4), (1e-3, 6)):
+        mine = run_mesh(ops, dev, fv, ffirst, fnum, (48, 40), blur, K, 0, 0)
+        o = oracle.rasterize_meshes(fv.numpy(), ffirst.numpy(), fnum.numpy(), (48, 40), blur, K, **CUDA)
+        assert_frag_equal(mine, o, "meshes with gaps vs oracle")
