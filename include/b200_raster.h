@@ -367,6 +367,23 @@ int b200r_points_alpha_render_backward(const float* grad_images, const float* fe
                                        float* grad_features, float* grad_dists, void* stream);
 
 /*
+ * Test hooks of the reference's coarse stage (pytorch3d._C._rasterize_meshes_coarse / _rasterize_points_coarse,
+ * pytorch3d/csrc/ext.cpp:69-73; RasterizeMeshesCoarse rasterize_meshes.h:292-318, RasterizePointsCoarse
+ * rasterize_points.h:140-166): the dense table bin_faces / bin_points int32 (N, BH, BW, M), BH = 1 + (H-1)/bin_size,
+ * -1 padded, elements of a bin in arbitrary order (sort for a canonical form).  bin_counts int32 (N, BH, BW) scratch;
+ * *overflow (device int32) is set to 1 if a bin received more than M elements (the reference prints a warning,
+ * rasterize_coarse.cu:186-201).  Not used by the rasterizer itself, whose tile lists are compact and exact.
+ */
+int b200r_rasterize_meshes_coarse(const float* face_verts, int64_t F, const int64_t* mesh_to_face_first_idx,
+                                  const int64_t* num_faces_per_mesh, int32_t N, int32_t H, int32_t W,
+                                  float blur_radius, int32_t bin_size, int32_t max_faces_per_bin, int32_t* bin_faces,
+                                  int32_t* bin_counts, int32_t* overflow, void* stream);
+int b200r_rasterize_points_coarse(const float* points, int64_t P, const int64_t* cloud_to_packed_first_idx,
+                                  const int64_t* num_points_per_cloud, const float* radius, int32_t N, int32_t H,
+                                  int32_t W, int32_t bin_size, int32_t max_points_per_bin, int32_t* bin_points,
+                                  int32_t* bin_counts, int32_t* overflow, void* stream);
+
+/*
  * Programmatic dependent launch between the kernels of one call (setup -> scan -> fill -> fine; backward -> scatter):
  * the next kernel is made resident while its predecessor drains.  On by default; results never depend on it.
  */

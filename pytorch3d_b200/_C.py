@@ -592,3 +592,110 @@ def interp_face_attrs_backward(pix_to_face: torch.Tensor, barycentric_coords: to
         _lib.check(lib.b200r_interp_face_attrs_backward(_ptr(p2f), _ptr(bary), _ptr(attrs), _ptr(gp), P, F, D,
                                                         _ptr(grad_bary), _ptr(grad_attrs), _stream_ptr(dev)))
     return grad_bary, grad_attrs
+
+
+# ------------------------------------------------------------------------------------------------ test hooks
+# pytorch3d/csrc/ext.cpp:69-73: "These are only visible for testing; users should not call them directly".  Provided so
+# that the reference's own tests of these entry points can run against this build; none of them is on the product path.
+
+def _coarse(fn_name, elems, first, num, image_size, bin_size, max_per_bin, blur_radius=None, radius=None):
+    dev = _require_cuda(("elements", elems), ("first_idx", first), ("num_per_batch", num))
+    lib = _lib.load()
+    H, W = int(image_size[0]), int(image_size[1])
+    N, E = int(num.shape[0]), int(elems.shape[0])
+    bin_size, M = int(bin_size), int(max_per_bin)
+    if bin_size <= 0:
+        raise RuntimeError("bin_size must be positive for the coarse stage")
+    BH, BW = 1 + (H - 1) // bin_size, 1 + (W - 1) // bin_size
+    if BH >= 22 or BW >= 22:  # kMaxItemsPerBin (rasterize_coarse.cu:244-249)
+        raise RuntimeError("In RasterizeCoarseCuda got num_bins_y: %d, num_bins_x: %d, too many bins" % (BH, BW))
+    el = elems.contiguous()
+    f64, n64 = first.contiguous().to(torch.int64), num.contiguous().to(torch.int64)
+    with torch.cuda.device(dev):
+        bins = torch.empty((N, BH, BW, M), dtype=torch.int32, device=dev)
+        counts = torch.empty((N, BH, BW), dtype=torch.int32, device=dev)
+        overflow = torch.zeros((1,), dtype=torch.int32, device=dev)
+        if blur_radius is not None:
+            _lib.check(lib.b200r_rasterize_meshes_coarse(_ptr(el), E, _ptr(f64), _ptr(n64), N, H, W, float(blur_radius),
+                                                         bin_size, M, bins.data_ptr(), counts.data_ptr(),
+                                                         overflow.data_ptr(), _stream_ptr(dev)))
+        else:
+            rad = radius.contiguous()
+            _lib.check(lib.b200r_rasterize_points_coarse(_ptr(el), E, _ptr(f64), _ptr(n64), _ptr(rad), N, H, W, bin_size,
+                                                         M, bins.data_ptr(), counts.data_ptr(), overflow.data_ptr(),
+                                                         _stream_ptr(dev)))
+        if int(overflow.item()) != 0:
+            import warnings
+            warnings.warn("Bin size was too small in the coarse rasterization phase. This caused an overflow, meaning "
+                          "output may be incomplete. To solve, try increasing max_faces_per_bin / max_points_per_bin, "
+                          "decreasing bin_size, or setting bin_size to 0 to use the naive rasterization.")
+        # canonical form: ascending element index inside every bin, -1 padding last
+        big = torch.iinfo(torch.int32).max
+        bins = torch.where(bins < 0, torch.full_like(bins, big), bins).sort(dim=-1).values
+        bins = torch.where(bins == big, torch.full_like(bins, -1), bins)
+    return bins
+
+
+def _rasterize_meshes_coarse(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, image_size, blur_radius, bin_size,
+                             max_faces_per_bin):
+    """pytorch3d._C._rasterize_meshes_coarse (RasterizeMeshesCoarse, rasterize_meshes.h:292-318) -> bin_faces
+    (N, BH, BW, M) int32, -1 padded, ascending inside every bin."""
+    if face_verts.dim() != 3 or face_verts.shape[1] != 3 or face_verts.shape[2] != 3:
+        raise RuntimeError("face_verts must have dimensions (num_faces, 3, 3)")
+    return _coarse("meshes", face_verts, mesh_to_face_first_idx, num_faces_per_mesh, image_size, bin_size,
+                   max_faces_per_bin, blur_radius=blur_radius)
+
+
+def _rasterize_points_coarse(points, cloud_to_packed_first_idx, num_points_per_cloud, image_size, radius, bin_size,
+                             max_points_per_bin):
+    """pytorch3d._C._rasterize_points_coarse (RasterizePointsCoarse, rasterize_points.h:140-166)."""
+    if points.dim() != 2 or points.shape[1] != 3:
+        raise RuntimeError("points must have dimensions (num_points, 3)")
+    return _coarse("points", points, cloud_to_packed_first_idx, num_points_per_cloud, image_size, bin_size,
+                   max_points_per_bin, radius=radius)
+
+
+def _rasterize_meshes_naive(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, clipped_faces_neighbor_idx,
+                            image_size, blur_radius, faces_per_pixel, perspective_correct, clip_barycentric_coords,
+                            cull_backfaces):
+    """pytorch3d._C._rasterize_meshes_naive (RasterizeMeshesNaive, rasterize_meshes.h:109-145): this build has one path;
+    it returns the naive kernel's result for every bin_size."""
+    return rasterize_meshes(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, clipped_faces_neighbor_idx,
+                            image_size, blur_radius, faces_per_pixel, 0, 0, perspective_correct,
+                            clip_barycentric_coords, cull_backfaces)
+
+
+def _rasterize_points_naive(points, cloud_to_packed_first_idx, num_points_per_cloud, image_size, radius,
+                            points_per_pixel):
+    """pytorch3d._C._rasterize_points_naive (RasterizePointsNaive, rasterize_points.h:65-95)."""
+    return rasterize_points(points, cloud_to_packed_first_idx, num_points_per_cloud, image_size, radius,
+                            points_per_pixel, 0, 0)
+
+
+def _rasterize_meshes_fine(face_verts, bin_faces, clipped_faces_neighbor_idx, image_size, blur_radius, bin_size,
+                           faces_per_pixel, perspective_correct, clip_barycentric_coords, cull_backfaces):
+    """pytorch3d._C._rasterize_meshes_fine (RasterizeMeshesFine, rasterize_meshes.h:407-452).  The reference's fine stage
+    looks only at the faces listed in a pixel's bin; this build bins exactly by itself, so `bin_faces` only tells which
+    image a face belongs to (the index range of the faces listed for image n) -- for a table produced by the coarse stage
+    (every face in every bin it can touch) the result is the same."""
+    if bin_faces.dim() != 4:
+        raise RuntimeError("bin_faces must have 4 dimensions")
+    N = int(bin_faces.shape[0])
+    flat = bin_faces.reshape(N, -1).to(torch.int64)
+    big = torch.iinfo(torch.int64).max
+    lo = torch.where(flat >= 0, flat, torch.full_like(flat, big)).min(dim=1).values.tolist()  # (host sync: test hook)
+    hi = flat.max(dim=1).values.tolist()
+    first_l, num_l, at = [], [], 0
+    for a, b in zip(lo, hi):  # ascending ranges; an image without listed faces gets an empty range
+        if b >= 0:
+            first_l.append(int(a))
+            num_l.append(int(b - a + 1))
+            at = int(b) + 1
+        else:
+            first_l.append(at)
+            num_l.append(0)
+    first = torch.tensor(first_l, dtype=torch.int64, device=face_verts.device)
+    num = torch.tensor(num_l, dtype=torch.int64, device=face_verts.device)
+    return rasterize_meshes(face_verts, first, num, clipped_faces_neighbor_idx, image_size, blur_radius,
+                            faces_per_pixel, bin_size, int(bin_faces.shape[3]), perspective_correct,
+                            clip_barycentric_coords, cull_backfaces)

@@ -67,6 +67,10 @@ SIGNATURES = {
         ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b200r_interp_face_attrs_forward": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "b200r_interp_face_attrs_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "b200r_rasterize_meshes_coarse": (
+        ctypes.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "b200r_rasterize_points_coarse": (
+        ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b200r_peer_alloc": (ctypes.c_int, [_sz, ctypes.POINTER(_vp), ctypes.c_char_p]),
     "b200r_peer_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "b200r_peer_close": (ctypes.c_int, [_vp]),

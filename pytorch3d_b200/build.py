@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libb200raster.so")
 SOURCES = ["raster_meshes.cu", "raster_points.cu", "compositing.cu", "interp_face_attrs.cu", "peer_exchange.cu",
-           "host_api.cu"]
+           "coarse_hooks.cu", "host_api.cu"]
 HEADERS = ["raster_math.cuh", "bulk_copy.cuh", "binning.cuh", "common.cuh", os.path.join("..", "..", "include", "b200_raster.h")]
 
 

@@ -327,3 +327,49 @@ def test_both_bindings_of_the_c_abi_agree(ops, dev):
             assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b), key
         assert torch.allclose(ga, gb, rtol=1e-4, atol=1e-5), key
     assert torch.equal(results[True]["tagged"][0][0], results[True]["plain"][0][0])
+
+
+def test_reference_test_hooks(ops, dev, ref_cuda):
+    """The hooks the reference exports for its own tests (ext.cpp:69-73): coarse bin tables equal the reference's CUDA
+    coarse stage (both sorted inside a bin), the hand-written expectation of tests/test_rasterize_meshes.py:1096-1163,
+    and naive / fine give the result of the public op."""
+    # the reference's own coarse test scene (16 x 16, bin_size 8, M = 3)
+    verts = torch.tensor([[-0.5, 0.1, 0.1], [-0.3, 0.6, 0.1], [-0.1, 0.1, 0.1], [-0.3, -0.1, 0.4], [0.3, 0.5, 0.4],
+                          [0.75, -0.1, 0.4], [0.2, -0.3, 0.9], [0.3, -0.7, 0.9], [0.6, -0.3, 0.9], [-0.4, 0.0, -1.5],
+                          [0.6, 0.6, -1.5], [0.8, 0.0, -1.5]], device=dev)
+    faces = torch.tensor([[1, 0, 2], [4, 3, 5], [7, 6, 8], [10, 9, 11]], dtype=torch.int64, device=dev)
+    fv = verts[faces]
+    first, num = torch.zeros(1, dtype=torch.int64, device=dev), torch.tensor([4], dtype=torch.int64, device=dev)
+    want = torch.full((1, 2, 2, 3), -1, dtype=torch.int32, device=dev)
+    want[0, 1, 1, 0] = 1
+    want[0, 0, 1, 0:2] = torch.tensor([1, 2], dtype=torch.int32, device=dev)
+    want[0, 1, 0, 0:2] = torch.tensor([0, 1], dtype=torch.int32, device=dev)
+    want[0, 0, 0, 0] = 1
+    got = ops._rasterize_meshes_coarse(fv, first, num, (16, 16), 0.0, 8, 3)
+    assert torch.equal(got, want)
+    # random scenes against the reference's CUDA coarse stage
+    fv, first, num = rand_faces(3000, 2, seed=21)
+    fv, first, num = fv.to(dev), first.to(dev), num.to(dev)
+    pts, pfirst, pnum, rad = (t.to(dev) for t in rand_points(4000, 2, seed=22))
+    for size, bs, blur in (((64, 64), 16, 0.0), ((48, 80), 8, 1e-3), ((33, 47), 16, 1e-2)):
+        mine = ops._rasterize_meshes_coarse(fv, first, num, size, blur, bs, 3000)
+        minep = ops._rasterize_points_coarse(pts, pfirst, pnum, size, rad, bs, 4000)
+        assert mine.dtype == torch.int32 and mine.shape[1:3] == (1 + (size[0] - 1) // bs, 1 + (size[1] - 1) // bs)
+        if ref_cuda is not None:
+            big = torch.iinfo(torch.int32).max
+            for m_, r_ in ((mine, ref_cuda._rasterize_meshes_coarse(fv, first, num, size, blur, bs, 3000)),
+                           (minep, ref_cuda._rasterize_points_coarse(pts, pfirst, pnum, size, rad, bs, 4000))):
+                rs = torch.where(r_ < 0, torch.full_like(r_, big), r_).sort(dim=-1).values
+                rs = torch.where(rs == big, torch.full_like(rs, -1), rs)
+                assert torch.equal(m_, rs)
+        # naive and fine hooks = the public op
+        nb = _minus_one(fv.shape[0], dev)
+        pub = ops.rasterize_meshes(fv, first, num, nb, size, blur, 4, 0, 0, False, False, False)
+        nai = ops._rasterize_meshes_naive(fv, first, num, nb, size, blur, 4, False, False, False)
+        fin = ops._rasterize_meshes_fine(fv, mine, nb, size, blur, bs, 4, False, False, False)
+        for a, b, c in zip(pub, nai, fin):
+            assert torch.equal(a, b) and torch.equal(a, c)
+        pp = ops.rasterize_points(pts, pfirst, pnum, size, rad, 5, 0, 0)
+        pn = ops._rasterize_points_naive(pts, pfirst, pnum, size, rad, 5)
+        for a, b in zip(pp, pn):
+            assert torch.equal(a, b)
