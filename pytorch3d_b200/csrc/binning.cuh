@@ -325,7 +325,12 @@ static __global__ void __launch_bounds__(256)
 // atomics of a dense image (config 3: 1.4 M returning atomics on 8192 counters, 93 % of the fill kernel's stall samples)
 // become shared-memory atomics plus one global atomic per touched tile and CTA.  Elements of another image than the
 // chunk's first one (a chunk may straddle clouds) use the global counters directly.
-constexpr int BIN_CHUNK = 2048;          // elements per CTA (8 per thread)
+// (elements per CTA: config 3 -- 8 x 100 k points -- binning 42.0 us with 2048 = 391 CTAs, 36.7 / 37.4 us with 1024, 37.9 us
+// with 512, 48.1 us with 256: more CTAs than SMs x resident CTAs against more global atomics per element)
+#ifndef B200R_BIN_CHUNK
+#define B200R_BIN_CHUNK 1024
+#endif
+constexpr int BIN_CHUNK = B200R_BIN_CHUNK;  // elements per CTA (4 per thread)
 constexpr int BIN_MAX_TILES = 8192;      // tiles per image that the private histogram can hold (32 KB)
 
 // Fill: local histogram -> one returning global atomic per touched tile reserves the CTA's range in the tile's

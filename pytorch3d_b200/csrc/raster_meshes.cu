@@ -1584,8 +1584,16 @@ __device__ __forceinline__ void warp_scatter(const BackwardParams& p, int face, 
 #ifndef B200R_BWD_PF_CTAS
 #define B200R_BWD_PF_CTAS 3
 #endif
+// Resident CTAs per SM the register budget is set for.  (Measured on the north-star batch: 4 CTAs, 64 registers: 96.3 us;
+// 5 CTAs, 48 registers, 84 bytes of spills: 135.2 us; 6 CTAs, 40 registers: 163.9 us -- the kernel is bound by load/store
+// instructions through the L1 pipeline, not by the warps in flight: every spill is one more of them.  For the same reason
+// pulling the next wave's indices into L2 with prefetch instructions -- `prefetch.global.L2` of the tile one wave of CTAs
+// ahead -- costs 96.3 -> 100.4 us, and an L1 prefetch of the next slot's face 96.3 -> 100.4 us.)
+#ifndef B200R_BWD_CTAS
+#define B200R_BWD_CTAS 4
+#endif
 template <int GV, bool PF>
-__global__ void __launch_bounds__(TILE_THREADS, PF ? B200R_BWD_PF_CTAS : 4) mesh_backward_kernel(const BackwardParams p) {
+__global__ void __launch_bounds__(TILE_THREADS, PF ? B200R_BWD_PF_CTAS : B200R_BWD_CTAS) mesh_backward_kernel(const BackwardParams p) {
   const int lane = threadIdx.x & 31;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = p.n0 + blockIdx.z;  // grid = (TX, TY, images)
   int xo, yo;

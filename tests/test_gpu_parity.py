@@ -473,3 +473,25 @@ def test_ranges_with_gaps(ops, dev):
         mine = run_mesh(ops, dev, fv, ffirst, fnum, (48, 40), blur, K, 0, 0)
         o = oracle.rasterize_meshes(fv.numpy(), ffirst.numpy(), fnum.numpy(), (48, 40), blur, K, **CUDA)
         assert_frag_equal(mine, o, "meshes with gaps vs oracle")
+
+
+def test_setup_pass_many_blocks_ragged_unaligned(ops, dev):
+    """The setup pass on many blocks of 256 faces: a ragged last block whose word count is not a multiple of four (plain
+    loads after the bulk copy), blocks that straddle two meshes (owner lookup per block + per-face fallback), and the same
+    faces from a source that is only 4-byte aligned (no bulk copy at all)."""
+    F = 400003
+    fv, first, num = rand_faces(F, 2, seed=31, scale=0.01)
+    mine = run_mesh(ops, dev, fv, first, num, (24, 40), 0.0, 4)
+    o = oracle.rasterize_meshes(fv.numpy(), first.numpy(), num.numpy(), (24, 40), 0.0, 4, **CUDA)
+    assert_frag_equal(mine, o, "many setup blocks vs oracle")
+    assert int((mine[0] >= 0).sum()) > 100
+    shifted = torch.zeros(F * 9 + 1, device=dev)
+    shifted[1:] = fv.to(dev).reshape(-1)
+    view = shifted[1:].view(F, 3, 3)
+    assert view.data_ptr() % 16 != 0 and view.is_contiguous()
+    nb = torch.full((F,), -1, dtype=torch.int64, device=dev)
+    nb._b200_all_minus_one = True
+    for blur, K in ((0.0, 4), (1e-3, 2)):
+        a = ops.rasterize_meshes(fv.to(dev), first.to(dev), num.to(dev), nb, (24, 40), blur, K, 0, 0, False, False, False)
+        b = ops.rasterize_meshes(view, first.to(dev), num.to(dev), nb, (24, 40), blur, K, 0, 0, False, False, False)
+        assert_frag_equal(a, b, "unaligned source")

@@ -24,6 +24,15 @@ for (size, blur, K, neigh) in [((64, 64), 0.0, 8, nb), ((48, 80), 1e-3, 4, nb), 
     gz, gb, gd = torch.randn_like(out[1]), torch.randn_like(out[2]), torch.randn_like(out[3])
     _C.rasterize_meshes_backward(fv, out[0], gz, gb, gd, False, False)
     print("meshes", size, blur, K, int((out[0] >= 0).sum()), flush=True)
+# many blocks of 256 faces in the setup pass, the last one ragged, one straddling the two meshes
+mb = synthetic.torus_batch(2, 331, 331, seed=1)
+fvb = synthetic.face_verts_of(mb).to(dev)
+nbb = torch.full((fvb.shape[0],), -1, dtype=torch.int64, device=dev)
+nbb._b200_all_minus_one = True
+outb = _C.rasterize_meshes(fvb, mb.mesh_to_faces_packed_first_idx().to(dev), mb.num_faces_per_mesh().to(dev), nbb, (32, 32),
+                           0.0, 4, 0, 0, False, False, False)
+print("meshes (many blocks)", fvb.shape[0], int((outb[0] >= 0).sum()), flush=True)
+del mb, fvb, nbb, outb
 verts, faces = m.verts_packed().to(dev), m.faces_packed().to(dev)
 out = _C.rasterize_meshes_indexed(verts, faces, first, num, (64, 64), 0.0, 8, False, False, False)
 _C.rasterize_meshes_backward_indexed(out[4], faces, verts.shape[0], out[0], torch.randn_like(out[1]),
