@@ -53,9 +53,9 @@ __device__ __forceinline__ bool rect_empty(uint2 r) { return (r.x & 0xFFFFu) > (
 
 // Count one element per tile of its rectangle.  Called by ALL 32 lanes of a warp (lanes without work pass an
 // empty rectangle): consecutive elements of a packed mesh are neighbours on screen, so most lanes of a warp
-// target the same few tiles -- the lanes that agree are found with __match_any_sync and only one of them issues
-// the atomic, with the group's population.  This removes the serialisation of thousands of atomics on the hot
-// tiles of a silhouette.
+// target the same few tiles -- runs of consecutive lanes that agree are found with a shuffle and a vote (first version:
+// all agreeing lanes, with __match_any_sync) and only the first lane of a run issues the atomic, with the run's length.
+// This removes the serialisation of thousands of atomics on the hot tiles of a silhouette.
 // AGG = false (point clouds, whose packed order carries no spatial coherence): every element simply issues its own
 // atomics -- the warp-wide MATCH per round costs more than the 32 uncontended atomics it would merge (8 x 100k
 // uniform points: 49 -> see profiles/README.md).
@@ -77,8 +77,21 @@ __device__ __forceinline__ void warp_count_rect(uint2 r, int n, int TY, int TX, 
   for (int i = 0; i < rounds; ++i) {
     const bool act = i < ntile;
     const int t = act ? (n * TY + ty) * TX + tx : -1 - lane;  // inactive lanes get unique keys
+#ifndef B200R_EXP_AGG_MATCH
+    // runs of consecutive lanes with the same tile -- a shuffle and two votes -- instead of __match_any_sync, whose result
+    // the atomic waited for (17 % of the setup kernel's stall samples; north-star binning 44.7 -> 40.8 us, config 2 23.6 ->
+    // 21.5 us); equal tiles that are not adjacent in the warp cost one more atomic
+    const int tprev = __shfl_up_sync(0xffffffffu, t, 1);
+    const bool cont = act && lane > 0 && t == tprev;
+    const unsigned conts = __ballot_sync(0xffffffffu, cont);
+    if (act && !cont) {
+      const unsigned after = lane == 31 ? 0u : conts >> (lane + 1);
+      atomicAdd(tile_count + t, 1 + (__ffs((int)~after) - 1));
+    }
+#else
     const unsigned grp = __match_any_sync(0xffffffffu, t);
     if (act && lane == __ffs(grp) - 1) atomicAdd(tile_count + t, __popc(grp));
+#endif
     if (++tx > tx1) {
       tx = tx0;
       ++ty;
@@ -304,6 +317,22 @@ static __global__ void __launch_bounds__(256)
   for (int i = 0; i < rounds; ++i) {
     const bool act = i < ntile;
     const int t = act ? (n * TY + ty) * TX + tx : -1 - lane;
+#ifndef B200R_EXP_AGG_MATCH
+    const int tprev = __shfl_up_sync(0xffffffffu, t, 1);
+    const bool cont = act && lane > 0 && t == tprev;
+    const unsigned conts = __ballot_sync(0xffffffffu, cont);
+    const unsigned heads = __ballot_sync(0xffffffffu, act && !cont);
+    // my run's first lane: the highest head at or below me; its length: the continuation bits that follow it
+    const int leader = act ? 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane)))) : lane;
+    int base = 0;
+    if (act && !cont) {
+      const unsigned after = lane == 31 ? 0u : conts >> (lane + 1);
+      base = atomicAdd(cursor + t, 1 + (__ffs((int)~after) - 1));
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (act) {
+      const int pos = base + (lane - leader);
+#else
     const unsigned grp = __match_any_sync(0xffffffffu, t);
     const int leader = __ffs(grp) - 1;
     int base = 0;
@@ -311,6 +340,7 @@ static __global__ void __launch_bounds__(256)
     base = __shfl_sync(0xffffffffu, base, leader);
     if (act) {
       const int pos = base + __popc(grp & ((1u << lane) - 1u));
+#endif
       if (pos >= 0 && (int64_t)pos < capacity) pairs[pos] = (int)e;  // (pos < 0: saturated / wrapped cursor)
     }
     if (++tx > tx1) {
@@ -364,10 +394,24 @@ static __global__ void __launch_bounds__(256)
       for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(hist + ty * TX + tx, 1);
   }
   __syncthreads();
+#ifdef B200R_EXP_PFILL_SERIAL
   for (int t = tid; t < T; t += 256) {
     const int c = hist[t];
     if (c > 0) hist[t] = atomicAdd(cursor + n0 * T + t, c);  // start of this CTA's range in the tile's segment
   }
+#else
+  // (four returning atomics in flight per thread: each would wait for its own round trip to L2 otherwise)
+  for (int t0 = tid; t0 < T; t0 += 4 * 256) {
+    int c[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) c[u] = t0 + u * 256 < T ? hist[t0 + u * 256] : 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) b[u] = c[u] > 0 ? atomicAdd(cursor + n0 * T + t0 + u * 256, c[u]) : 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (c[u] > 0) hist[t0 + u * 256] = b[u];  // start of this CTA's range in the tile's segment
+  }
+#endif
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < BIN_CHUNK / 256; ++i) {

@@ -1408,6 +1408,8 @@ struct BackwardParams {
   const float* grad_dists;
   int N, H, W, K, TY, TX;
   int n0;  // first image of this launch
+  int g_vec;   // the gradient output is 8-byte aligned: 8-byte vector reductions
+  int64_t F;
   float rx, ry;
   int persp, clip;
   float* grad_face_verts;
@@ -1440,6 +1442,8 @@ __device__ __forceinline__ void backward_one(const BackwardParams& p, float px, 
                                              float gd, float gb0, float gb1, float gb2, bool persp, bool clip,
                                              float (&out)[9]) {
   const float* v = p.face_verts + fi * 9;
+  // (the face's 36 bytes as the three 16-byte pieces that contain them, shifted into place with selects -- 3 load
+  // instructions instead of 9 -- was measured and is no gain: north-star batch 94.2 vs 94.2 us, with blur 222 vs 215 us)
   const Face f = {__ldg(v + 0), __ldg(v + 1), __ldg(v + 2), __ldg(v + 3), __ldg(v + 4),
                   __ldg(v + 5), __ldg(v + 6), __ldg(v + 7), __ldg(v + 8)};
   const float den = bary_denominator(f);
@@ -1538,6 +1542,9 @@ __device__ __forceinline__ void backward_one(const BackwardParams& p, float px, 
 // the warp merges ALL lanes that carry the same face: one set of 9 atomics per distinct face of the warp
 // instead of per pixel (the kernel is sensitive to the number of atomics: merging only within pixel rows costs
 // +10 us on the north-star batch).
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {  // sm_90+ vector reduction, 8-byte aligned
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ void warp_scatter(const BackwardParams& p, int face, float (&g)[9], int lane) {
   // All lanes that hit the same face are found with one MATCH; each lane then adds up its successors in the
   // group by pointer jumping (after round r a lane holds the sum of 2^r consecutive group members), so the
@@ -1557,6 +1564,10 @@ __device__ __forceinline__ void warp_scatter(const BackwardParams& p, int face, 
     next = next >= 0 ? nn : -1;
   }
   if (face >= 0 && lane == __ffs((int)grp) - 1) {
+    // (the kernel is sensitive to the number of reduction instructions -- with a blur band, where most slots are hits, they
+    // bound it: north-star batch with blur 1e-4 280 -> 222 us, config 5 447 -> 344 us with 8-byte vector reductions where
+    // the target is 8-byte aligned: a face's 36 bytes / a vertex's 12 bytes start at a multiple of 4 whose parity is that
+    // of the index; 5 instead of 9 / 6 instead of 9 instructions, the same words and sums)
     if (p.faces != nullptr) {
       const int64_t* fc = p.faces + (int64_t)face * 3;
 #pragma unroll
@@ -1564,12 +1575,35 @@ __device__ __forceinline__ void warp_scatter(const BackwardParams& p, int face, 
         const int64_t vi = __ldg(fc + j);
         if (vi < 0 || vi >= p.V) continue;  // (out-of-range indices: an error in the reference; ignored like the gather)
         float* o = p.grad_verts + vi * 3;
+#ifndef B200R_EXP_BWD_SCALAR_RED
+        if (p.g_vec) {
+          const bool odd = (vi & 1) != 0;
+          const float s1 = odd ? g[3 * j] : g[3 * j + 2];
+          const float a = odd ? g[3 * j + 1] : g[3 * j], b = odd ? g[3 * j + 2] : g[3 * j + 1];
+          if (s1 != 0.0f) atomicAdd(o + (odd ? 0 : 2), s1);
+          if (a != 0.0f || b != 0.0f) red_add_v2(o + (odd ? 1 : 0), a, b);
+          continue;
+        }
+#endif
 #pragma unroll
         for (int c = 0; c < 3; ++c)
           if (g[3 * j + c] != 0.0f) atomicAdd(o + c, g[3 * j + c]);
       }
     } else {
       float* o = p.grad_face_verts + (int64_t)face * 9;
+#ifndef B200R_EXP_BWD_SCALAR_RED
+      // (16-byte reductions on the aligned groups inside the 36 bytes -- a four-way switch on face & 3, 3 or 4 reductions per
+      // face -- were measured against this: north-star batch with blur 225 vs 215 us, config 5 364 vs 354 us: the divergent
+      // switch costs more than the shorter sequences save)
+      if (p.g_vec) {
+        const int odd = face & 1;
+        atomicAdd(o + (odd ? 0 : 8), odd ? g[0] : g[8]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          red_add_v2(o + 2 * j + odd, odd ? g[2 * j + 1] : g[2 * j], odd ? g[2 * j + 2] : g[2 * j + 1]);
+        return;
+      }
+#endif
 #pragma unroll
       for (int i = 0; i < 9; ++i) atomicAdd(o + i, g[i]);
     }
@@ -1660,6 +1694,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PF ? B200R_BWD_PF_CTAS : B200R_B
         if (!PF || j >= 4) {
           gz = __ldg(p.grad_zbuf + i);
           gd = __ldg(p.grad_dists + i);
+          // (8 + 4 byte loads of the three barycentric gradients instead of three scalar ones: 94.2 -> 98.4 us, more spills)
           gb0 = __ldg(p.grad_bary + i * 3);
           gb1 = __ldg(p.grad_bary + i * 3 + 1);
           gb2 = __ldg(p.grad_bary + i * 3 + 2);
@@ -1890,6 +1925,8 @@ static int backward_impl(const float* face_verts, int64_t F, const int64_t* pix_
   p.face_verts = face_verts; p.pix_to_face = pix_to_face;
   p.grad_zbuf = grad_zbuf; p.grad_bary = grad_bary; p.grad_dists = grad_dists;
   p.N = N; p.H = H; p.W = W; p.K = K; p.TY = TY; p.TX = TX;
+  p.F = F;
+  p.g_vec = (reinterpret_cast<uintptr_t>(faces != nullptr ? grad_verts : grad_face_verts) & 7u) == 0 ? 1 : 0;
   p.rx = ndc_range(W, H); p.ry = ndc_range(H, W);
   p.persp = perspective_correct; p.clip = clip_barycentric_coords;
   p.grad_face_verts = grad_face_verts;

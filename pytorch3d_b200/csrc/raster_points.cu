@@ -69,6 +69,22 @@ __global__ void __launch_bounds__(256)
   const int tid = threadIdx.x, T = TY * TX;
   const int64_t p0 = (int64_t)blockIdx.x * BIN_CHUNK;
   pdl_trigger();
+  // all of the thread's points first (one round trip to DRAM for the chunk instead of one per point: the loads were 31 % of
+  // the kernel's stall samples when each iteration waited for its own)
+  float xs[BIN_CHUNK / 256], ys[BIN_CHUNK / 256], zs[BIN_CHUNK / 256], rs[BIN_CHUNK / 256];
+#ifndef B200R_EXP_PSETUP_NOHOIST
+#pragma unroll
+  for (int i = 0; i < BIN_CHUNK / 256; ++i) {
+    const int64_t pi = p0 + i * 256 + tid;
+    xs[i] = ys[i] = zs[i] = rs[i] = 0.0f;
+    if (pi < P) {
+      xs[i] = __ldg(points + pi * 3 + 0);
+      ys[i] = __ldg(points + pi * 3 + 1);
+      zs[i] = __ldg(points + pi * 3 + 2);
+      rs[i] = __ldg(radius + pi);
+    }
+  }
+#endif
   for (int t = tid; t < T; t += 256) hist[t] = 0;
   const int n0 = find_owner(first, num, N, p0);  // the chunk's image (uniform); -1: the chunk starts in a gap
   const int64_t lo0 = n0 >= 0 ? __ldg(first + n0) : 0, hi0 = n0 >= 0 ? lo0 + __ldg(num + n0) : 0;
@@ -77,8 +93,13 @@ __global__ void __launch_bounds__(256)
   for (int i = 0; i < BIN_CHUNK / 256; ++i) {
     const int64_t pi = p0 + i * 256 + tid;
     if (pi >= P) continue;
+#ifndef B200R_EXP_PSETUP_NOHOIST
+    const float x = xs[i], y = ys[i], z = zs[i], r = rs[i];
+#else
+    (void)xs; (void)ys; (void)zs; (void)rs;
     const float x = __ldg(points + pi * 3 + 0), y = __ldg(points + pi * 3 + 1), z = __ldg(points + pi * 3 + 2);
     const float r = __ldg(radius + pi);
+#endif
     const int n = (pi >= lo0 && pi < hi0) ? n0 : find_owner(first, num, N, pi);
     uint2 rc = make_uint2(RECT_EMPTY_X, 0u);
     if (n >= 0 && !(z < 0.0f)) rc = bbox_to_tile_rect(fsub(x, r), fadd(x, r), fsub(y, r), fadd(y, r), H, W, rx, ry);
@@ -540,7 +561,7 @@ template <bool STAGED>
 __global__ void __launch_bounds__(TILE_THREADS)
     points_backward_kernel(const float* __restrict__ points, const int32_t* __restrict__ idxs,
                            const float* __restrict__ grad_zbuf, const float* __restrict__ grad_dists, int n0, int H,
-                           int W, int K, float rx, float ry, float* __restrict__ grad_points) {
+                           int W, int K, float rx, float ry, float* __restrict__ grad_points, int g_vec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = n0 + blockIdx.z;
@@ -608,9 +629,22 @@ __global__ void __launch_bounds__(TILE_THREADS)
       next = next >= 0 ? nn : -1;
     }
     if (pi >= 0 && lane == __ffs((int)grp) - 1) {
-      atomicAdd(grad_points + (int64_t)pi * 3 + 0, gx);
-      atomicAdd(grad_points + (int64_t)pi * 3 + 1, gy);
-      atomicAdd(grad_points + (int64_t)pi * 3 + 2, gz);
+      float* o = grad_points + (int64_t)pi * 3;
+#ifndef B200R_EXP_BWD_SCALAR_RED
+      if (g_vec) {
+        // (a point's 12 bytes start at a multiple of 4 whose parity is that of the index: one 8-byte vector reduction and
+        // one scalar one instead of three -- fewer instructions through the L1 / MIO pipeline, the same sums)
+        const bool odd = (pi & 1) != 0;
+        atomicAdd(o + (odd ? 0 : 2), odd ? gx : gz);
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o + (odd ? 1 : 0)), "f"(odd ? gy : gx), "f"(odd ? gz : gy)
+                     : "memory");
+      } else
+#endif
+      {
+        atomicAdd(o + 0, gx);
+        atomicAdd(o + 1, gy);
+        atomicAdd(o + 2, gz);
+      }
     }
   }
 }
@@ -731,6 +765,7 @@ extern "C" int b200r_rasterize_points_backward(const float* points, int64_t P, c
   const bool staged = K <= SMEMQ_MAX_K && ((int64_t)W * K) % 4 == 0 && aligned16(idxs) && aligned16(grad_zbuf) &&
                       aligned16(grad_dists);
   const size_t smem = staged ? (size_t)K * QSTRIDE * 12 : 0;
+  const int g_vec = (reinterpret_cast<uintptr_t>(grad_points) & 7u) == 0 ? 1 : 0;
   if (staged) {
     static bool configured[64] = {};
     int dev_ = 0;
@@ -746,11 +781,11 @@ extern "C" int b200r_rasterize_points_backward(const float* points, int64_t P, c
     if (staged)
       points_backward_kernel<true><<<grid, TILE_THREADS, smem, stream>>>(points, idxs, grad_zbuf, grad_dists, n0, H,
                                                                        W, K, ndc_range(W, H), ndc_range(H, W),
-                                                                       grad_points);
+                                                                       grad_points, g_vec);
     else
       points_backward_kernel<false><<<grid, TILE_THREADS, 0, stream>>>(points, idxs, grad_zbuf, grad_dists, n0, H,
                                                                        W, K, ndc_range(W, H), ndc_range(H, W),
-                                                                       grad_points);
+                                                                       grad_points, g_vec);
   }
   B200R_LAUNCHED("points_backward_kernel");
   if (prof) {
