@@ -59,7 +59,7 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-NCU_SUMMARIES = ["ncu_r02_final_ns_metrics.json", "ncu_r02_ns_metrics.json", "ncu_r01_ns_metrics.json"]  # newest first
+NCU_SUMMARIES = ["ncu_r02_final2_ns_metrics.json", "ncu_r02_final_ns_metrics.json", "ncu_r02_ns_metrics.json", "ncu_r01_ns_metrics.json"]  # newest first
 
 
 def ncu_traffic_bytes(kernel):
@@ -353,7 +353,7 @@ def run_ours(args, rank, local_rank, world):
         if traffic_src else None,
         "algorithmic_bytes_per_launch": fine_bytes, "ms_per_launch": float(ph[1]), "peak_source": peak_src,
         "other_kernels": {
-            "binning(memset+setup+scan+fill; the list sort runs inside the fine kernel)": {"ms": float(ph[0])},
+            "binning(zero+setup+scan+fill; the list sort runs inside the fine kernel)": {"ms": float(ph[0])},
             "mesh_backward_kernel": bwd,
         },
         "step": {"algorithmic_bytes": fine_bytes + bwd_bytes,

@@ -51,6 +51,19 @@ __device__ __forceinline__ uint2 bbox_to_tile_rect(float xmin, float xmax, float
 
 __device__ __forceinline__ bool rect_empty(uint2 r) { return (r.x & 0xFFFFu) > (r.x >> 16); }
 
+// The tile counters are zeroed by a kernel the setup pass is chained to (programmatic dependent launch) instead of a memset
+// node: the setup pass's loads and arithmetic overlap it and wait only before their first atomic (binning -1.8 us).
+#ifndef B200R_EXP_MEMSET_NODE
+static __global__ void __launch_bounds__(256) zero_ints_kernel(int* __restrict__ p, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  pdl_trigger();
+  if (i + 4 <= n && (reinterpret_cast<uintptr_t>(p) & 15u) == 0)
+    *reinterpret_cast<int4*>(p + i) = make_int4(0, 0, 0, 0);
+  else
+    for (int64_t j = i; j < n && j < i + 4; ++j) p[j] = 0;
+}
+#endif
+
 // Count one element per tile of its rectangle.  Called by ALL 32 lanes of a warp (lanes without work pass an
 // empty rectangle): consecutive elements of a packed mesh are neighbours on screen, so most lanes of a warp
 // target the same few tiles -- runs of consecutive lanes that agree are found with a shuffle and a vote (first version:

@@ -166,6 +166,9 @@ __global__ void __launch_bounds__(SETUP_FACES, B200R_SETUP_CTAS)
                               : make_float4(__int_as_float(rng.x), __int_as_float(rng.y), __int_as_float(rng.z),
                                             __int_as_float(rng.w));
   }
+#ifndef B200R_EXP_MEMSET_NODE
+  pdl_wait();  // the counters are zeroed by the kernel this one is chained to (see zero_ints_kernel)
+#endif
   warp_count_rect(r, n, TY, TX, tile_count, tid & 31);  // all lanes participate
 }
 
@@ -1563,6 +1566,8 @@ __device__ __forceinline__ void warp_scatter(const BackwardParams& p, int face, 
     const int nn = __shfl_sync(0xffffffffu, next, src);
     next = next >= 0 ? nn : -1;
   }
+  // (runs of consecutive lanes with the same face -- a shuffle and a vote instead of MATCH, with a segmented shuffle-down
+  // reduction -- were measured against this: 96.3 vs 94.2 us, with blur 249 vs 215 us: faces span pixel rows)
   if (face >= 0 && lane == __ffs((int)grp) - 1) {
     // (the kernel is sensitive to the number of reduction instructions -- with a blur band, where most slots are hits, they
     // bound it: north-star batch with blur 1e-4 280 -> 222 us, config 5 447 -> 344 us with 8-byte vector reductions where
@@ -1759,19 +1764,29 @@ static int forward_impl(const float* face_verts, const float* verts, int64_t V, 
 
   const bool prof = profiling_enabled();
   if (prof) phase_timer().record(0, stream);
+#ifndef B200R_EXP_MEMSET_NODE
+  zero_ints_kernel<<<(unsigned)((ntiles + 1023) / 1024), 256, 0, stream>>>(ws.tile_count, ntiles);
+  B200R_LAUNCHED("zero_ints_kernel");
+#else
   B200R_CUDA_OK(cudaMemsetAsync(ws.tile_count, 0, sizeof(int) * (size_t)ntiles, stream));
+#endif
   if (F > 0) {
     const unsigned sgrid = (unsigned)((F + SETUP_FACES - 1) / SETUP_FACES);
+#ifndef B200R_EXP_MEMSET_NODE
+#define B200R_SETUP_LAUNCH(KERNEL, ...) B200R_CUDA_OK(launch_chained(KERNEL, dim3(sgrid), dim3(SETUP_FACES), 0, stream, __VA_ARGS__))
+#else
+#define B200R_SETUP_LAUNCH(KERNEL, ...) KERNEL<<<sgrid, SETUP_FACES, 0, stream>>>(__VA_ARGS__)
+#endif
     if (faces != nullptr) {
-      mesh_setup_count_kernel<true><<<sgrid, SETUP_FACES, 0, stream>>>(
-          nullptr, verts, V, faces, face_verts_out, neighbor, F, first, num, N, H, W, TY, TX, rx, ry, sqrt_blur,
-          cull_backfaces, ws.rect, ws.tile_count, rec);
+      B200R_SETUP_LAUNCH(mesh_setup_count_kernel<true>, (const float*)nullptr, verts, V, faces, face_verts_out, neighbor, F,
+                         first, num, N, H, W, TY, TX, rx, ry, sqrt_blur, cull_backfaces, ws.rect, ws.tile_count, rec);
       face_verts = face_verts_out;
     } else {
-      mesh_setup_count_kernel<false><<<sgrid, SETUP_FACES, 0, stream>>>(
-          face_verts, nullptr, 0, nullptr, nullptr, neighbor, F, first, num, N, H, W, TY, TX, rx, ry, sqrt_blur,
-          cull_backfaces, ws.rect, ws.tile_count, rec);
+      B200R_SETUP_LAUNCH(mesh_setup_count_kernel<false>, face_verts, (const float*)nullptr, (int64_t)0,
+                         (const int64_t*)nullptr, (float*)nullptr, neighbor, F, first, num, N, H, W, TY, TX, rx, ry,
+                         sqrt_blur, cull_backfaces, ws.rect, ws.tile_count, rec);
     }
+#undef B200R_SETUP_LAUNCH
     B200R_LAUNCHED("mesh_setup_count_kernel");
   }
   // Schedule of the fine pass (see tile_scan_kernel): worth the extra pass of the scan kernel and one more dependent load

@@ -55,6 +55,9 @@ __global__ void __launch_bounds__(SETUP_POINTS)
     rect[pi] = make_uint4(rc.x, rc.y, (uint32_t)max(n, 0), 0u);
     prec[pi] = make_float4(x, y, z, r);
   }
+#ifndef B200R_EXP_MEMSET_NODE
+  pdl_wait();  // the counters are zeroed by the kernel this one is chained to (see zero_ints_kernel)
+#endif
   warp_count_rect<false>(rc, n, TY, TX, tile_count, tid & 31);
 }
 
@@ -89,6 +92,9 @@ __global__ void __launch_bounds__(256)
   const int n0 = find_owner(first, num, N, p0);  // the chunk's image (uniform); -1: the chunk starts in a gap
   const int64_t lo0 = n0 >= 0 ? __ldg(first + n0) : 0, hi0 = n0 >= 0 ? lo0 + __ldg(num + n0) : 0;
   __syncthreads();
+#ifndef B200R_EXP_MEMSET_NODE
+  pdl_wait();  // the counters are zeroed by the kernel this one is chained to (see zero_ints_kernel)
+#endif
 #pragma unroll
   for (int i = 0; i < BIN_CHUNK / 256; ++i) {
     const int64_t pi = p0 + i * 256 + tid;
@@ -686,17 +692,25 @@ extern "C" int b200r_rasterize_points_forward(const float* points, int64_t P, co
 
   const bool prof = profiling_enabled();
   if (prof) phase_timer().record(0, stream);
+#ifndef B200R_EXP_MEMSET_NODE
+  zero_ints_kernel<<<(unsigned)((ntiles + 1023) / 1024), 256, 0, stream>>>(ws.tile_count, ntiles);
+  B200R_LAUNCHED("zero_ints_kernel");
+#else
   B200R_CUDA_OK(cudaMemsetAsync(ws.tile_count, 0, sizeof(int) * (size_t)ntiles, stream));
+#endif
   // (a private histogram over one image's tiles per CTA, if it fits; see binning.cuh)
   const bool private_hist = (int64_t)TY * TX <= BIN_MAX_TILES;
   const size_t hist_bytes = sizeof(int) * (size_t)TY * TX;
   if (P > 0) {
+    // (chained to the zeroing kernel: the loads and the per-point arithmetic overlap it)
     if (private_hist)
-      points_setup_count_private_kernel<<<(unsigned)((P + BIN_CHUNK - 1) / BIN_CHUNK), 256, hist_bytes, stream>>>(
-          points, radius, P, first, num, N, H, W, TY, TX, rx, ry, ws.rect, ws.tile_count, prec);
+      B200R_CUDA_OK(launch_chained(points_setup_count_private_kernel, dim3((unsigned)((P + BIN_CHUNK - 1) / BIN_CHUNK)),
+                                   dim3(256), hist_bytes, stream, points, radius, P, first, num, N, H, W, TY, TX, rx, ry,
+                                   ws.rect, ws.tile_count, prec));
     else
-      points_setup_count_kernel<<<(unsigned)((P + SETUP_POINTS - 1) / SETUP_POINTS), SETUP_POINTS, 0, stream>>>(
-          points, radius, P, first, num, N, H, W, TY, TX, rx, ry, ws.rect, ws.tile_count, prec);
+      B200R_CUDA_OK(launch_chained(points_setup_count_kernel, dim3((unsigned)((P + SETUP_POINTS - 1) / SETUP_POINTS)),
+                                   dim3(SETUP_POINTS), 0, stream, points, radius, P, first, num, N, H, W, TY, TX, rx, ry,
+                                   ws.rect, ws.tile_count, prec));
     B200R_LAUNCHED("points_setup_count_kernel");
   }
   B200R_CUDA_OK(launch_chained(tile_scan_kernel, dim3(1), dim3(1024), 0, stream, ws.tile_count, ws.tile_offset,
